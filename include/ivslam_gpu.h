@@ -1,0 +1,159 @@
+/* ivslam_gpu.h — C ABI of the B200-native (sm_100a) IV-SLAM stereo front-end.
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path.  The reference
+ * (ut-amrl/IV_SLAM) has no FFI layer; the seam is two C++ signatures inside libORB_SLAM2.so:
+ *
+ *   ORB_SLAM2::ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels,
+ *                                         int iniThFAST, int minThFAST, bool enableIntrospection)
+ *                                              introspective_ORB_SLAM/include/ORBextractor.h:57-58
+ *   void ORBextractor::operator()(cv::InputArray image, cv::InputArray mask,
+ *                                 std::vector<cv::KeyPoint>&, cv::OutputArray descriptors)
+ *                                              include/ORBextractor.h:65-67, src/ORBextractor.cc:1224-1296
+ *   void Frame::ComputeStereoMatches()         include/Frame.h:163,  src/Frame.cc:758-932
+ *
+ * Every entry point below names the reference interface it replaces.  shim/ holds the C++
+ * classes with the reference's exact signatures built on this ABI.
+ *
+ * Conventions: plain pointers and sizes only; int status return (0 = IVG_OK, negative = error,
+ * text from ivg_strerror); no exceptions cross the ABI; caller owns all host buffers.
+ * One handle owns one CUDA stream and its device workspace.  Different handles may be driven
+ * concurrently from different host threads (the reference runs the left and right extractor
+ * on two std::threads, src/Frame.cc:115-125); a single handle is not re-entrant.
+ * There is no CPU fallback: every call fails with IVG_ERR_CUDA / IVG_ERR_NO_DEVICE when no
+ * sm_100-class GPU is usable.
+ */
+#ifndef IVSLAM_GPU_H_
+#define IVSLAM_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVG_OK 0
+#define IVG_ERR_INVALID (-1)    /* bad argument / handle state                                  */
+#define IVG_ERR_GEOMETRY (-2)   /* image too small for the reference's cell grid (it would divide by zero) */
+#define IVG_ERR_CAPACITY (-3)   /* caller buffer or reserved batch too small                       */
+#define IVG_ERR_CUDA (-4)       /* CUDA runtime error (see ivg_last_cuda_error)                    */
+#define IVG_ERR_NO_DEVICE (-5)  /* no CUDA device / not an sm_100 part                             */
+#define IVG_ERR_STATE (-6)      /* call order: nothing extracted yet, batch sizes differ, ...      */
+
+typedef struct ivg_extractor ivg_extractor;
+
+/* Same memory layout as cv::KeyPoint (28 bytes) so a shim can memcpy into std::vector<cv::KeyPoint>. */
+typedef struct ivg_keypoint {
+  float x, y;        /* pt, level-0 pixels (level coordinates * scale factor of the octave)        */
+  float size;        /* (int)(31 * scale[octave])                     src/ORBextractor.cc:1138    */
+  float angle;       /* degrees in [0,360), cv::fastAtan2 of the intensity centroid  :78-105       */
+  float response;    /* FAST score (x introspection weight when a cost-map is given) :1058-1080    */
+  int32_t octave;
+  int32_t class_id;  /* always -1                                                                  */
+} ivg_keypoint;
+
+const char* ivg_strerror(int status);
+const char* ivg_last_cuda_error(void);
+/* Library/device probe: returns IVG_OK and fills name/sm (e.g. 100) when `device` is usable. */
+int ivg_device_info(int device, char* name, int name_cap, int* sm, int* sm_count);
+
+/* ---- ORBextractor::ORBextractor (include/ORBextractor.h:57-58, src/ORBextractor.cc:411-476) ---- */
+int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float scaleFactor, int nlevels,
+                         int iniThFAST, int minThFAST, int enableIntrospection);
+void ivg_extractor_destroy(ivg_extractor* h);
+
+/* Pre-allocates the device workspace for `max_batch` images of width x height (otherwise done lazily on the
+ * first call and whenever the shape or batch grows). */
+int ivg_extractor_reserve(ivg_extractor* h, int width, int height, int max_batch);
+
+/* GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:69-91).  which: 0 scale, 1 inverse scale, 2 sigma^2,
+ * 3 inverse sigma^2.  out must hold nlevels floats. */
+int ivg_get_levels(const ivg_extractor* h);
+float ivg_get_scale_factor(const ivg_extractor* h);
+int ivg_get_scale_table(const ivg_extractor* h, int which, float* out);
+int ivg_get_features_per_level(const ivg_extractor* h, int* out);
+int ivg_max_keypoints(const ivg_extractor* h);   /* capacity one image can produce = sum of features per level */
+
+/* ---- ORBextractor::operator() (src/ORBextractor.cc:1224-1296), one image ----
+ * image: 8-bit gray, `stride` bytes per row.  cost: the IV-SLAM cost-map ("mask" argument), same size, or NULL.
+ * The cost-map is used only when the handle was created with enableIntrospection (src/ORBextractor.cc:1231).
+ * Writes *n_out keypoints (reference order: level-major, cell row-major, nth_element permutation) and
+ * n_out x 32 descriptor bytes.  An empty image (NULL / zero size) returns IVG_OK with *n_out = 0 (:1227-1228).
+ * Synchronous: results are in the host buffers on return. */
+int ivg_extract(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride,
+                const uint8_t* cost, size_t cost_stride,
+                ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
+
+/* ---- the same for a batch of n equally-shaped images (frame-parallel data path) ----
+ * images: n frames, frame f starts at images + f*frame_bytes, rows `stride` bytes apart.  costs likewise or NULL.
+ * keypoints: n*cap records, descriptors: n*cap*32 bytes, n_out: n ints.  Frame f writes at f*cap.
+ * The three phases are exposed separately so a caller can keep inputs resident or overlap copies:
+ *   ivg_upload_batch  (async H2D on the handle's stream; host memory should be pinned for real overlap)
+ *   ivg_run_batch     (async, kernels only, inputs = whatever was uploaded / written through ivg_device_input)
+ *   ivg_download_batch(async D2H of keypoints/descriptors/counts into the given buffers)
+ *   ivg_sync          (blocks until the stream is idle; reports deferred CUDA errors)
+ * ivg_extract_batch = upload + run + download + sync. */
+int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
+                      size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes,
+                      ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
+int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
+                     size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes);
+int ivg_run_batch(ivg_extractor* h);
+int ivg_download_batch(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
+int ivg_sync(ivg_extractor* h);
+
+/* Device-side level-0 input plane of frame `index` (pitch in *pitch): lets a producer already on the GPU (e.g. the
+ * introspection CNN's cost-map) write inputs without a host round trip.  which: 0 image, 2 cost-map.
+ * Call ivg_set_batch first to declare how many frames / whether cost-maps are present. */
+int ivg_set_batch(ivg_extractor* h, int n, int width, int height, int with_cost);
+int ivg_device_input(ivg_extractor* h, int index, int which, void** dev_ptr, size_t* pitch);
+
+/* ---- mvImagePyramid / mvQualityImagePyramid (include/ORBextractor.h:91-92; read by src/Frame.cc:765,855,867,872) ----
+ * Copies one level of frame `index` of the last batch to host.  which: 0 image pyramid, 1 blurred level
+ * (the GaussianBlur working copy, src/ORBextractor.cc:1276-1277), 2 quality (cost-map) pyramid. */
+int ivg_level_size(const ivg_extractor* h, int level, int* width, int* height);
+int ivg_get_pyramid_level(ivg_extractor* h, int index, int level, int which, uint8_t* dst, size_t dst_stride);
+/* Per-level keypoints in level coordinates before scaling (x, y, response), for stage-wise parity tests. */
+int ivg_get_level_keypoints(ivg_extractor* h, int index, int level, float* x, float* y, float* response, int cap, int* n_out);
+
+/* ---- Frame::ComputeStereoMatches (src/Frame.cc:758-932) ----
+ * Uses what the two handles hold on the device after their last extract/run: both image pyramids, keypoints and
+ * descriptors (frame f of `left` is matched against frame f of `right`).  mbf = Camera.bf; maxD = the disparity
+ * limit the reference derives as mbf/mb (it reads mb before assigning it; nominal value = fx).
+ * uRight/depth: n*cap floats each, -1 where there is no match (mvuRight / mvDepth).  No surviving match = no-op
+ * (the reference indexes an empty vector there).  Runs on left's stream after right's work completes.
+ * ivg_stereo_match = frame 0 only, synchronous.  The batch form is async (ivg_sync(left) to wait) unless sync != 0. */
+int ivg_stereo_match(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD,
+                     float* uRight, float* depth, int cap);
+int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD,
+                           float* uRight, float* depth, int cap, int sync);
+/* Same matcher on caller-supplied keypoints/descriptors (what Frame holds in mvKeys/mvKeysRight/mDescriptors*),
+ * against the pyramids of frame 0 resident in the two handles.  Synchronous. */
+int ivg_stereo_match_keypoints(ivg_extractor* left, ivg_extractor* right,
+                               const ivg_keypoint* kL, int nL, const uint8_t* dL,
+                               const ivg_keypoint* kR, int nR, const uint8_t* dR,
+                               float mbf, float maxD, float* uRight, float* depth);
+/* Pyramid only (no detection) for frame 0: stages mvImagePyramid for ivg_stereo_match_keypoints. Synchronous. */
+int ivg_compute_pyramid(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride);
+
+/* ---- measurement helpers (bench.py) ---- */
+/* CUDA-event timer on the handle's stream: start records an event, stop records another, elapsed waits for it. */
+int ivg_timer_start(ivg_extractor* h);
+int ivg_timer_stop(ivg_extractor* h);
+int ivg_timer_elapsed_ms(ivg_extractor* h, float* ms);
+/* Kernel launches issued by this handle since creation (our own kernels only; copies are not counted). */
+long long ivg_launch_count(const ivg_extractor* h);
+/* Pinned host memory for real async copies. */
+int ivg_host_alloc(void** ptr, size_t bytes);
+int ivg_host_free(void* ptr);
+/* Writes `bytes` of device memory on the handle's stream (L2 flush between timed iterations). */
+int ivg_flush_l2(ivg_extractor* h, size_t bytes);
+/* When enabled (default off) run_batch wraps the kernel sequence of a batch in a CUDA graph that is re-used while
+ * shape/batch stay the same. */
+int ivg_set_graph_mode(ivg_extractor* h, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVSLAM_GPU_H_ */

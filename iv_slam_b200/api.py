@@ -1,0 +1,308 @@
+"""ctypes binding of the C ABI (include/ivslam_gpu.h) — the host-side mirror of the reference interface.
+
+`ORBextractor` has the reference class's constructor arguments and call semantics
+(introspective_ORB_SLAM/include/ORBextractor.h:54-128): `kps, desc = ex(image, mask)`, `GetLevels()`,
+`GetScaleFactors()`, `mvImagePyramid`-style level access.  `compute_stereo_matches(left, right, mbf, maxD)` is
+Frame::ComputeStereoMatches (src/Frame.cc:758-932) on what the two extractors hold on the device.
+
+There is NO CPU fallback: importing works anywhere (so the build check can import the package), but creating an
+extractor without the compiled library or without an sm_100 GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libivslam_gpu.so")
+
+IVG_OK = 0
+
+
+class IvgError(RuntimeError):
+    def __init__(self, status, what=""):
+        self.status = status
+        L = _lib
+        msg = L.ivg_strerror(status).decode() if L else str(status)
+        detail = L.ivg_last_cuda_error().decode() if (L and status == -4) else ""
+        super().__init__("%s: %s (%d) %s" % (what, msg, status, detail))
+
+
+_lib = None
+
+
+def lib():
+    """Loads iv_slam_b200/lib/libivslam_gpu.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libivslam_gpu.so is not built (%s); run `make -C iv_slam_b200/csrc` — there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32p, f32p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    sz = C.c_size_t
+    sig = {
+        "ivg_strerror": (C.c_char_p, [C.c_int]),
+        "ivg_last_cuda_error": (C.c_char_p, []),
+        "ivg_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, i32p, i32p]),
+        "ivg_extractor_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "ivg_extractor_destroy": (None, [vp]),
+        "ivg_extractor_reserve": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+        "ivg_get_levels": (C.c_int, [vp]),
+        "ivg_get_scale_factor": (C.c_float, [vp]),
+        "ivg_get_scale_table": (C.c_int, [vp, C.c_int, vp]),
+        "ivg_get_features_per_level": (C.c_int, [vp, vp]),
+        "ivg_max_keypoints": (C.c_int, [vp]),
+        "ivg_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, C.c_int, i32p]),
+        "ivg_extract_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz, vp, vp, C.c_int, vp]),
+        "ivg_upload_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
+        "ivg_run_batch": (C.c_int, [vp]),
+        "ivg_download_batch": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+        "ivg_sync": (C.c_int, [vp]),
+        "ivg_set_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "ivg_device_input": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(sz)]),
+        "ivg_level_size": (C.c_int, [vp, C.c_int, i32p, i32p]),
+        "ivg_get_pyramid_level": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, sz]),
+        "ivg_get_level_keypoints": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, i32p]),
+        "ivg_stereo_match": (C.c_int, [vp, vp, C.c_float, C.c_float, vp, vp, C.c_int]),
+        "ivg_stereo_match_batch": (C.c_int, [vp, vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int]),
+        "ivg_stereo_match_keypoints": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp]),
+        "ivg_compute_pyramid": (C.c_int, [vp, vp, C.c_int, C.c_int, sz]),
+        "ivg_timer_start": (C.c_int, [vp]),
+        "ivg_timer_stop": (C.c_int, [vp]),
+        "ivg_timer_elapsed_ms": (C.c_int, [vp, f32p]),
+        "ivg_launch_count": (C.c_longlong, [vp]),
+        "ivg_host_alloc": (C.c_int, [C.POINTER(vp), sz]),
+        "ivg_host_free": (C.c_int, [vp]),
+        "ivg_flush_l2": (C.c_int, [vp, sz]),
+        "ivg_set_graph_mode": (C.c_int, [vp, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    L._signatures = sig
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """Names declared in include/ivslam_gpu.h that the binding expects (used by the CPU-side ABI test)."""
+    lib()
+    return sorted(_lib._signatures)
+
+
+def _ck(status, what):
+    if status != IVG_OK:
+        raise IvgError(status, what)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_info(device=0):
+    name = C.create_string_buffer(128)
+    sm, cnt = C.c_int(), C.c_int()
+    rc = lib().ivg_device_info(device, name, 128, C.byref(sm), C.byref(cnt))
+    return rc, name.value.decode(), sm.value, cnt.value
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (for real async H2D/D2H in the batch path)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(shape)) * self.dtype.itemsize
+        self.ptr = C.c_void_p()
+        _ck(lib().ivg_host_alloc(C.byref(self.ptr), max(self.nbytes, 1)), "ivg_host_alloc")
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().ivg_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ORBextractor:
+    """ORB_SLAM2::ORBextractor on a B200. Same constructor arguments as the reference (ORBextractor.h:57-58)."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, enableIntrospection=False, device=0):
+        self._h = C.c_void_p()
+        _ck(lib().ivg_extractor_create(C.byref(self._h), device, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST,
+                                       int(bool(enableIntrospection))), "ivg_extractor_create")
+        self.nfeatures, self.nlevels, self.device = nfeatures, nlevels, device
+        self.cap = lib().ivg_max_keypoints(self._h)
+        self._batch = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ivg_extractor_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- getters of the reference class (ORBextractor.h:69-91)
+    def GetLevels(self):
+        return lib().ivg_get_levels(self._h)
+
+    def GetScaleFactor(self):
+        return lib().ivg_get_scale_factor(self._h)
+
+    def _table(self, which):
+        out = np.zeros(self.nlevels, np.float32)
+        _ck(lib().ivg_get_scale_table(self._h, which, _p(out)), "ivg_get_scale_table")
+        return out
+
+    def GetScaleFactors(self):
+        return self._table(0)
+
+    def GetInverseScaleFactors(self):
+        return self._table(1)
+
+    def GetScaleSigmaSquares(self):
+        return self._table(2)
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._table(3)
+
+    def features_per_level(self):
+        out = np.zeros(self.nlevels, np.int32)
+        _ck(lib().ivg_get_features_per_level(self._h, _p(out)), "ivg_get_features_per_level")
+        return out
+
+    def reserve(self, width, height, max_batch):
+        _ck(lib().ivg_extractor_reserve(self._h, width, height, max_batch), "ivg_extractor_reserve")
+
+    # -- operator()
+    def __call__(self, image, mask=None):
+        """(keypoints[KP_DTYPE], descriptors[N,32]) for one 8-bit gray image; mask = IV-SLAM cost-map or None."""
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1
+        if mask is not None:
+            assert mask.dtype == np.uint8 and mask.shape == image.shape and mask.strides[1] == 1
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int(0)
+        _ck(lib().ivg_extract(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], _p(mask),
+                              mask.strides[0] if mask is not None else 0, _p(kps), _p(desc), self.cap, C.byref(n)), "ivg_extract")
+        self._batch = 1
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, masks=None):
+        """images: [n,H,W] u8 C-contiguous. Returns (kps[n,cap], desc[n,cap,32], counts[n])."""
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.flags.c_contiguous
+        n, H, W = images.shape
+        if masks is not None:
+            assert masks.dtype == np.uint8 and masks.shape == images.shape and masks.flags.c_contiguous
+        kps = np.zeros((n, self.cap), KP_DTYPE)
+        desc = np.zeros((n, self.cap, 32), np.uint8)
+        cnt = np.zeros(n, np.int32)
+        _ck(lib().ivg_extract_batch(self._h, n, _p(images), W, H, W, H * W, _p(masks), W, H * W, _p(kps), _p(desc), self.cap, _p(cnt)),
+            "ivg_extract_batch")
+        self._batch = n
+        return kps, desc, cnt
+
+    # -- split phases (bench / pipelining)
+    def upload(self, images, masks=None):
+        n, H, W = images.shape
+        _ck(lib().ivg_upload_batch(self._h, n, _p(images), W, H, images.strides[1], images.strides[0], _p(masks),
+                                   masks.strides[1] if masks is not None else 0, masks.strides[0] if masks is not None else 0), "ivg_upload_batch")
+        self._batch = n
+
+    def run(self):
+        _ck(lib().ivg_run_batch(self._h), "ivg_run_batch")
+
+    def download(self, kps, desc, cnt):
+        _ck(lib().ivg_download_batch(self._h, _p(kps), _p(desc), kps.shape[-1], _p(cnt)), "ivg_download_batch")
+
+    def sync(self):
+        _ck(lib().ivg_sync(self._h), "ivg_sync")
+
+    def compute_pyramid(self, image):
+        _ck(lib().ivg_compute_pyramid(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0]), "ivg_compute_pyramid")
+        self._batch = 1
+
+    # -- mvImagePyramid / mvQualityImagePyramid access
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        _ck(lib().ivg_level_size(self._h, level, C.byref(w), C.byref(h)), "ivg_level_size")
+        return w.value, h.value
+
+    def level(self, level, which=0, index=0):
+        """which: 0 mvImagePyramid[level], 1 blurred working copy, 2 mvQualityImagePyramid[level], 3 FAST candidate map."""
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _ck(lib().ivg_get_pyramid_level(self._h, index, level, which, _p(out), out.strides[0]), "ivg_get_pyramid_level")
+        return out
+
+    def level_keypoints(self, level, index=0):
+        cap = self.cap
+        x, y, r = (np.zeros(cap, np.float32) for _ in range(3))
+        n = C.c_int(0)
+        _ck(lib().ivg_get_level_keypoints(self._h, index, level, _p(x), _p(y), _p(r), cap, C.byref(n)), "ivg_get_level_keypoints")
+        return x[:n.value].copy(), y[:n.value].copy(), r[:n.value].copy()
+
+    # -- measurement
+    def timer_start(self):
+        _ck(lib().ivg_timer_start(self._h), "ivg_timer_start")
+
+    def timer_stop(self):
+        _ck(lib().ivg_timer_stop(self._h), "ivg_timer_stop")
+
+    def timer_ms(self):
+        ms = C.c_float()
+        _ck(lib().ivg_timer_elapsed_ms(self._h, C.byref(ms)), "ivg_timer_elapsed_ms")
+        return ms.value
+
+    def launch_count(self):
+        return lib().ivg_launch_count(self._h)
+
+    def flush_l2(self, nbytes=256 << 20):
+        _ck(lib().ivg_flush_l2(self._h, nbytes), "ivg_flush_l2")
+
+
+def compute_stereo_matches(left, right, mbf, maxD):
+    """Frame::ComputeStereoMatches for frame 0 of the last extraction -> (mvuRight[N], mvDepth[N]) sized to left.cap."""
+    u = np.empty(left.cap, np.float32)
+    d = np.empty(left.cap, np.float32)
+    _ck(lib().ivg_stereo_match(left._h, right._h, mbf, maxD, _p(u), _p(d), left.cap), "ivg_stereo_match")
+    return u, d
+
+
+def compute_stereo_matches_batch(left, right, mbf, maxD, uRight=None, depth=None, sync=True):
+    n = left._batch
+    if uRight is None:
+        uRight = np.empty((n, left.cap), np.float32)
+        depth = np.empty((n, left.cap), np.float32)
+    _ck(lib().ivg_stereo_match_batch(left._h, right._h, mbf, maxD, _p(uRight), _p(depth), uRight.shape[-1], int(sync)), "ivg_stereo_match_batch")
+    return uRight, depth
+
+
+def compute_stereo_matches_keypoints(left, right, kL, dL, kR, dR, mbf, maxD):
+    """The matcher on caller-supplied keypoints/descriptors against the pyramids resident in the two extractors."""
+    kL = np.ascontiguousarray(kL, KP_DTYPE)
+    kR = np.ascontiguousarray(kR, KP_DTYPE)
+    dL = np.ascontiguousarray(dL, np.uint8)
+    dR = np.ascontiguousarray(dR, np.uint8)
+    u = np.full(kL.size, -1, np.float32)
+    d = np.full(kL.size, -1, np.float32)
+    _ck(lib().ivg_stereo_match_keypoints(left._h, right._h, _p(kL), kL.size, _p(dL), _p(kR), kR.size, _p(dR), mbf, maxD, _p(u), _p(d)),
+        "ivg_stereo_match_keypoints")
+    return u, d

@@ -1,0 +1,699 @@
+// ivslam_gpu.cu — host side of the C ABI declared in include/ivslam_gpu.h.
+//
+// Mirrors ORB_SLAM2::ORBextractor (introspective_ORB_SLAM/include/ORBextractor.h:54-128, src/ORBextractor.cc:411-476
+// constructor tables, :1224-1296 operator()) and the orchestration of the stereo Frame constructor
+// (src/Frame.cc:115-125 two extractions, :193 ComputeStereoMatches).  All pixel work is done by the sm_100a kernels
+// in k_*.cuh; this file builds the per-shape tables (level sizes, cell grids, x/y detect flags, bilinear taps — the
+// float/double mix of the reference is kept so the integer tables come out identical), owns the device workspace
+// and sequences the launches on the handle's stream.  No CPU fallback exists: without a usable GPU every entry
+// point returns an error.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ivslam_gpu.h"
+#include "common.cuh"
+#include "k_blur.cuh"
+#include "k_describe.cuh"
+#include "k_fast.cuh"
+#include "k_pyramid.cuh"
+#include "k_select.cuh"
+#include "k_stereo.cuh"
+
+using namespace ivg;
+
+namespace {
+
+thread_local std::string g_cuda_err;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      g_cuda_err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+      return IVG_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+const int8_t kPatternHost[1024] = {
+#include "../../include/ivslam_brief_pattern.inc"
+};
+
+inline int cv_round(float v) { return (int)lrintf(v); }
+inline int cv_round(double v) { return (int)lrint(v); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n && p) return IVG_OK;
+    release();
+    if (count == 0) count = 1;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+    return IVG_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct ivg_extractor {
+  int device = 0;
+  int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+  double scaleFactor = 1.2;
+  bool enableIntrospection = false;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> nPerLevel, umax;
+  int kpCap = 0;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evDone = nullptr, evT0 = nullptr, evT1 = nullptr;
+  cudaEvent_t waitFor = nullptr;        // an event of another handle that must complete before we overwrite our buffers
+  long long launches = 0;
+
+  // shape-dependent state
+  int W = 0, H = 0, maxBatch = 0;
+  bool shapeReady = false;
+  FrameSet fs{};                        // template (pointers filled, nImages/weighted set per run)
+  int curBatch = 0;
+  bool curWeighted = false;
+  bool haveResults = false, havePyramid = false;
+  std::vector<CellDev> cellsPlain, cellsWeighted;
+  DevBuf<uint8_t> pyr, blur, cand, qual, xflags, yflagsPlain, yflagsWeighted, outKp, outDesc;
+  DevBuf<CellDev> dCellsPlain, dCellsWeighted;
+  DevBuf<ResizeTap> rtab;
+  DevBuf<uint32_t> cellList, cellCost;
+  DevBuf<int2> cellCount;
+  DevBuf<uint2> workCell, workLevel, levelKp;
+  DevBuf<int> levelCount, outN, sad, nExt;
+  DevBuf<float> uRight, depth;
+  // stereo on caller-supplied keypoints
+  DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
+  bool graphMode = false;
+};
+
+namespace {
+
+int build_tables(ivg_extractor* h) {
+  // src/ORBextractor.cc:417-432 (float tables; the scaleFactor member is double, include/ORBextractor.h:108)
+  const int nl = h->nlevels;
+  h->scale.resize(nl); h->sigma2.resize(nl); h->invScale.resize(nl); h->invSigma2.resize(nl);
+  h->scale[0] = 1.f; h->sigma2[0] = 1.f;
+  for (int i = 1; i < nl; ++i) { h->scale[i] = (float)(h->scale[i - 1] * h->scaleFactor); h->sigma2[i] = h->scale[i] * h->scale[i]; }
+  for (int i = 0; i < nl; ++i) { h->invScale[i] = 1.f / h->scale[i]; h->invSigma2[i] = 1.f / h->sigma2[i]; }
+  // :437-452
+  h->nPerLevel.resize(nl);
+  float factor = (float)(1.0f / h->scaleFactor);
+  float nDesired = h->nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; ++l) { h->nPerLevel[l] = cv_round(nDesired); sum += h->nPerLevel[l]; nDesired *= factor; }
+  h->nPerLevel[nl - 1] = std::max(h->nfeatures - sum, 0);
+  h->kpCap = 0;
+  for (int l = 0; l < nl; ++l) h->kpCap += h->nPerLevel[l];
+  // :458-475
+  h->umax.assign(HALF_PATCH + 1, 0);
+  int vmax = (int)std::floor(HALF_PATCH * std::sqrt(2.f) / 2 + 1);
+  int vmin = (int)std::ceil(HALF_PATCH * std::sqrt(2.f) / 2);
+  const double hp2 = HALF_PATCH * HALF_PATCH;
+  for (int v = 0; v <= vmax; ++v) h->umax[v] = cv_round(std::sqrt(hp2 - v * v));
+  for (int v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+    while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+    h->umax[v] = v0; ++v0;
+  }
+  return IVG_OK;
+}
+
+void make_taps(int S, int D, std::vector<ResizeTap>& out) {
+  const double inv_scale = (double)D / S;
+  const double scale = 1.0 / inv_scale;
+  for (int d = 0; d < D; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(f);
+    f -= s;
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= S - 1) { f = 0.f; s = S - 1; }
+    ResizeTap t;
+    t.s0 = (uint16_t)s; t.s1 = (uint16_t)std::min(s + 1, S - 1);
+    t.c0 = (int16_t)cv_round((1.f - f) * 2048.f); t.c1 = (int16_t)cv_round(f * 2048.f);
+    out.push_back(t);
+  }
+}
+
+// Per-shape geometry: level sizes (src/ORBextractor.cc:1302-1303), cell grids (:884-907), detect flags, tap tables.
+int build_shape(ivg_extractor* h, int W, int H, int batch) {
+  const int nl = h->nlevels;
+  if (W > 4095 || H > 4095) return IVG_ERR_INVALID;     // 12-bit packed coordinates
+  FrameSet fs{};
+  fs.nlevels = nl; fs.iniTh = std::min(std::max(h->iniTh, 0), 255); fs.minTh = std::min(std::max(h->minTh, 0), 255);
+  fs.scoreTh = std::min(fs.iniTh, fs.minTh);
+  std::vector<uint8_t> xf, yfp, yfw;
+  std::vector<ResizeTap> taps;
+  h->cellsPlain.clear(); h->cellsWeighted.clear();
+  size_t planeOff = 0;
+  unsigned listOff = 0;
+  int kpOff = 0, ftBase = 0, btBase = 0;
+  const float imageRatio = (float)W / H;
+  for (int l = 0; l < nl; ++l) {
+    LevelDev& L = fs.lv[l];
+    const float sc = h->invScale[l];
+    L.w = cv_round((float)W * sc); L.h = cv_round((float)H * sc);
+    L.pitch = (int)align_up(L.w, 64);
+    L.planeOff = (unsigned)planeOff;
+    planeOff += align_up((size_t)L.pitch * L.h, 256);
+    L.scale = h->scale[l]; L.invScale = h->invScale[l];
+    L.sizeField = (float)(int)(PATCH * h->scale[l]);
+    L.nDesired = h->nPerLevel[l];
+    L.kpOff = kpOff; kpOff += L.nDesired;
+    // grid
+    L.cols = (int)std::sqrt((float)L.nDesired / (5 * imageRatio));
+    L.rows = (int)(imageRatio * L.cols);
+    L.maxBX = L.w - EDGE; L.maxBY = L.h - EDGE;
+    const int Wd = L.maxBX - EDGE, Hd = L.maxBY - EDGE;
+    if (L.cols < 1 || L.rows < 1 || Wd < 1 || Hd < 1) return IVG_ERR_GEOMETRY;
+    L.cellW = (int)std::ceil((float)Wd / L.cols);
+    L.cellH = (int)std::ceil((float)Hd / L.rows);
+    L.nCells = L.rows * L.cols;
+    if ((L.cols - 1) * L.cellW > Wd || (L.rows - 1) * L.cellH > Hd) return IVG_ERR_GEOMETRY;
+    if (L.nCells > SEL_MAX_CELLS) return IVG_ERR_CAPACITY;
+    L.nfeaturesCell = (int)std::ceil((float)L.nDesired / L.nCells);
+    L.cellBase = (int)h->cellsPlain.size();
+    L.ftX = (L.maxBX - FT_ORG + FT_W - 1) / FT_W; L.ftY = (L.maxBY - FT_ORG + FT_H - 1) / FT_H;
+    L.ftBase = ftBase; ftBase += L.ftX * L.ftY;
+    L.btX = (L.w + BT_W - 1) / BT_W; L.btY = (L.h + BT_H - 1) / BT_H;
+    L.btBase = btBase; btBase += L.btX * L.btY;
+    // flags
+    L.flagX = (int)xf.size(); L.flagY = (int)yfp.size();
+    xf.resize(xf.size() + L.w, 0); yfp.resize(yfp.size() + L.h, 0); yfw.resize(yfw.size() + L.h, 0);
+    uint8_t* fx = &xf[L.flagX]; uint8_t* fyp = &yfp[L.flagY]; uint8_t* fyw = &yfw[L.flagY];
+    const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
+    const int chW = std::max(hYlast - 6, 0);                    // weighted: every row searches this many rows
+    for (int j = 0; j < L.cols; ++j) {
+      const int x0 = EDGE + j * L.cellW, x1 = j < L.cols - 1 ? x0 + L.cellW : L.maxBX;
+      for (int x = x0; x < x1; ++x) fx[x] = FLAG_IN | (x == x0 ? FLAG_FIRST : 0) | (x == x1 - 1 ? FLAG_LAST : 0);
+    }
+    for (int i = 0; i < L.rows; ++i) {
+      const int y0 = EDGE + i * L.cellH, y1 = i < L.rows - 1 ? y0 + L.cellH : L.maxBY;
+      for (int y = y0; y < y1; ++y) fyp[y] = FLAG_IN | (y == y0 ? FLAG_FIRST : 0) | (y == y1 - 1 ? FLAG_LAST : 0);
+      for (int y = y0; y < y0 + chW; ++y) fyw[y] = FLAG_IN | (y == y0 ? FLAG_FIRST : 0) | (y == y0 + chW - 1 ? FLAG_LAST : 0);
+    }
+    // cells, row-major
+    L.listBase = listOff;
+    for (int i = 0; i < L.rows; ++i)
+      for (int j = 0; j < L.cols; ++j) {
+        CellDev c{};
+        c.level = l;
+        c.x0 = EDGE + j * L.cellW; c.cw = (j < L.cols - 1 ? c.x0 + L.cellW : L.maxBX) - c.x0;
+        c.y0 = EDGE + i * L.cellH; c.ch = (i < L.rows - 1 ? c.y0 + L.cellH : L.maxBY) - c.y0;
+        c.wx = c.x0 - 3; c.ww = j < L.cols - 1 ? L.cellW + 6 : L.maxBX + 3 - c.wx;
+        c.wy = c.y0 - 3; c.wh = i < L.rows - 1 ? L.cellH + 6 : L.maxBY + 3 - c.wy;
+        c.listOff = listOff;
+        c.listCap = (unsigned)(((c.cw + 1) / 2) * ((c.ch + 1) / 2));
+        listOff += c.listCap;
+        h->cellsPlain.push_back(c);
+        CellDev cw = c;
+        cw.ch = chW;
+        h->cellsWeighted.push_back(cw);
+      }
+    L.listCap = listOff - L.listBase;
+    // taps
+    if (l > 0) {
+      L.rtabX = (int)taps.size(); make_taps(fs.lv[l - 1].w, L.w, taps);
+      L.rtabY = (int)taps.size(); make_taps(fs.lv[l - 1].h, L.h, taps);
+    }
+  }
+  fs.planeBytes = align_up(planeOff, (size_t)fs.lv[0].pitch * 4);   // multiple of the level-0 pitch: batched 3-D copies
+  while (fs.planeBytes % fs.lv[0].pitch) fs.planeBytes += 256;
+  fs.listCapTotal = listOff;
+  fs.nCellsTotal = (int)h->cellsPlain.size();
+  fs.kpCap = kpOff;
+  fs.ftTotal = ftBase; fs.btTotal = btBase;
+  if (fs.kpCap > 65535) return IVG_ERR_CAPACITY;           // stereo packs the right index in 16 bits
+
+  const size_t B = (size_t)batch;
+  int rc;
+  if ((rc = h->pyr.alloc(B * fs.planeBytes))) return rc;
+  if ((rc = h->blur.alloc(B * fs.planeBytes))) return rc;
+  if ((rc = h->cand.alloc(B * fs.planeBytes))) return rc;
+  if (h->enableIntrospection && (rc = h->qual.alloc(B * fs.planeBytes))) return rc;
+  if ((rc = h->xflags.alloc(xf.size()))) return rc;
+  if ((rc = h->yflagsPlain.alloc(yfp.size()))) return rc;
+  if ((rc = h->yflagsWeighted.alloc(yfw.size()))) return rc;
+  if ((rc = h->dCellsPlain.alloc(h->cellsPlain.size()))) return rc;
+  if ((rc = h->dCellsWeighted.alloc(h->cellsWeighted.size()))) return rc;
+  if ((rc = h->rtab.alloc(taps.size()))) return rc;
+  if ((rc = h->cellList.alloc(B * fs.listCapTotal))) return rc;
+  if ((rc = h->cellCost.alloc(B * fs.nCellsTotal))) return rc;
+  if ((rc = h->cellCount.alloc(B * fs.nCellsTotal))) return rc;
+  if ((rc = h->workCell.alloc(B * fs.listCapTotal))) return rc;
+  if ((rc = h->workLevel.alloc(B * fs.listCapTotal))) return rc;
+  if ((rc = h->levelKp.alloc(B * fs.kpCap))) return rc;
+  if ((rc = h->levelCount.alloc(B * MAX_LEVELS))) return rc;
+  if ((rc = h->outKp.alloc(B * fs.kpCap * 28))) return rc;
+  if ((rc = h->outDesc.alloc(B * fs.kpCap * 32))) return rc;
+  if ((rc = h->outN.alloc(B))) return rc;
+  if ((rc = h->uRight.alloc(B * fs.kpCap))) return rc;
+  if ((rc = h->depth.alloc(B * fs.kpCap))) return rc;
+  if ((rc = h->sad.alloc(B * fs.kpCap))) return rc;
+  CK(cudaMemcpyAsync(h->xflags.p, xf.data(), xf.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->yflagsPlain.p, yfp.data(), yfp.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->yflagsWeighted.p, yfw.data(), yfw.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->dCellsPlain.p, h->cellsPlain.data(), h->cellsPlain.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->dCellsWeighted.p, h->cellsWeighted.data(), h->cellsWeighted.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
+  if (!taps.empty()) CK(cudaMemcpyAsync(h->rtab.p, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->outN.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->levelCount.p, 0, B * MAX_LEVELS * sizeof(int), h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+
+  fs.pyr = h->pyr.p; fs.blur = h->blur.p; fs.cand = h->cand.p; fs.qual = h->qual.p;
+  fs.xflags = h->xflags.p; fs.rtab = h->rtab.p;
+  fs.cellList = h->cellList.p; fs.cellCount = h->cellCount.p; fs.cellCost = h->cellCost.p;
+  fs.workCell = h->workCell.p; fs.workLevel = h->workLevel.p; fs.levelKp = h->levelKp.p;
+  fs.levelCount = h->levelCount.p; fs.outKp = h->outKp.p; fs.outDesc = h->outDesc.p; fs.outN = h->outN.p;
+  h->fs = fs;
+  h->W = W; h->H = H; h->maxBatch = batch; h->shapeReady = true;
+  h->haveResults = false; h->havePyramid = false; h->curBatch = 0;
+  return IVG_OK;
+}
+
+int ensure_shape(ivg_extractor* h, int W, int H, int batch) {
+  if (W <= 0 || H <= 0 || batch <= 0) return IVG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (h->shapeReady && h->W == W && h->H == H && batch <= h->maxBatch) return IVG_OK;
+  CK(cudaStreamSynchronize(h->stream));
+  const int b = (h->shapeReady && h->W == W && h->H == H) ? std::max(batch, h->maxBatch) : batch;
+  h->shapeReady = false;
+  return build_shape(h, W, H, b);
+}
+
+int honour_wait(ivg_extractor* h) {
+  if (h->waitFor) { CK(cudaStreamWaitEvent(h->stream, h->waitFor, 0)); h->waitFor = nullptr; }
+  return IVG_OK;
+}
+
+FrameSet active_fs(const ivg_extractor* h) {
+  FrameSet fs = h->fs;
+  fs.nImages = h->curBatch;
+  fs.weighted = h->curWeighted ? 1 : 0;
+  fs.yflags = h->curWeighted ? h->yflagsWeighted.p : h->yflagsPlain.p;
+  fs.cells = h->curWeighted ? h->dCellsWeighted.p : h->dCellsPlain.p;
+  return fs;
+}
+
+int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
+  for (int l = 1; l < fs.nlevels; ++l) {
+    dim3 grid((fs.lv[l].w + 127) / 128, (fs.lv[l].h + 7) / 8, fs.nImages), block(32, 8);
+    k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 0); h->launches++;
+    if (fs.weighted) { k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 1); h->launches++; }
+  }
+  CK(cudaGetLastError());
+  return IVG_OK;
+}
+
+int launch_extract(ivg_extractor* h) {
+  const FrameSet fs = active_fs(h);
+  int rc = launch_pyramid(h, fs);
+  if (rc) return rc;
+  k_fast_nms<<<dim3(fs.ftTotal, fs.nImages), 256, 0, h->stream>>>(fs); h->launches++;
+  k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); h->launches++;
+  k_cell_scan<<<dim3(fs.nCellsTotal, fs.nImages), 128, 0, h->stream>>>(fs); h->launches++;
+  k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, sizeof(SelShared), h->stream>>>(fs); h->launches++;
+  k_orient_describe<<<dim3((fs.kpCap + 7) / 8, fs.nImages), 256, 0, h->stream>>>(fs); h->launches++;
+  CK(cudaGetLastError());
+  h->haveResults = true; h->havePyramid = true;
+  return IVG_OK;
+}
+
+std::once_flag g_once;
+int g_init_rc = IVG_OK;
+
+int init_device_constants(int device) {
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpyToSymbol(c_pattern, kPatternHost, sizeof(kPatternHost)));
+  CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
+  return IVG_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* ivg_strerror(int s) {
+  switch (s) {
+    case IVG_OK: return "ok";
+    case IVG_ERR_INVALID: return "invalid argument";
+    case IVG_ERR_GEOMETRY: return "image too small for the reference cell grid";
+    case IVG_ERR_CAPACITY: return "capacity exceeded";
+    case IVG_ERR_CUDA: return "CUDA error";
+    case IVG_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case IVG_ERR_STATE: return "invalid call order / state";
+  }
+  return "unknown";
+}
+
+const char* ivg_last_cuda_error(void) { return g_cuda_err.c_str(); }
+
+int ivg_device_info(int device, char* name, int name_cap, int* sm, int* sm_count) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { g_cuda_err = "no CUDA device"; return IVG_ERR_NO_DEVICE; }
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  if (name && name_cap > 0) { std::strncpy(name, p.name, name_cap - 1); name[name_cap - 1] = 0; }
+  if (sm) *sm = p.major * 10 + p.minor;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  return p.major == 10 ? IVG_OK : IVG_ERR_NO_DEVICE;   // the library carries sm_100a code only
+}
+
+int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float scaleFactor, int nlevels,
+                         int iniThFAST, int minThFAST, int enableIntrospection) {
+  if (!out) return IVG_ERR_INVALID;
+  *out = nullptr;
+  if (nfeatures < 1 || nlevels < 1 || nlevels > MAX_LEVELS || !(scaleFactor > 1.0f)) return IVG_ERR_INVALID;
+  int rc = ivg_device_info(device, nullptr, 0, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaSetDevice(device));
+  ivg_extractor* h = new ivg_extractor();
+  h->device = device; h->nfeatures = nfeatures; h->scaleFactor = scaleFactor; h->nlevels = nlevels;
+  h->iniTh = iniThFAST; h->minTh = minThFAST; h->enableIntrospection = enableIntrospection != 0;
+  build_tables(h);
+  // one-time per-device constants (pattern) — per device in a multi-GPU process
+  static std::mutex mu;
+  static bool done[64] = {false};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 64 && !done[device]) {
+      rc = init_device_constants(device);
+      if (rc) { delete h; return rc; }
+      done[device] = true;
+    }
+  }
+  int um[16];
+  for (int i = 0; i < 16; ++i) um[i] = h->umax[i];
+  if (cudaMemcpyToSymbol(c_umax, um, sizeof(um)) != cudaSuccess) { g_cuda_err = "cudaMemcpyToSymbol(c_umax)"; delete h; return IVG_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evDone, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&h->evT0) != cudaSuccess || cudaEventCreate(&h->evT1) != cudaSuccess) {
+    g_cuda_err = "stream/event creation failed"; delete h; return IVG_ERR_CUDA;
+  }
+  *out = h;
+  return IVG_OK;
+}
+
+void ivg_extractor_destroy(ivg_extractor* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->pyr.release(); h->blur.release(); h->cand.release(); h->qual.release(); h->xflags.release();
+  h->yflagsPlain.release(); h->yflagsWeighted.release(); h->outKp.release(); h->outDesc.release();
+  h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release();
+  h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
+  h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
+  h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release();
+  if (h->evDone) cudaEventDestroy(h->evDone);
+  if (h->evT0) cudaEventDestroy(h->evT0);
+  if (h->evT1) cudaEventDestroy(h->evT1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int ivg_extractor_reserve(ivg_extractor* h, int width, int height, int max_batch) {
+  if (!h) return IVG_ERR_INVALID;
+  return ensure_shape(h, width, height, max_batch);
+}
+
+int ivg_get_levels(const ivg_extractor* h) { return h ? h->nlevels : 0; }
+float ivg_get_scale_factor(const ivg_extractor* h) { return h ? (float)h->scaleFactor : 0.f; }
+int ivg_get_scale_table(const ivg_extractor* h, int which, float* out) {
+  if (!h || !out || which < 0 || which > 3) return IVG_ERR_INVALID;
+  const std::vector<float>& t = which == 0 ? h->scale : which == 1 ? h->invScale : which == 2 ? h->sigma2 : h->invSigma2;
+  for (int i = 0; i < h->nlevels; ++i) out[i] = t[i];
+  return IVG_OK;
+}
+int ivg_get_features_per_level(const ivg_extractor* h, int* out) {
+  if (!h || !out) return IVG_ERR_INVALID;
+  for (int i = 0; i < h->nlevels; ++i) out[i] = h->nPerLevel[i];
+  return IVG_OK;
+}
+int ivg_max_keypoints(const ivg_extractor* h) { return h ? h->kpCap : 0; }
+
+int ivg_set_batch(ivg_extractor* h, int n, int width, int height, int with_cost) {
+  if (!h) return IVG_ERR_INVALID;
+  int rc = ensure_shape(h, width, height, n);
+  if (rc) return rc;
+  h->curBatch = n;
+  h->curWeighted = with_cost && h->enableIntrospection;   // src/ORBextractor.cc:1231
+  return IVG_OK;
+}
+
+int ivg_device_input(ivg_extractor* h, int index, int which, void** dev_ptr, size_t* pitch) {
+  if (!h || !h->shapeReady || index < 0 || index >= h->maxBatch || !dev_ptr) return IVG_ERR_INVALID;
+  uint8_t* base = which == 0 ? h->pyr.p : which == 2 ? h->qual.p : nullptr;
+  if (!base) return IVG_ERR_INVALID;
+  *dev_ptr = base + (size_t)index * h->fs.planeBytes;
+  if (pitch) *pitch = h->fs.lv[0].pitch;
+  return IVG_OK;
+}
+
+static int copy_frames_in(ivg_extractor* h, uint8_t* plane, int n, const uint8_t* src, size_t stride, size_t frame_bytes) {
+  const FrameSet& fs = h->fs;
+  const size_t dpitch = fs.lv[0].pitch;
+  if (n > 1 && stride > 0 && frame_bytes % stride == 0 && fs.planeBytes % dpitch == 0) {
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(src), stride, h->W, frame_bytes / stride);
+    p.dstPtr = make_cudaPitchedPtr(plane, dpitch, h->W, fs.planeBytes / dpitch);
+    p.extent = make_cudaExtent(h->W, h->H, n);
+    p.kind = cudaMemcpyHostToDevice;
+    CK(cudaMemcpy3DAsync(&p, h->stream));
+  } else {
+    for (int f = 0; f < n; ++f)
+      CK(cudaMemcpy2DAsync(plane + (size_t)f * fs.planeBytes, dpitch, src + (size_t)f * frame_bytes, stride, h->W, h->H,
+                           cudaMemcpyHostToDevice, h->stream));
+  }
+  return IVG_OK;
+}
+
+int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
+                     size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes) {
+  if (!h || !images || n < 1 || stride < (size_t)width) return IVG_ERR_INVALID;
+  int rc = ivg_set_batch(h, n, width, height, costs != nullptr);
+  if (rc) return rc;
+  if ((rc = honour_wait(h))) return rc;
+  if ((rc = copy_frames_in(h, h->pyr.p, n, images, stride, frame_bytes))) return rc;
+  if (h->curWeighted) {
+    if (cost_stride < (size_t)width) return IVG_ERR_INVALID;
+    if ((rc = copy_frames_in(h, h->qual.p, n, costs, cost_stride, cost_frame_bytes))) return rc;
+  }
+  return IVG_OK;
+}
+
+int ivg_run_batch(ivg_extractor* h) {
+  if (!h || !h->shapeReady || h->curBatch < 1) return IVG_ERR_STATE;
+  CK(cudaSetDevice(h->device));
+  int rc = honour_wait(h);
+  if (rc) return rc;
+  return launch_extract(h);
+}
+
+int ivg_download_batch(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+  if (!h || !h->haveResults) return IVG_ERR_STATE;
+  if (cap < h->fs.kpCap) return IVG_ERR_CAPACITY;
+  const int n = h->curBatch;
+  const size_t k = h->fs.kpCap;
+  if (keypoints) CK(cudaMemcpy2DAsync(keypoints, (size_t)cap * 28, h->outKp.p, k * 28, k * 28, n, cudaMemcpyDeviceToHost, h->stream));
+  if (descriptors) CK(cudaMemcpy2DAsync(descriptors, (size_t)cap * 32, h->outDesc.p, k * 32, k * 32, n, cudaMemcpyDeviceToHost, h->stream));
+  if (n_out) CK(cudaMemcpyAsync(n_out, h->outN.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return IVG_OK;
+}
+
+int ivg_sync(ivg_extractor* h) {
+  if (!h) return IVG_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  return IVG_OK;
+}
+
+int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
+                      size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes,
+                      ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+  if (!h) return IVG_ERR_INVALID;
+  if (cap < h->kpCap) return IVG_ERR_CAPACITY;
+  int rc = ivg_upload_batch(h, n, images, width, height, stride, frame_bytes, costs, cost_stride, cost_frame_bytes);
+  if (rc) return rc;
+  if ((rc = ivg_run_batch(h))) return rc;
+  if ((rc = ivg_download_batch(h, keypoints, descriptors, cap, n_out))) return rc;
+  return ivg_sync(h);
+}
+
+int ivg_extract(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride,
+                const uint8_t* cost, size_t cost_stride, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+  if (!h || !n_out) return IVG_ERR_INVALID;
+  *n_out = 0;
+  if (!image || width <= 0 || height <= 0) return IVG_OK;     // empty image: silent return (src/ORBextractor.cc:1227-1228)
+  return ivg_extract_batch(h, 1, image, width, height, stride, (size_t)height * stride, cost, cost_stride,
+                           (size_t)height * cost_stride, keypoints, descriptors, cap, n_out);
+}
+
+int ivg_compute_pyramid(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride) {
+  if (!h || !image) return IVG_ERR_INVALID;
+  int rc = ivg_upload_batch(h, 1, image, width, height, stride, (size_t)height * stride, nullptr, 0, 0);
+  if (rc) return rc;
+  const FrameSet fs = active_fs(h);
+  if ((rc = launch_pyramid(h, fs))) return rc;
+  h->havePyramid = true;
+  return ivg_sync(h);
+}
+
+int ivg_level_size(const ivg_extractor* h, int level, int* width, int* height) {
+  if (!h || !h->shapeReady || level < 0 || level >= h->nlevels) return IVG_ERR_INVALID;
+  if (width) *width = h->fs.lv[level].w;
+  if (height) *height = h->fs.lv[level].h;
+  return IVG_OK;
+}
+
+int ivg_get_pyramid_level(ivg_extractor* h, int index, int level, int which, uint8_t* dst, size_t dst_stride) {
+  if (!h || !h->havePyramid || level < 0 || level >= h->nlevels || index < 0 || index >= h->curBatch || !dst) return IVG_ERR_STATE;
+  const LevelDev& L = h->fs.lv[level];
+  const uint8_t* base = which == 0 ? h->pyr.p : which == 1 ? h->blur.p : which == 2 ? h->qual.p : which == 3 ? h->cand.p : nullptr;
+  if (!base || dst_stride < (size_t)L.w) return IVG_ERR_INVALID;
+  if (which == 2 && !h->curWeighted) return IVG_ERR_STATE;
+  CK(cudaMemcpy2DAsync(dst, dst_stride, base + (size_t)index * h->fs.planeBytes + L.planeOff, L.pitch, L.w, L.h,
+                       cudaMemcpyDeviceToHost, h->stream));
+  return ivg_sync(h);
+}
+
+int ivg_get_level_keypoints(ivg_extractor* h, int index, int level, float* x, float* y, float* response, int cap, int* n_out) {
+  if (!h || !h->haveResults || level < 0 || level >= h->nlevels || index < 0 || index >= h->curBatch || !n_out) return IVG_ERR_STATE;
+  const LevelDev& L = h->fs.lv[level];
+  int cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, h->levelCount.p + (size_t)index * MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *n_out = cnt;
+  if (cnt > cap) return IVG_ERR_CAPACITY;
+  std::vector<uint2> tmp(cnt);
+  if (cnt) {
+    CK(cudaMemcpyAsync(tmp.data(), h->levelKp.p + (size_t)index * h->fs.kpCap + L.kpOff, cnt * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  for (int i = 0; i < cnt; ++i) {
+    float r; std::memcpy(&r, &tmp[i].x, 4);
+    if (x) x[i] = (float)((tmp[i].y >> 8) & 0xFFF);
+    if (y) y[i] = (float)(tmp[i].y >> 20);
+    if (response) response[i] = r;
+  }
+  return IVG_OK;
+}
+
+// ---------------------------------------------------------------------------------------- stereo
+static int stereo_launch(ivg_extractor* left, ivg_extractor* right, const StereoArgs& A, int nPairs) {
+  const FrameSet fs = active_fs(left);
+  k_stereo_match<<<dim3((A.cap + 7) / 8, nPairs), 256, 0, left->stream>>>(fs, A); left->launches++;
+  k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); left->launches++;
+  CK(cudaGetLastError());
+  return IVG_OK;
+}
+
+int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD,
+                           float* uRight, float* depth, int cap, int sync) {
+  if (!left || !right || !left->haveResults || !right->haveResults) return IVG_ERR_STATE;
+  if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
+      left->curBatch != right->curBatch || left->fs.planeBytes != right->fs.planeBytes || left->fs.kpCap != right->fs.kpCap)
+    return IVG_ERR_STATE;
+  if (cap < left->fs.kpCap) return IVG_ERR_CAPACITY;
+  CK(cudaSetDevice(left->device));
+  const int n = left->curBatch;
+  CK(cudaEventRecord(right->evDone, right->stream));
+  CK(cudaStreamWaitEvent(left->stream, right->evDone, 0));
+  StereoArgs A{};
+  A.kpL = left->outKp.p; A.descL = left->outDesc.p; A.nL = left->outN.p;
+  A.kpR = right->outKp.p; A.descR = right->outDesc.p; A.nR = right->outN.p;
+  A.pyrL = left->pyr.p; A.pyrR = right->pyr.p; A.planeBytes = left->fs.planeBytes;
+  A.cap = left->fs.kpCap; A.nRows = left->fs.lv[0].h; A.mbf = mbf; A.maxD = maxD;
+  A.uRight = left->uRight.p; A.depth = left->depth.p; A.sad = left->sad.p; A.bestDist = nullptr;
+  int rc = stereo_launch(left, right, A, n);
+  if (rc) return rc;
+  const size_t k = A.cap;
+  if (uRight) CK(cudaMemcpy2DAsync(uRight, (size_t)cap * 4, left->uRight.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, left->stream));
+  if (depth) CK(cudaMemcpy2DAsync(depth, (size_t)cap * 4, left->depth.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, left->stream));
+  // the right handle must not overwrite its pyramids/keypoints before the matcher has read them
+  CK(cudaEventRecord(left->evDone, left->stream));
+  right->waitFor = left->evDone;
+  if (sync) return ivg_sync(left);
+  return IVG_OK;
+}
+
+int ivg_stereo_match(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD, float* uRight, float* depth, int cap) {
+  if (!left || !right) return IVG_ERR_INVALID;
+  if (left->curBatch != 1 || right->curBatch != 1) return IVG_ERR_STATE;
+  return ivg_stereo_match_batch(left, right, mbf, maxD, uRight, depth, cap, 1);
+}
+
+int ivg_stereo_match_keypoints(ivg_extractor* left, ivg_extractor* right, const ivg_keypoint* kL, int nL, const uint8_t* dL,
+                               const ivg_keypoint* kR, int nR, const uint8_t* dR, float mbf, float maxD, float* uRight, float* depth) {
+  if (!left || !right || !left->havePyramid || !right->havePyramid) return IVG_ERR_STATE;
+  if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
+      left->fs.planeBytes != right->fs.planeBytes)
+    return IVG_ERR_STATE;
+  if (nL < 0 || nR < 0 || nR > 65535 || (nL && (!kL || !dL)) || (nR && (!kR || !dR))) return IVG_ERR_INVALID;
+  if (nL == 0) return IVG_OK;
+  CK(cudaSetDevice(left->device));
+  int rc;
+  const int cap = std::max(nL, std::max(nR, 1));
+  if ((rc = left->extKpL.alloc((size_t)cap * 28)) || (rc = left->extDescL.alloc((size_t)cap * 32)) ||
+      (rc = left->extKpR.alloc((size_t)cap * 28)) || (rc = left->extDescR.alloc((size_t)cap * 32)) || (rc = left->nExt.alloc(2)))
+    return rc;
+  DevBuf<float> u, d; DevBuf<int> s;
+  if ((rc = u.alloc(cap)) || (rc = d.alloc(cap)) || (rc = s.alloc(cap))) return rc;
+  CK(cudaEventRecord(right->evDone, right->stream));
+  CK(cudaStreamWaitEvent(left->stream, right->evDone, 0));
+  cudaStream_t st = left->stream;
+  const int cnt[2] = {nL, nR};
+  CK(cudaMemcpyAsync(left->nExt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(left->extKpL.p, kL, (size_t)nL * 28, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(left->extDescL.p, dL, (size_t)nL * 32, cudaMemcpyHostToDevice, st));
+  if (nR) {
+    CK(cudaMemcpyAsync(left->extKpR.p, kR, (size_t)nR * 28, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(left->extDescR.p, dR, (size_t)nR * 32, cudaMemcpyHostToDevice, st));
+  }
+  StereoArgs A{};
+  A.kpL = left->extKpL.p; A.descL = left->extDescL.p; A.nL = left->nExt.p;
+  A.kpR = left->extKpR.p; A.descR = left->extDescR.p; A.nR = left->nExt.p + 1;
+  A.pyrL = left->pyr.p; A.pyrR = right->pyr.p; A.planeBytes = left->fs.planeBytes;
+  A.cap = cap; A.nRows = left->fs.lv[0].h; A.mbf = mbf; A.maxD = maxD;
+  A.uRight = u.p; A.depth = d.p; A.sad = s.p; A.bestDist = nullptr;
+  rc = stereo_launch(left, right, A, 1);
+  if (!rc && uRight) { cudaError_t e = cudaMemcpyAsync(uRight, u.p, (size_t)nL * 4, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) rc = IVG_ERR_CUDA; }
+  if (!rc && depth) { cudaError_t e = cudaMemcpyAsync(depth, d.p, (size_t)nL * 4, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) rc = IVG_ERR_CUDA; }
+  cudaError_t e = cudaStreamSynchronize(st);
+  u.release(); d.release(); s.release();
+  if (e != cudaSuccess) { g_cuda_err = cudaGetErrorString(e); return IVG_ERR_CUDA; }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------- measurement helpers
+int ivg_timer_start(ivg_extractor* h) { if (!h) return IVG_ERR_INVALID; CK(cudaEventRecord(h->evT0, h->stream)); return IVG_OK; }
+int ivg_timer_stop(ivg_extractor* h) { if (!h) return IVG_ERR_INVALID; CK(cudaEventRecord(h->evT1, h->stream)); return IVG_OK; }
+int ivg_timer_elapsed_ms(ivg_extractor* h, float* ms) {
+  if (!h || !ms) return IVG_ERR_INVALID;
+  CK(cudaEventSynchronize(h->evT1));
+  CK(cudaEventElapsedTime(ms, h->evT0, h->evT1));
+  return IVG_OK;
+}
+long long ivg_launch_count(const ivg_extractor* h) { return h ? h->launches : 0; }
+int ivg_host_alloc(void** ptr, size_t bytes) { if (!ptr) return IVG_ERR_INVALID; CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable)); return IVG_OK; }
+int ivg_host_free(void* ptr) { CK(cudaFreeHost(ptr)); return IVG_OK; }
+int ivg_flush_l2(ivg_extractor* h, size_t bytes) {
+  if (!h) return IVG_ERR_INVALID;
+  static thread_local DevBuf<uint8_t> scratch;
+  int rc = scratch.alloc(bytes);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(scratch.p, 0x5a, bytes, h->stream));
+  return IVG_OK;
+}
+int ivg_set_graph_mode(ivg_extractor* h, int enable) { if (!h) return IVG_ERR_INVALID; h->graphMode = enable != 0; return IVG_OK; }
+
+}  // extern "C"

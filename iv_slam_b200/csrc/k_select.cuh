@@ -1,0 +1,225 @@
+// k_select.cuh — K3: keypoint selection of ComputeKeyPointsOld, the LIVE selection path of the reference
+// (introspective_ORB_SLAM/src/ORBextractor.cc:880-1213; operator() calls it at :1248, the OctTree variant at :1247
+// is commented out — SURVEY F1).
+//
+//   k_cell_scan   one CTA per FAST cell: scans the cell's detect range of the candidate map in row-major order
+//                 (= cv::FAST's emission order), ballot-compacts the corners into the cell's list, counts how many
+//                 reach iniThFAST / minThFAST (the "<= 3 keypoints => retry with minThFAST" rule, :1045-1052 —
+//                 it counts post-NMS keypoints), and sums the cost-map over the cell window for IV-SLAM's
+//                 introspection weighting (:976-984).
+//   k_level_select one CTA per (level, frame): thread 0 replays the sequential budget logic (cell weights :942-987,
+//                 per-cell budgets :1028-1031/:1085-1096, the one-shot redistribution loop :1101-1133);
+//                 each warp then trims cells with the replayed std::nth_element (retainBest + resize, :1146-1148),
+//                 and thread 0 trims the level (:1162-1166).  Output order = reference order.
+// Deterministic: no atomics decide any order.
+#pragma once
+#include "common.cuh"
+#include "introselect.h"
+
+namespace ivg {
+
+constexpr int SEL_MAX_CELLS = 1024;      // cells per level the select kernel can hold in shared memory
+constexpr int SEL_LEVEL_CAP = 4096;      // level list entries kept in shared memory (else global fallback)
+constexpr int SEL_CELL_CAP = 512;        // per-warp cell list entries kept in shared memory (else global fallback)
+constexpr int SEL_WARPS = 8;
+
+__global__ void __launch_bounds__(128) k_cell_scan(FrameSet fs) {
+  const CellDev c = fs.cells[blockIdx.x];
+  const LevelDev& L = fs.lv[c.level];
+  const size_t img = blockIdx.y;
+  const uint8_t* cand = fs.cand + img * fs.planeBytes + L.planeOff;
+  uint32_t* list = fs.cellList + img * fs.listCapTotal + c.listOff;
+  __shared__ int wcnt[4];
+  __shared__ int wini[4], wmin[4];
+  __shared__ unsigned wsum[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = c.cw * c.ch;
+  int running = 0, nIni = 0, nMin = 0;
+  for (int start = 0; start < total; start += 128) {
+    const int i = start + tid;
+    int s = 0, x = 0, y = 0;
+    if (i < total) {
+      y = i / c.cw; x = i - y * c.cw;
+      s = __ldg(cand + (size_t)(c.y0 + y) * L.pitch + c.x0 + x);
+    }
+    const bool is = s != 0;                      // s >= scoreTh by construction
+    nIni += (is && s >= fs.iniTh);
+    nMin += (is && s >= fs.minTh);
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    int off = running;
+    for (int w = 0; w < warp; ++w) off += wcnt[w];
+    if (is) list[off + __popc(m & ((1u << lane) - 1))] = pack_xys(c.x0 + x, c.y0 + y, s);
+    running += wcnt[0] + wcnt[1] + wcnt[2] + wcnt[3];
+    __syncthreads();
+  }
+  // block reductions of the two counters (+ cost sum)
+  unsigned csum = 0;
+  if (fs.weighted) {
+    const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
+    const int wt = c.ww * c.wh;
+    for (int i = tid; i < wt; i += 128) {
+      const int y = i / c.ww, x = i - y * c.ww;
+      csum += __ldg(q + (size_t)(c.wy + y) * L.pitch + c.wx + x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    nIni += __shfl_xor_sync(0xffffffffu, nIni, o);
+    nMin += __shfl_xor_sync(0xffffffffu, nMin, o);
+    csum += __shfl_xor_sync(0xffffffffu, csum, o);
+  }
+  if (lane == 0) { wini[warp] = nIni; wmin[warp] = nMin; wsum[warp] = csum; }
+  __syncthreads();
+  if (tid == 0) {
+    fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = make_int2(wmin[0] + wmin[1] + wmin[2] + wmin[3], wini[0] + wini[1] + wini[2] + wini[3]);
+    fs.cellCost[img * fs.nCellsTotal + blockIdx.x] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+    // running == number of list entries (corners at scoreTh)
+  }
+}
+
+// response weight of IV-SLAM's introspection: 2 * (1/(1 + cost/255)) - 1, all float (src/ORBextractor.cc:1070-1071)
+__device__ __forceinline__ float introspection_weight(float cost) {
+  const float q = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fdiv_rn(cost, 255.0f)));
+  return __fsub_rn(__fmul_rn(2.0f, q), 1.0f);
+}
+
+struct SelShared {
+  SelItem levelBuf[SEL_LEVEL_CAP];
+  SelItem cellBuf[SEL_WARPS][SEL_CELL_CAP];
+  int nTotal[SEL_MAX_CELLS];
+  int nStored[SEL_MAX_CELLS];
+  int nRetain[SEL_MAX_CELLS];
+  int prefix[SEL_MAX_CELLS];
+  float nfc[SEL_MAX_CELLS];
+  unsigned char thr[SEL_MAX_CELLS];
+  unsigned char noMore[SEL_MAX_CELLS];
+  int total;
+  int count;
+};
+
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelShared& S = *reinterpret_cast<SelShared*>(smem_raw);
+  const int level = blockIdx.x;
+  const size_t img = blockIdx.y;
+  const LevelDev& L = fs.lv[level];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nCells = L.nCells;
+  const int2* cc = fs.cellCount + img * fs.nCellsTotal + L.cellBase;
+  const CellDev* cells = fs.cells + L.cellBase;
+
+  for (int c = tid; c < nCells; c += blockDim.x) {
+    const int2 v = cc[c];                         // x: corners at minTh, y: corners at iniTh
+    const bool retry = v.y <= 3;                  // cellKeyPoints.size() <= 3 after FAST(iniTh)  (:1047)
+    S.thr[c] = (unsigned char)(retry ? fs.minTh : fs.iniTh);
+    S.nTotal[c] = retry ? v.x : v.y;
+    S.nStored[c] = fs.iniTh < fs.minTh ? v.y : v.x;   // entries in the stored list (corners at scoreTh)
+    S.nfc[c] = (float)L.nfeaturesCell;
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    const int nDesired = L.nDesired;
+    if (fs.weighted) {
+      // cell weights, row-major, float accumulation order as in the reference (:942-987)
+      const uint32_t* cost = fs.cellCost + img * fs.nCellsTotal + L.cellBase;
+      float wsum = 0.0f;
+      for (int c = 0; c < nCells; ++c) {
+        const float area = __fmul_rn((float)cells[c].ww, (float)cells[c].wh);
+        const float mean = __fdiv_rn((float)cost[c], area);
+        const float qs = (float)(1.0 / (1.0 + (double)__fdiv_rn(mean, 255.0f)));
+        const float qn = __fsub_rn(__fmul_rn(2.0f, qs), 1.0f);
+        S.nfc[c] = qn;                            // parked; converted to a budget below
+        wsum = __fadd_rn(wsum, qn);
+      }
+      for (int c = 0; c < nCells; ++c) {
+        const float v = ceilf(__fdiv_rn(__fmul_rn((float)nDesired, S.nfc[c]), wsum));
+        S.nfc[c] = (1.0f < v) ? v : 1.0f;         // std::max(1.0f, v); NaN -> 1
+      }
+    }
+    int nNoMore = 0, nToDistribute = 0;
+    for (int c = 0; c < nCells; ++c) {            // :1082-1097
+      const int nKeys = S.nTotal[c];
+      const float f = S.nfc[c];
+      if ((float)nKeys > f) { S.nRetain[c] = (int)f; S.noMore[c] = 0; }
+      else {
+        S.nRetain[c] = nKeys;
+        nToDistribute = (int)__fadd_rn((float)nToDistribute, __fsub_rn(f, (float)nKeys));
+        S.noMore[c] = 1; nNoMore++;
+      }
+    }
+    if (nToDistribute > 0 && nNoMore < nCells) {  // the while loop runs exactly once (:1103-1133)
+      for (int c = 0; c < nCells; ++c) {
+        if (S.noMore[c]) continue;
+        const int nNew = (int)__fadd_rn(S.nfc[c], ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore))));
+        if (S.nTotal[c] > nNew) S.nRetain[c] = nNew;
+        else { S.nRetain[c] = S.nTotal[c]; nToDistribute += nNew - S.nTotal[c]; S.noMore[c] = 1; nNoMore++; }
+      }
+    }
+    int run = 0;
+    for (int c = 0; c < nCells; ++c) { S.prefix[c] = run; run += min(max(S.nRetain[c], 0), S.nTotal[c]); }
+    S.total = run;
+  }
+  __syncthreads();
+
+  const int total = S.total;
+  SelItem* levelBuf = total <= SEL_LEVEL_CAP ? S.levelBuf
+                                             : reinterpret_cast<SelItem*>(fs.workLevel + img * fs.listCapTotal + L.listBase);
+  const uint8_t* qual = fs.qual + img * fs.planeBytes + L.planeOff;
+
+  for (int c = warp; c < nCells; c += SEL_WARPS) {
+    const int n = S.nTotal[c];
+    const int keep = min(max(S.nRetain[c], 0), n);
+    if (keep == 0) continue;
+    const int stored = S.nStored[c], thr = S.thr[c];
+    const uint32_t* list = fs.cellList + img * fs.listCapTotal + cells[c].listOff;
+    SelItem* buf = n <= SEL_CELL_CAP ? S.cellBuf[warp]
+                                     : reinterpret_cast<SelItem*>(fs.workCell + img * fs.listCapTotal + cells[c].listOff);
+    int run = 0;
+    for (int base = 0; base < stored; base += 32) {
+      const int i = base + lane;
+      uint32_t e = 0;
+      bool pass = false;
+      if (i < stored) { e = list[i]; pass = unpack_s(e) >= thr; }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        float r = (float)unpack_s(e);
+        if (fs.weighted) {
+          const float cost = (float)__ldg(qual + (size_t)unpack_y(e) * L.pitch + unpack_x(e));
+          r = __fmul_rn(r, introspection_weight(cost));
+        }
+        buf[run + __popc(m & ((1u << lane) - 1))] = SelItem{__float_as_uint(r), e};
+      }
+      run += __popc(m);
+    }
+    __syncwarp();
+    if (buf != S.cellBuf[warp]) __threadfence_block();
+    if (lane == 0 && n > keep) sel_nth_element(buf, keep - 1, n);
+    __syncwarp();
+    if (buf != S.cellBuf[warp]) __threadfence_block();
+    const int dst = S.prefix[c];
+    for (int i = lane; i < keep; i += 32) levelBuf[dst + i] = buf[i];
+    __syncwarp();
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  if (tid == 0) {
+    int count = total;
+    if (total > L.nDesired) {
+      if (L.nDesired == 0) count = 0;
+      else { sel_nth_element(levelBuf, L.nDesired - 1, total); count = L.nDesired; }
+    }
+    S.count = count;
+    fs.levelCount[img * MAX_LEVELS + level] = count;
+  }
+  __threadfence_block();
+  __syncthreads();
+  const int count = S.count;
+  uint2* out = fs.levelKp + img * fs.kpCap + L.kpOff;
+  for (int i = tid; i < count; i += blockDim.x) out[i] = make_uint2(levelBuf[i].key, levelBuf[i].val);
+}
+
+}  // namespace ivg
