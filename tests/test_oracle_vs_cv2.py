@@ -1,0 +1,132 @@
+"""CPU tests (no GPU): pin the oracle (oracle/ivslam_oracle.cpp) to the real OpenCV 4.13 primitives and to the
+cv2-composed restatement of the reference pipeline.  The reference has no tests or golden vectors for this path
+(SURVEY §4), so this is what "parity pinned" rests on."""
+import cv2
+import numpy as np
+import pytest
+
+from iv_slam_b200 import synthetic as S
+from oracle.cv2_pipeline import Cv2Extractor, compute_stereo_matches
+
+from helpers import load_golden
+
+cv2.setNumThreads(1)
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1241, 376, 1034, 313), (1034, 313, 862, 261), (960, 600, 800, 500),
+                                          (346, 105, 288, 88), (97, 61, 81, 51), (640, 480, 640, 480), (300, 200, 251, 167)])
+def test_resize_matches_cv2(oracle, sw, sh, dw, dh):
+    img = np.random.default_rng(sw * 7 + dh).integers(0, 256, (sh, sw), dtype=np.uint8)
+    assert np.array_equal(oracle.resize_linear(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+@pytest.mark.parametrize("w,h", [(1241, 376), (346, 105), (64, 48), (9, 7), (37, 5)])
+def test_gauss_matches_cv2(oracle, w, h):
+    img = np.random.default_rng(w + h).integers(0, 256, (h, w), dtype=np.uint8)
+    ref = cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+    assert np.array_equal(oracle.gauss7(img), ref)
+
+
+@pytest.mark.parametrize("th", [7, 12, 20, 50])
+@pytest.mark.parametrize("kind", ["texture", "noise", "window"])
+def test_fast_matches_cv2(oracle, th, kind):
+    if kind == "texture":
+        img = S.make_image(320, 200, 5)
+    elif kind == "noise":
+        img = np.random.default_rng(3).integers(0, 256, (120, 160), dtype=np.uint8)
+    else:   # a strided ROI like the reference's cell windows
+        img = S.make_image(400, 300, 6)[40:40 + 58, 100:100 + 247]
+    det = cv2.FastFeatureDetector_create(th, True)
+    ref = np.array([(k.pt[0], k.pt[1], k.response) for k in det.detect(np.ascontiguousarray(img))]).reshape(-1, 3)
+    xs, ys, sc = oracle.fast9(img, th)
+    assert np.array_equal(ref, np.stack([xs, ys, sc], 1).astype(np.float64))
+
+
+def test_fast_atan2_matches_cv2(oracle):
+    rng = np.random.default_rng(0)
+    y = rng.integers(-1500000, 1500000, 20000).astype(np.float32)
+    x = rng.integers(-1500000, 1500000, 20000).astype(np.float32)
+    y[:50] = 0
+    x[25:75] = 0
+    ref = np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    assert np.array_equal(ref, oracle.fast_atan2(y, x))
+
+
+def test_retain_best_is_nth_element_prefix(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        n = int(rng.integers(1, 80))
+        resp = rng.integers(7, 40, n).astype(np.float32)
+        k = int(rng.integers(0, n + 3))
+        keep = oracle.retain_best(resp, k)
+        if k >= n:
+            assert np.array_equal(keep, np.arange(n))
+        else:
+            assert keep.size == k
+            if k:
+                cut = np.sort(resp)[::-1][k - 1]
+                assert (resp[keep] >= cut).all() and (np.sort(resp[keep])[::-1] == np.sort(resp)[::-1][:k]).all()
+
+
+@pytest.mark.parametrize("w,h,nf,ini,intro", [(480, 200, 600, 20, False), (400, 300, 500, 12, True), (752, 480, 1200, 20, True)])
+def test_pipeline_matches_cv2_composition(oracle, w, h, nf, ini, intro):
+    img = S.make_image(w, h, 21)
+    cost = S.make_cost_map(w, h, 22) if intro else None
+    eo = oracle.OracleExtractor(nf, 1.2, 8, ini, 7, intro)
+    ec = Cv2Extractor(nf, 1.2, 8, ini, 7, intro)
+    ko, do = eo(img, cost)
+    kc, dc = ec(img, cost)
+    assert list(eo.features_per_level()) == ec.nper
+    assert list(eo.umax()) == ec.umax == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    for l in range(8):
+        assert np.array_equal(eo.level(l, 0), ec.last_pyramid[l])
+        if ec.last_blur[l] is not None:
+            assert np.array_equal(eo.level(l, 1), ec.last_blur[l])
+        if intro:
+            assert np.array_equal(eo.level(l, 2), ec.last_qpyr[l])
+    assert ko.size == kc.size
+    for f in ko.dtype.names:
+        assert np.array_equal(ko[f], kc[f]), f
+    assert np.array_equal(do, dc)
+
+
+@pytest.mark.parametrize("name", ["small_plain", "small_cost", "kitti_c1", "jackal_c2"])
+def test_oracle_reproduces_golden(oracle, name):
+    """tests/golden/*.npz were produced by make_golden.py from cv2 4.13; the C++ oracle must reproduce them bit-for-bit."""
+    g = load_golden(name)
+    nf, ini, mn, intro = (int(v) for v in g["params"])
+    mbf, maxD = (float(v) for v in g["calib"])
+    eL, eR = oracle.OracleExtractor(nf, 1.2, 8, ini, mn, bool(intro)), oracle.OracleExtractor(nf, 1.2, 8, ini, mn, False)
+    r = oracle.stereo_frame(eL, eR, g["left"], g["right"], g.get("cost"), mbf, maxD, threads=2)
+    for side, k, d in (("L", "kL", "dL"), ("R", "kR", "dR")):
+        assert r[k].size == g[k].size
+        for f in r[k].dtype.names:
+            assert np.array_equal(r[k][f], g[k][f]), (side, f)
+        assert np.array_equal(r[d], g[d])
+    assert np.array_equal(r["uRight"], g["uRight"]) and np.array_equal(r["depth"], g["depth"])
+
+
+def test_stereo_oracle_matches_python_restatement(oracle):
+    img, right = S.make_stereo_pair(640, 240, 31)
+    eL, eR = oracle.OracleExtractor(800, 1.2, 8, 20, 7), oracle.OracleExtractor(800, 1.2, 8, 20, 7)
+    r = oracle.stereo_frame(eL, eR, img, right, None, 386.1448, 718.856, threads=1)
+    sc = eL.scale_factors()
+    inv = (np.float32(1) / sc).astype(np.float32)
+    pyrL, pyrR = [eL.level(l) for l in range(8)], [eR.level(l) for l in range(8)]
+    u, d = compute_stereo_matches(r["kL"], r["dL"], r["kR"], r["dR"], pyrL, pyrR, sc, inv, 386.1448, 718.856)
+    assert np.array_equal(u, r["uRight"]) and np.array_equal(d, r["depth"])
+    assert (u >= 0).sum() > 100
+
+
+def test_oracle_edge_cases(oracle):
+    e = oracle.OracleExtractor(500, 1.2, 8, 20, 7)
+    k, d = e(np.full((240, 320), 128, np.uint8))          # flat image: no corners anywhere
+    assert k.size == 0 and d.shape == (0, 32)
+    with pytest.raises(RuntimeError):                       # grid would be 0 columns: the reference divides by zero
+        e(np.zeros((60, 80), np.uint8))
+    # non-contiguous rows (a ROI of a larger buffer) give the same result as a compact copy
+    big = S.make_image(500, 300, 9)
+    roi = big[10:250, 20:420]
+    k1, d1 = e(roi)
+    k2, d2 = e(np.ascontiguousarray(roi))
+    assert np.array_equal(d1, d2) and all(np.array_equal(k1[f], k2[f]) for f in k1.dtype.names)
