@@ -149,6 +149,20 @@ int ivg_host_alloc(void** ptr, size_t bytes);
 int ivg_host_free(void* ptr);
 /* Writes `bytes` of device memory on the handle's stream (L2 flush between timed iterations). */
 int ivg_flush_l2(ivg_extractor* h, size_t bytes);
+/* Per-kernel device time: while enabled every kernel launch of this handle is bracketed by two CUDA events on the
+ * handle's stream.  ivg_profile_read waits for the stream and returns accumulated milliseconds and launch counts per
+ * kernel id since the last enable (arrays of IVG_NUM_KERNELS). */
+#define IVG_K_RESIZE 0
+#define IVG_K_FAST 1
+#define IVG_K_BLUR 2
+#define IVG_K_CELLS 3
+#define IVG_K_SELECT 4
+#define IVG_K_DESCRIBE 5
+#define IVG_K_STEREO 6
+#define IVG_K_MEDIAN 7
+#define IVG_NUM_KERNELS 8
+int ivg_profile_enable(ivg_extractor* h, int enable);
+int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches);
 /* When enabled (default off) run_batch wraps the kernel sequence of a batch in a CUDA graph that is re-used while
  * shape/batch stay the same. */
 int ivg_set_graph_mode(ivg_extractor* h, int enable);

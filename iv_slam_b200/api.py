@@ -21,6 +21,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libivslam_gpu.so")
 
 IVG_OK = 0
+KERNEL_NAMES = ("k_resize_level", "k_fast_nms", "k_gauss7", "k_cell_scan", "k_level_select", "k_orient_describe",
+                "k_stereo_match", "k_stereo_median")
 
 
 class IvgError(RuntimeError):
@@ -80,6 +82,8 @@ def lib():
         "ivg_host_free": (C.c_int, [vp]),
         "ivg_flush_l2": (C.c_int, [vp, sz]),
         "ivg_set_graph_mode": (C.c_int, [vp, C.c_int]),
+        "ivg_profile_enable": (C.c_int, [vp, C.c_int]),
+        "ivg_profile_read": (C.c_int, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -273,6 +277,16 @@ class ORBextractor:
 
     def launch_count(self):
         return lib().ivg_launch_count(self._h)
+
+    def profile_enable(self, on=True):
+        _ck(lib().ivg_profile_enable(self._h, int(on)), "ivg_profile_enable")
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since profile_enable."""
+        ms = np.zeros(len(KERNEL_NAMES), np.float64)
+        cnt = np.zeros(len(KERNEL_NAMES), np.int64)
+        _ck(lib().ivg_profile_read(self._h, _p(ms), _p(cnt)), "ivg_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_NAMES)}
 
     def flush_l2(self, nbytes=256 << 20):
         _ck(lib().ivg_flush_l2(self._h, nbytes), "ivg_flush_l2")

@@ -96,9 +96,32 @@ struct ivg_extractor {
   // stereo on caller-supplied keypoints
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
   bool graphMode = false;
+  // per-kernel CUDA-event profile (bench.py roofline): events bracket every launch while enabled
+  bool profile = false;
+  std::vector<cudaEvent_t> profEv;     // pairs
+  std::vector<int> profKid;
+  size_t profUsed = 0;
+  double profMs[IVG_NUM_KERNELS] = {0};
+  long long profCnt[IVG_NUM_KERNELS] = {0};
 };
 
 namespace {
+
+struct ProfScope {   // brackets one kernel launch with two events when profiling is on
+  ivg_extractor* h; size_t slot; bool on;
+  ProfScope(ivg_extractor* h_, int kid) : h(h_), slot(0), on(h_->profile) {
+    h->launches++;
+    if (!on) return;
+    if (h->profUsed + 2 > h->profEv.size()) {
+      for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->profEv.push_back(e); }
+    }
+    slot = h->profUsed; h->profUsed += 2;
+    h->profKid.resize(h->profEv.size() / 2);
+    h->profKid[slot / 2] = kid;
+    cudaEventRecord(h->profEv[slot], h->stream);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(h->profEv[slot + 1], h->stream); }
+};
 
 int build_tables(ivg_extractor* h) {
   // src/ORBextractor.cc:417-432 (float tables; the scaleFactor member is double, include/ORBextractor.h:108)
@@ -308,8 +331,8 @@ FrameSet active_fs(const ivg_extractor* h) {
 int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
   for (int l = 1; l < fs.nlevels; ++l) {
     dim3 grid((fs.lv[l].w + 127) / 128, (fs.lv[l].h + 7) / 8, fs.nImages), block(32, 8);
-    k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 0); h->launches++;
-    if (fs.weighted) { k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 1); h->launches++; }
+    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 0); }
+    if (fs.weighted) { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 1); }
   }
   CK(cudaGetLastError());
   return IVG_OK;
@@ -319,11 +342,11 @@ int launch_extract(ivg_extractor* h) {
   const FrameSet fs = active_fs(h);
   int rc = launch_pyramid(h, fs);
   if (rc) return rc;
-  k_fast_nms<<<dim3(fs.ftTotal, fs.nImages), 256, 0, h->stream>>>(fs); h->launches++;
-  k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); h->launches++;
-  k_cell_scan<<<dim3(fs.nCellsTotal, fs.nImages), 128, 0, h->stream>>>(fs); h->launches++;
-  k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, sizeof(SelShared), h->stream>>>(fs); h->launches++;
-  k_orient_describe<<<dim3((fs.kpCap + 7) / 8, fs.nImages), 256, 0, h->stream>>>(fs); h->launches++;
+  { ProfScope ps(h, IVG_K_FAST); k_fast_nms<<<dim3(fs.ftTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_CELLS); k_cell_scan<<<dim3(fs.nCellsTotal, fs.nImages), 128, 0, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, sizeof(SelShared), h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + 7) / 8, fs.nImages), 256, 0, h->stream>>>(fs); }
   CK(cudaGetLastError());
   h->haveResults = true; h->havePyramid = true;
   return IVG_OK;
@@ -415,6 +438,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
   h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release();
+  for (cudaEvent_t e : h->profEv) cudaEventDestroy(e);
   if (h->evDone) cudaEventDestroy(h->evDone);
   if (h->evT0) cudaEventDestroy(h->evT0);
   if (h->evT1) cudaEventDestroy(h->evT1);
@@ -591,8 +615,8 @@ int ivg_get_level_keypoints(ivg_extractor* h, int index, int level, float* x, fl
 // ---------------------------------------------------------------------------------------- stereo
 static int stereo_launch(ivg_extractor* left, ivg_extractor* right, const StereoArgs& A, int nPairs) {
   const FrameSet fs = active_fs(left);
-  k_stereo_match<<<dim3((A.cap + 7) / 8, nPairs), 256, 0, left->stream>>>(fs, A); left->launches++;
-  k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); left->launches++;
+  { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + 7) / 8, nPairs), 256, 0, left->stream>>>(fs, A); }
+  { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());
   return IVG_OK;
 }
@@ -692,6 +716,27 @@ int ivg_flush_l2(ivg_extractor* h, size_t bytes) {
   int rc = scratch.alloc(bytes);
   if (rc) return rc;
   CK(cudaMemsetAsync(scratch.p, 0x5a, bytes, h->stream));
+  return IVG_OK;
+}
+int ivg_profile_enable(ivg_extractor* h, int enable) {
+  if (!h) return IVG_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  h->profile = enable != 0;
+  h->profUsed = 0;
+  for (int k = 0; k < IVG_NUM_KERNELS; ++k) { h->profMs[k] = 0; h->profCnt[k] = 0; }
+  return IVG_OK;
+}
+int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches) {
+  if (!h) return IVG_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t s = 0; s + 1 < h->profUsed; s += 2) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, h->profEv[s], h->profEv[s + 1]));
+    const int k = h->profKid[s / 2];
+    h->profMs[k] += t; h->profCnt[k]++;
+  }
+  h->profUsed = 0;
+  for (int k = 0; k < IVG_NUM_KERNELS; ++k) { if (ms) ms[k] = h->profMs[k]; if (launches) launches[k] = h->profCnt[k]; }
   return IVG_OK;
 }
 int ivg_set_graph_mode(ivg_extractor* h, int enable) { if (!h) return IVG_ERR_INVALID; h->graphMode = enable != 0; return IVG_OK; }
