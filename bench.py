@@ -52,9 +52,8 @@ def algorithmic_bytes(w, h):
     n, n_raw = 2000, 3200
     return {
         "k_resize_level": 2 * P - L0 - L7,                 # read level l-1, write level l, l = 1..7 (all 7 launches)
-        "k_fast_nms": P + P,                               # read every level once, write the candidate map
+        "k_fast_cells": P + 8 * n_raw,                     # read every level once, write the corner lists (K2/K3 of SURVEY §8d)
         "k_gauss7": 2 * P,                                 # read P, write blurred P
-        "k_cell_scan": P + 4 * n_raw,                      # read candidate map, write corner lists
         "k_level_select": 4 * n_raw + 8 * n,
         "k_orient_describe": min(961 * n, P) + min(1369 * n, P) + 32 * n + 28 * n,
         "k_stereo_match": 2.4e6,                           # per PAIR (B_stereo)

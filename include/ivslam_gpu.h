@@ -155,12 +155,11 @@ int ivg_flush_l2(ivg_extractor* h, size_t bytes);
 #define IVG_K_RESIZE 0
 #define IVG_K_FAST 1
 #define IVG_K_BLUR 2
-#define IVG_K_CELLS 3
-#define IVG_K_SELECT 4
-#define IVG_K_DESCRIBE 5
-#define IVG_K_STEREO 6
-#define IVG_K_MEDIAN 7
-#define IVG_NUM_KERNELS 8
+#define IVG_K_SELECT 3
+#define IVG_K_DESCRIBE 4
+#define IVG_K_STEREO 5
+#define IVG_K_MEDIAN 6
+#define IVG_NUM_KERNELS 7
 int ivg_profile_enable(ivg_extractor* h, int enable);
 int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches);
 /* When enabled (default off) run_batch wraps the kernel sequence of a batch in a CUDA graph that is re-used while

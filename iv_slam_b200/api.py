@@ -21,8 +21,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libivslam_gpu.so")
 
 IVG_OK = 0
-KERNEL_NAMES = ("k_resize_level", "k_fast_nms", "k_gauss7", "k_cell_scan", "k_level_select", "k_orient_describe",
-                "k_stereo_match", "k_stereo_median")
+KERNEL_NAMES = ("k_resize_level", "k_fast_cells", "k_gauss7", "k_level_select", "k_orient_describe", "k_stereo_match",
+                "k_stereo_median")
 
 
 class IvgError(RuntimeError):
@@ -250,7 +250,7 @@ class ORBextractor:
         return w.value, h.value
 
     def level(self, level, which=0, index=0):
-        """which: 0 mvImagePyramid[level], 1 blurred working copy, 2 mvQualityImagePyramid[level], 3 FAST candidate map."""
+        """which: 0 mvImagePyramid[level], 1 blurred working copy, 2 mvQualityImagePyramid[level]."""
         w, h = self.level_size(level)
         out = np.empty((h, w), np.uint8)
         _ck(lib().ivg_get_pyramid_level(self._h, index, level, which, _p(out), out.strides[0]), "ivg_get_pyramid_level")

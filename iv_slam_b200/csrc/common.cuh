@@ -1,7 +1,7 @@
 // common.cuh — device-visible layout descriptors shared by all kernels of the stereo front-end.
 //
 // HBM layout (one "frame set" per extractor handle, B = reserved batch):
-//   plane[which][b]   which in {image pyramid, blurred pyramid, FAST candidate map, cost-map pyramid};
+//   plane[which][b]   which in {image pyramid, blurred pyramid, cost-map pyramid};
 //                     every plane holds all levels of one frame back to back, each level row-pitched
 //                     (pitch = width rounded up to 64 B, so rows are 16 B aligned for vector access).
 //   cellList[b]       u32 per possible FAST corner of every cell, row-major inside the cell (y<<20 | x<<8 | score)
@@ -20,12 +20,6 @@ constexpr int EDGE = 19;          // EDGE_THRESHOLD, src/ORBextractor.cc:75
 constexpr int HALF_PATCH = 15;    // HALF_PATCH_SIZE, :74
 constexpr int PATCH = 31;         // PATCH_SIZE, :73
 
-// x/y flags of a level: which pixels a FAST cell window actually tests, and where cell detect ranges begin/end
-constexpr uint8_t FLAG_IN = 1, FLAG_FIRST = 2, FLAG_LAST = 4;
-
-// FAST / blur tiles
-constexpr int FT_W = 64, FT_H = 32, FT_ORG = 16;   // FAST tiles start at x=y=16 (16 B aligned), detect area starts at 19
-constexpr int BT_W = 64, BT_H = 32;
 
 struct LevelDev {
   int w, h, pitch;
@@ -36,9 +30,9 @@ struct LevelDev {
   int cols, rows, cellW, cellH, nCells;
   int cellBase;           // first cell index of this level in the cell tables
   int kpOff;              // offset of this level inside levelKp (prefix sum of nDesired)
-  int ftBase, ftX, ftY;   // FAST tile numbering
+  int fSP, fSS, fBH;      // k_fast_cells: staged words per row, score bytes per row, rows per band
   int btBase, btX, btY;   // blur tile numbering
-  int flagX, flagY;       // offsets into xflags / yflags
+  int rzPitch, rzRows;    // k_resize_level: staged source bytes per row / rows of one output tile (this level as destination)
   int rtabX, rtabY;       // offsets into the resize tap tables (level >= 1)
   unsigned listBase;      // first cellList slot of this level
   unsigned listCap;       // cellList slots of this level
@@ -49,7 +43,7 @@ struct LevelDev {
 struct CellDev {          // one FAST cell of ComputeKeyPointsOld (src/ORBextractor.cc:989-1023)
   int level;
   int x0, y0, cw, ch;     // detect range (window minus its 3-px FAST margin), level coordinates
-  int wx, wy, ww, wh;     // the FAST window itself = cost-map averaging window (:976-978)
+  int wx, wy, ww, wh;     // cost-map averaging window of the budget pass (:976-978) = the cell's nominal FAST window
   unsigned listOff;       // first cellList slot
   unsigned listCap;
 };
@@ -60,11 +54,10 @@ struct FrameSet {
   int nlevels, nImages, weighted;
   int iniTh, minTh, scoreTh;
   int nCellsTotal, kpCap;
-  int ftTotal, btTotal;
+  int btTotal;
   unsigned listCapTotal;
   size_t planeBytes;
-  uint8_t* pyr; uint8_t* blur; uint8_t* cand; uint8_t* qual;     // [nImages][planeBytes]
-  const uint8_t* xflags; const uint8_t* yflags;                   // yflags already points at the active variant
+  uint8_t* pyr; uint8_t* blur; uint8_t* qual;                    // [nImages][planeBytes]
   const CellDev* cells;                                           // active variant
   const ResizeTap* rtab;
   uint32_t* cellList;      // [nImages][listCapTotal]

@@ -27,6 +27,8 @@ using namespace ivg;
 
 namespace {
 
+constexpr size_t FAST_SMEM_BUDGET = 44 * 1024;   // k_fast_cells stages at most this much per CTA (taller cells are banded)
+
 thread_local std::string g_cuda_err;
 
 #define CK(call)                                                                                   \
@@ -85,7 +87,8 @@ struct ivg_extractor {
   bool curWeighted = false;
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
-  DevBuf<uint8_t> pyr, blur, cand, qual, xflags, yflagsPlain, yflagsWeighted, outKp, outDesc;
+  DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc;
+  size_t fastSmem = 0, resizeSmem = 0;
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
   DevBuf<uint32_t> cellList, cellCost;
@@ -175,12 +178,12 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   FrameSet fs{};
   fs.nlevels = nl; fs.iniTh = std::min(std::max(h->iniTh, 0), 255); fs.minTh = std::min(std::max(h->minTh, 0), 255);
   fs.scoreTh = std::min(fs.iniTh, fs.minTh);
-  std::vector<uint8_t> xf, yfp, yfw;
   std::vector<ResizeTap> taps;
   h->cellsPlain.clear(); h->cellsWeighted.clear();
   size_t planeOff = 0;
   unsigned listOff = 0;
-  int kpOff = 0, ftBase = 0, btBase = 0;
+  int kpOff = 0, btBase = 0;
+  size_t fastSmem = 0, resizeSmem = 0;
   const float imageRatio = (float)W / H;
   for (int l = 0; l < nl; ++l) {
     LevelDev& L = fs.lv[l];
@@ -206,25 +209,20 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     if (L.nCells > SEL_MAX_CELLS) return IVG_ERR_CAPACITY;
     L.nfeaturesCell = (int)std::ceil((float)L.nDesired / L.nCells);
     L.cellBase = (int)h->cellsPlain.size();
-    L.ftX = (L.maxBX - FT_ORG + FT_W - 1) / FT_W; L.ftY = (L.maxBY - FT_ORG + FT_H - 1) / FT_H;
-    L.ftBase = ftBase; ftBase += L.ftX * L.ftY;
-    L.btX = (L.w + BT_W - 1) / BT_W; L.btY = (L.h + BT_H - 1) / BT_H;
+    L.btX = (L.w + BL_W - 1) / BL_W; L.btY = (L.h + BL_H - 1) / BL_H;
     L.btBase = btBase; btBase += L.btX * L.btY;
-    // flags
-    L.flagX = (int)xf.size(); L.flagY = (int)yfp.size();
-    xf.resize(xf.size() + L.w, 0); yfp.resize(yfp.size() + L.h, 0); yfw.resize(yfw.size() + L.h, 0);
-    uint8_t* fx = &xf[L.flagX]; uint8_t* fyp = &yfp[L.flagY]; uint8_t* fyw = &yfw[L.flagY];
+    // k_fast_cells shared-memory geometry: 4 B per staged pixel (two rows packed) + 1 B per score
+    L.fSP = (int)align_up(L.cellW + 9, 4);
+    L.fSS = (int)align_up(L.cellW, 4) + 8;
+    {
+      const int perRow = 4 * L.fSP + L.fSS;
+      int bh = (int)(FAST_SMEM_BUDGET / perRow) - 8;
+      bh = std::max(bh, 4);
+      L.fBH = std::min(bh, L.cellH);
+      fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + (size_t)L.fSS * (L.fBH + 4));
+    }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
     const int chW = std::max(hYlast - 6, 0);                    // weighted: every row searches this many rows
-    for (int j = 0; j < L.cols; ++j) {
-      const int x0 = EDGE + j * L.cellW, x1 = j < L.cols - 1 ? x0 + L.cellW : L.maxBX;
-      for (int x = x0; x < x1; ++x) fx[x] = FLAG_IN | (x == x0 ? FLAG_FIRST : 0) | (x == x1 - 1 ? FLAG_LAST : 0);
-    }
-    for (int i = 0; i < L.rows; ++i) {
-      const int y0 = EDGE + i * L.cellH, y1 = i < L.rows - 1 ? y0 + L.cellH : L.maxBY;
-      for (int y = y0; y < y1; ++y) fyp[y] = FLAG_IN | (y == y0 ? FLAG_FIRST : 0) | (y == y1 - 1 ? FLAG_LAST : 0);
-      for (int y = y0; y < y0 + chW; ++y) fyw[y] = FLAG_IN | (y == y0 ? FLAG_FIRST : 0) | (y == y0 + chW - 1 ? FLAG_LAST : 0);
-    }
     // cells, row-major
     L.listBase = listOff;
     for (int i = 0; i < L.rows; ++i)
@@ -248,6 +246,18 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     if (l > 0) {
       L.rtabX = (int)taps.size(); make_taps(fs.lv[l - 1].w, L.w, taps);
       L.rtabY = (int)taps.size(); make_taps(fs.lv[l - 1].h, L.h, taps);
+      int maxW = 1, maxR = 1;
+      for (int x0 = 0; x0 < L.w; x0 += RZ_W) {
+        const int x1 = std::min(x0 + RZ_W, L.w) - 1;
+        const int sxa = taps[L.rtabX + x0].s0 & ~3, sxe = taps[L.rtabX + x1].s1;
+        maxW = std::max(maxW, (sxe - sxa) / 4 + 1);
+      }
+      for (int y0 = 0; y0 < L.h; y0 += RZ_H) {
+        const int y1 = std::min(y0 + RZ_H, L.h) - 1;
+        maxR = std::max(maxR, taps[L.rtabY + y1].s1 - taps[L.rtabY + y0].s0 + 1);
+      }
+      L.rzPitch = maxW * 4; L.rzRows = maxR;
+      resizeSmem = std::max(resizeSmem, align_up((size_t)L.rzPitch * L.rzRows, 16) + (size_t)L.rzRows * RZ_W * 2);
     }
   }
   fs.planeBytes = align_up(planeOff, (size_t)fs.lv[0].pitch * 4);   // multiple of the level-0 pitch: batched 3-D copies
@@ -255,18 +265,16 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   fs.listCapTotal = listOff;
   fs.nCellsTotal = (int)h->cellsPlain.size();
   fs.kpCap = kpOff;
-  fs.ftTotal = ftBase; fs.btTotal = btBase;
+  fs.btTotal = btBase;
+  h->fastSmem = fastSmem; h->resizeSmem = resizeSmem;
+  if (fastSmem > 200 * 1024 || resizeSmem > 200 * 1024) return IVG_ERR_CAPACITY;
   if (fs.kpCap > 65535) return IVG_ERR_CAPACITY;           // stereo packs the right index in 16 bits
 
   const size_t B = (size_t)batch;
   int rc;
   if ((rc = h->pyr.alloc(B * fs.planeBytes))) return rc;
   if ((rc = h->blur.alloc(B * fs.planeBytes))) return rc;
-  if ((rc = h->cand.alloc(B * fs.planeBytes))) return rc;
   if (h->enableIntrospection && (rc = h->qual.alloc(B * fs.planeBytes))) return rc;
-  if ((rc = h->xflags.alloc(xf.size()))) return rc;
-  if ((rc = h->yflagsPlain.alloc(yfp.size()))) return rc;
-  if ((rc = h->yflagsWeighted.alloc(yfw.size()))) return rc;
   if ((rc = h->dCellsPlain.alloc(h->cellsPlain.size()))) return rc;
   if ((rc = h->dCellsWeighted.alloc(h->cellsWeighted.size()))) return rc;
   if ((rc = h->rtab.alloc(taps.size()))) return rc;
@@ -283,9 +291,6 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   if ((rc = h->uRight.alloc(B * fs.kpCap))) return rc;
   if ((rc = h->depth.alloc(B * fs.kpCap))) return rc;
   if ((rc = h->sad.alloc(B * fs.kpCap))) return rc;
-  CK(cudaMemcpyAsync(h->xflags.p, xf.data(), xf.size(), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->yflagsPlain.p, yfp.data(), yfp.size(), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->yflagsWeighted.p, yfw.data(), yfw.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->dCellsPlain.p, h->cellsPlain.data(), h->cellsPlain.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->dCellsWeighted.p, h->cellsWeighted.data(), h->cellsWeighted.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
   if (!taps.empty()) CK(cudaMemcpyAsync(h->rtab.p, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice, h->stream));
@@ -293,8 +298,8 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   CK(cudaMemsetAsync(h->levelCount.p, 0, B * MAX_LEVELS * sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
 
-  fs.pyr = h->pyr.p; fs.blur = h->blur.p; fs.cand = h->cand.p; fs.qual = h->qual.p;
-  fs.xflags = h->xflags.p; fs.rtab = h->rtab.p;
+  fs.pyr = h->pyr.p; fs.blur = h->blur.p; fs.qual = h->qual.p;
+  fs.rtab = h->rtab.p;
   fs.cellList = h->cellList.p; fs.cellCount = h->cellCount.p; fs.cellCost = h->cellCost.p;
   fs.workCell = h->workCell.p; fs.workLevel = h->workLevel.p; fs.levelKp = h->levelKp.p;
   fs.levelCount = h->levelCount.p; fs.outKp = h->outKp.p; fs.outDesc = h->outDesc.p; fs.outN = h->outN.p;
@@ -323,16 +328,15 @@ FrameSet active_fs(const ivg_extractor* h) {
   FrameSet fs = h->fs;
   fs.nImages = h->curBatch;
   fs.weighted = h->curWeighted ? 1 : 0;
-  fs.yflags = h->curWeighted ? h->yflagsWeighted.p : h->yflagsPlain.p;
   fs.cells = h->curWeighted ? h->dCellsWeighted.p : h->dCellsPlain.p;
   return fs;
 }
 
 int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
   for (int l = 1; l < fs.nlevels; ++l) {
-    dim3 grid((fs.lv[l].w + 127) / 128, (fs.lv[l].h + 7) / 8, fs.nImages), block(32, 8);
-    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 0); }
-    if (fs.weighted) { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, block, 0, h->stream>>>(fs, l, 1); }
+    dim3 grid((fs.lv[l].w + RZ_W - 1) / RZ_W, (fs.lv[l].h + RZ_H - 1) / RZ_H, fs.nImages);
+    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 0); }
+    if (fs.weighted) { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 1); }
   }
   CK(cudaGetLastError());
   return IVG_OK;
@@ -342,9 +346,8 @@ int launch_extract(ivg_extractor* h) {
   const FrameSet fs = active_fs(h);
   int rc = launch_pyramid(h, fs);
   if (rc) return rc;
-  { ProfScope ps(h, IVG_K_FAST); k_fast_nms<<<dim3(fs.ftTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
-  { ProfScope ps(h, IVG_K_CELLS); k_cell_scan<<<dim3(fs.nCellsTotal, fs.nImages), 128, 0, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, sizeof(SelShared), h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + 7) / 8, fs.nImages), 256, 0, h->stream>>>(fs); }
   CK(cudaGetLastError());
@@ -352,13 +355,13 @@ int launch_extract(ivg_extractor* h) {
   return IVG_OK;
 }
 
-std::once_flag g_once;
-int g_init_rc = IVG_OK;
 
 int init_device_constants(int device) {
   CK(cudaSetDevice(device));
   CK(cudaMemcpyToSymbol(c_pattern, kPatternHost, sizeof(kPatternHost)));
   CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
+  CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return IVG_OK;
 }
 
@@ -432,8 +435,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->pyr.release(); h->blur.release(); h->cand.release(); h->qual.release(); h->xflags.release();
-  h->yflagsPlain.release(); h->yflagsWeighted.release(); h->outKp.release(); h->outDesc.release();
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release();
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
@@ -582,7 +584,7 @@ int ivg_level_size(const ivg_extractor* h, int level, int* width, int* height) {
 int ivg_get_pyramid_level(ivg_extractor* h, int index, int level, int which, uint8_t* dst, size_t dst_stride) {
   if (!h || !h->havePyramid || level < 0 || level >= h->nlevels || index < 0 || index >= h->curBatch || !dst) return IVG_ERR_STATE;
   const LevelDev& L = h->fs.lv[level];
-  const uint8_t* base = which == 0 ? h->pyr.p : which == 1 ? h->blur.p : which == 2 ? h->qual.p : which == 3 ? h->cand.p : nullptr;
+  const uint8_t* base = which == 0 ? h->pyr.p : which == 1 ? h->blur.p : which == 2 ? h->qual.p : nullptr;
   if (!base || dst_stride < (size_t)L.w) return IVG_ERR_INVALID;
   if (which == 2 && !h->curWeighted) return IVG_ERR_STATE;
   CK(cudaMemcpy2DAsync(dst, dst_stride, base + (size_t)index * h->fs.planeBytes + L.planeOff, L.pitch, L.w, L.h,

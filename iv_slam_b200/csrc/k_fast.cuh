@@ -1,157 +1,212 @@
-// k_fast.cuh — K2: FAST-9/16 corner score + cell-masked 3x3 non-max suppression over every pyramid level.
+// k_fast.cuh — K2+K3a fused: per-cell FAST-9/16 score, cell-local 3x3 non-max suppression and ordered (row-major)
+// warp-ballot compaction of the surviving corners into the cell's list.
 //
 // Replaces the per-cell cv::FAST(cellImage, kps, th, true) calls of ComputeKeyPointsOld
-// (introspective_ORB_SLAM/src/ORBextractor.cc:1045 and :1051).  SURVEY Appendix A.3:
+// (introspective_ORB_SLAM/src/ORBextractor.cc:1045 and :1051) including their emission order, and cv::sum over the
+// cost-map window (:976-978).  SURVEY Appendix A.3:
 //   * the corner score S (largest threshold at which the pixel is still a 9-arc corner) does not depend on the
-//     threshold, and "corner at th" <=> S >= th, so ONE score pass serves both iniThFAST and minThFAST;
-//   * the reference runs FAST per cell window, so NMS at the edge of a cell's detect range sees zeros for pixels
-//     that belong to the neighbouring cell: neighbours outside the centre's own detect range are skipped, using
-//     per-level x/y flag tables (FLAG_FIRST / FLAG_LAST mark where a range begins / ends);
-//   * pixels outside every detect range (including the rows IV-SLAM's stale-hY quirk never searches)
-//     are not candidates.
-// Output: candidate map, one byte per pixel = S if the pixel survives NMS (S >= minThFAST), else 0.
+//     threshold and "corner at th" <=> S >= th, so ONE score pass serves both iniThFAST and minThFAST; the
+//     "<= 3 keypoints => retry with minThFAST" rule (:1047-1052) only needs the two counts, taken here;
+//   * the reference runs FAST per cell window, so NMS never sees scores of the neighbouring cell: one CTA = one cell,
+//     scores outside the cell's own detect range simply do not exist (zero border);
+//   * with a cost-map the detect rows shrink to the stale window height of the last cell row: that is
+//     just a different cell table.
 //
-// One CTA = one 64x32 tile of one level of one frame (tile table spans all levels: one launch per batch).
-// Integer stencil work: the pixel tile (+4 px halo) is staged in shared memory with aligned 32-bit loads, the
-// arc test runs for every pixel, the exact score only for the compacted list of pixels that pass (dense warps).
+// Work shape: integer stencil, ~60 instructions per pixel, no data-dependent branches in the score pass.
+//   stage   the cell's pixels (+3 px ring margin) are loaded with aligned 32-bit words and stored in shared memory as
+//           one 32-bit word per pixel holding TWO vertically adjacent pixels in 16-bit lanes (pix(x,y) | pix(x,y+1)<<16),
+//           so that every ring sample of a vertical pixel pair is ONE conflict-free LDS.32 already in the packed
+//           16x2 layout of the DPX min/max instructions;
+//   score   each thread scores a vertical pixel pair: 16 packed differences and a 3-input min/max network
+//           (VIMNMX3.U16x2): min over every 9-arc = min3 of three 3-minima, 80 packed ops for 2 pixels;
+//   nms     3x3 strict maximum inside the cell, 4 pixels per thread, then ballot/scan compaction in row-major order
+//           (= cv::FAST's emission order) straight into the cell list; no atomics decide any order.
+// Tall cells are processed in bands of rows (2 score rows recomputed per band) so shared memory stays bounded.
 #pragma once
 #include "common.cuh"
 
 namespace ivg {
 
-constexpr int FT_PITCH = 80;                 // bytes per staged row: x0-4 .. x0+75
-constexpr int FT_ROWS = FT_H + 8;            // y0-4 .. y0+35
-constexpr int FT_TESTW = FT_W + 2, FT_TESTH = FT_H + 2;
+__device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 
-__device__ __forceinline__ bool arc9(uint32_t m) {   // 9 contiguous set bits in a circular 16-bit mask
-  m |= m << 16;
-  uint32_t t = m & (m >> 1);
-  t &= t >> 2;
-  t &= t >> 4;
-  t &= m >> 8;
-  return t != 0;
-}
-
-// exact score from the 16 ring differences d[k] = centre - ring[k]
-__device__ __forceinline__ int fast_score16(const int (&d)[16]) {
-  int lo3[16], hi3[16];
+// T = max over arcs of (min over arc of D) combined with the dark polarity, per 16-bit lane; D[k] = 256 + centre - ring[k]
+__device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
+  unsigned lo3[16], hi3[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    lo3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
-    hi3[k] = max(max(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
+    lo3[k] = vmin3(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
+    hi3[k] = vmax3(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
   }
-  int best = -1024, worst = 1024;
+  unsigned mn[16], mx[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const int mn = min(min(lo3[k], lo3[(k + 3) & 15]), lo3[(k + 6) & 15]);   // min over the arc k..k+8
-    const int mx = max(max(hi3[k], hi3[(k + 3) & 15]), hi3[(k + 6) & 15]);
-    best = max(best, mn);
-    worst = min(worst, mx);
+    mn[k] = vmin3(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);   // min over the arc k..k+8
+    mx[k] = vmax3(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
   }
-  return max(best, -worst) - 1;
+  unsigned b0 = vmax3(mn[0], mn[1], mn[2]), b1 = vmax3(mn[3], mn[4], mn[5]), b2 = vmax3(mn[6], mn[7], mn[8]);
+  unsigned b3 = vmax3(mn[9], mn[10], mn[11]), b4 = vmax3(mn[12], mn[13], mn[14]);
+  const unsigned best = vmax3(vmax3(b0, b1, b2), vmax3(b3, b4, mn[15]), 0u);
+  unsigned w0 = vmin3(mx[0], mx[1], mx[2]), w1 = vmin3(mx[3], mx[4], mx[5]), w2 = vmin3(mx[6], mx[7], mx[8]);
+  unsigned w3 = vmin3(mx[9], mx[10], mx[11]), w4 = vmin3(mx[12], mx[13], mx[14]);
+  const unsigned worst = vmin3(vmin3(w0, w1, w2), vmin3(w3, w4, mx[15]), 0xFFFFFFFFu);
+  // bright: best-256, dark: 256-worst  =>  S + 257 = max(best, 512 - worst)
+  return __vmaxu2(best, 0x02000200u - worst);
 }
 
-__global__ void __launch_bounds__(256) k_fast_nms(FrameSet fs) {
-  __shared__ __align__(16) uint8_t spix[FT_ROWS * FT_PITCH];
-  __shared__ __align__(16) uint8_t sscore[FT_ROWS * FT_PITCH];
-  __shared__ uint8_t sxf[FT_PITCH], syf[FT_ROWS];
-  __shared__ uint16_t slist[FT_TESTW * FT_TESTH];
-  __shared__ int scount;
+__global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  __shared__ int wcnt[2][8];
+  __shared__ int sred[3][8];
 
-  // locate the level of this tile
-  int level = 0;
-#pragma unroll 1
-  for (int l = 1; l < fs.nlevels; ++l)
-    if ((int)blockIdx.x >= fs.lv[l].ftBase) level = l;
-  const LevelDev& L = fs.lv[level];
-  const int t = blockIdx.x - L.ftBase;
-  const int x0 = FT_ORG + (t % L.ftX) * FT_W, y0 = FT_ORG + (t / L.ftX) * FT_H;
-  const size_t frameOff = (size_t)blockIdx.y * fs.planeBytes + L.planeOff;
-  const uint8_t* img = fs.pyr + frameOff;
-  const int tid = threadIdx.x;
+  const CellDev c = fs.cells[blockIdx.x];
+  const LevelDev& L = fs.lv[c.level];
+  const size_t img = blockIdx.y;
+  const uint8_t* pix = fs.pyr + img * fs.planeBytes + L.planeOff;
+  uint32_t* list = fs.cellList + img * fs.listCapTotal + c.listOff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cw = c.cw, ch = c.ch;
+  const int SP = L.fSP, SS = L.fSS, BH = L.fBH;
+  uint32_t* sp = reinterpret_cast<uint32_t*>(fsm);
+  uint8_t* ss = fsm + (size_t)4 * SP * (BH + 8);
+  const int xa = (c.x0 - 3) & ~3;          // global x of staged column 0 (word aligned)
+  const int cOff = c.x0 - xa;              // staged column of detect column 0
+  const int scoreTh = fs.scoreTh;
+  const int nChunks = (cw + 31) >> 5, nG = (cw + 3) >> 2;
 
-  if (tid == 0) scount = 0;
-  // stage pixels: rows y0-4.., 20 aligned words per row starting at x0-4 (x0 is a multiple of 16)
-  for (int i = tid; i < FT_ROWS * (FT_PITCH / 4); i += 256) {
-    const int r = i / (FT_PITCH / 4), c = i % (FT_PITCH / 4);
-    const int gy = y0 - 4 + r, gx = x0 - 4 + 4 * c;
-    uint32_t v = 0;
-    if (gy < L.h && gx < L.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + gx));
-    reinterpret_cast<uint32_t*>(spix)[i] = v;
-    reinterpret_cast<uint32_t*>(sscore)[i] = 0;
-  }
-  if (tid < FT_PITCH) { const int gx = x0 - 4 + tid; sxf[tid] = gx < L.w ? fs.xflags[L.flagX + gx] : 0; }
-  if (tid >= 128 && tid < 128 + FT_ROWS) { const int gy = y0 - 4 + (tid - 128); syf[tid - 128] = gy < L.h ? fs.yflags[L.flagY + gy] : 0; }
-  __syncthreads();
+  int running = 0, nIni = 0, nMin = 0, par = 0;
 
-  const int th = fs.scoreTh;   // min(iniThFAST, minThFAST)
-  constexpr int DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-  constexpr int DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  for (int r0 = 0; r0 < ch; r0 += BH) {
+    const int r1 = min(r0 + BH, ch);
+    const int s0 = max(r0 - 1, 0), s1 = min(r1 + 1, ch);
+    const int nPairs = (s1 - s0 + 1) >> 1;
+    const int nWR = 2 * nPairs + 5;
 
-  // phase 1: 9-arc test at minThFAST for every in-range pixel of the tile + 1 px ring
-  for (int i = tid; i < FT_TESTW * FT_TESTH; i += 256) {
-    const int ry = i / FT_TESTW, rx = i - ry * FT_TESTW;
-    const int sy = ry + 3, sx = rx + 3;                 // staged coordinates of pixel (x0-1+rx, y0-1+ry)
-    if (!((sxf[sx] & FLAG_IN) && (syf[sy] & FLAG_IN))) continue;
-    const uint8_t* p = spix + sy * FT_PITCH + sx;
-    const int v = p[0], hi = v + th, lo = v - th;
-    uint32_t br = 0, dk = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int r = p[DY[k] * FT_PITCH + DX[k]];
-      br |= (r > hi ? 1u : 0u) << k;
-      dk |= (r < lo ? 1u : 0u) << k;
-    }
-    if (arc9(br) || arc9(dk)) slist[atomicAdd(&scount, 1)] = (uint16_t)(sy * FT_PITCH + sx);
-  }
-  __syncthreads();
-
-  // phase 2: exact score for the pixels that passed (dense)
-  const int n = scount;
-  for (int j = tid; j < n; j += 256) {
-    const int idx = slist[j];
-    const uint8_t* p = spix + idx;
-    const int v = p[0];
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = v - (int)p[DY[k] * FT_PITCH + DX[k]];
-    sscore[idx] = (uint8_t)fast_score16(d);
-  }
-  __syncthreads();
-
-  // phase 3: NMS inside the centre's own detect range, 4 pixels per thread, one aligned 32-bit store
-  uint8_t* cand = fs.cand + frameOff;
-  for (int g = tid; g < (FT_W / 4) * FT_H; g += 256) {
-    const int ry = g / (FT_W / 4), rx4 = (g % (FT_W / 4)) * 4;
-    const int gy = y0 + ry, gx = x0 + rx4;
-    if (gy >= L.h || gx >= L.pitch) continue;
-    const int sy = ry + 4;
-    const uint8_t yf = syf[sy];
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int sx = rx4 + 4 + i;
-      const uint8_t* s = sscore + sy * FT_PITCH + sx;
-      const int c = s[0];
-      if (c == 0) continue;
-      const uint8_t xf = sxf[sx];
-      const bool l = !(xf & FLAG_FIRST), r = !(xf & FLAG_LAST), u = !(yf & FLAG_FIRST), d = !(yf & FLAG_LAST);
-      bool keep = true;
-      if (l) keep = keep && c > s[-1];
-      if (r) keep = keep && c > s[1];
-      if (u) {
-        keep = keep && c > s[-FT_PITCH];
-        if (l) keep = keep && c > s[-FT_PITCH - 1];
-        if (r) keep = keep && c > s[-FT_PITCH + 1];
+    // ---- stage: word row q = pixel rows (q, q+1) of global row gy0 + q
+    const int gy0 = c.y0 + s0 - 3;
+    for (int i = tid; i < nWR * (SP >> 2); i += 256) {
+      const int q = i / (SP >> 2), g = i - q * (SP >> 2);
+      const int gx = xa + 4 * g;
+      uint32_t a = 0, b = 0;
+      if (gx < L.pitch) {
+        const uint8_t* p = pix + (size_t)(gy0 + q) * L.pitch + gx;
+        a = __ldg(reinterpret_cast<const uint32_t*>(p));
+        b = __ldg(reinterpret_cast<const uint32_t*>(p + L.pitch));
       }
-      if (d) {
-        keep = keep && c > s[FT_PITCH];
-        if (l) keep = keep && c > s[FT_PITCH - 1];
-        if (r) keep = keep && c > s[FT_PITCH + 1];
-      }
-      if (keep) out |= (uint32_t)c << (8 * i);
+      uint4 o;
+      o.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu;
+      o.y = __byte_perm(a, b, 0x0501) & 0x00FF00FFu;
+      o.z = __byte_perm(a, b, 0x0602) & 0x00FF00FFu;
+      o.w = __byte_perm(a, b, 0x0703) & 0x00FF00FFu;
+      *reinterpret_cast<uint4*>(sp + q * SP + 4 * g) = o;
     }
-    *reinterpret_cast<uint32_t*>(cand + (size_t)gy * L.pitch + gx) = out;
+    for (int i = tid; i < (SS >> 2) * (s1 - s0 + 2); i += 256) reinterpret_cast<uint32_t*>(ss)[i] = 0;
+    __syncthreads();
+
+    // ---- score: one vertical pixel pair per thread
+    for (int it = warp; it < nPairs * nChunks; it += 8) {
+      const int p = it / nChunks, x = (it - p * nChunks) * 32 + lane;
+      if (x < cw) {
+        const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
+        const unsigned C = ctr[0] + 0x01000100u;
+        unsigned D[16];
+        D[0] = C - ctr[3 * SP];          D[1] = C - ctr[3 * SP + 1];      D[2] = C - ctr[2 * SP + 2];      D[3] = C - ctr[SP + 3];
+        D[4] = C - ctr[3];               D[5] = C - ctr[-SP + 3];         D[6] = C - ctr[-2 * SP + 2];     D[7] = C - ctr[-3 * SP + 1];
+        D[8] = C - ctr[-3 * SP];         D[9] = C - ctr[-3 * SP - 1];     D[10] = C - ctr[-2 * SP - 2];    D[11] = C - ctr[-SP - 3];
+        D[12] = C - ctr[-3];             D[13] = C - ctr[SP - 3];         D[14] = C - ctr[2 * SP - 2];     D[15] = C - ctr[3 * SP - 1];
+        const unsigned T = fast_score_pair(D);
+        int sA = (int)(T & 0xFFFFu) - 257, sB = (int)(T >> 16) - 257;
+        sA = sA >= scoreTh ? sA : 0;
+        sB = sB >= scoreTh ? sB : 0;
+        uint8_t* o = ss + (2 * p + 1) * SS + 4 + x;
+        o[0] = (uint8_t)sA;
+        if (s0 + 2 * p + 1 < s1) o[SS] = (uint8_t)sB;
+      }
+    }
+    __syncthreads();
+
+    // ---- NMS + ordered compaction over detect rows [r0, r1)
+    const int nItems = (r1 - r0) * nG;
+    for (int base = 0; base < nItems; base += 256) {
+      const int i = base + tid;
+      unsigned mask = 0;
+      uint32_t cword = 0;
+      int row = 0, x = 0;
+      if (i < nItems) {
+        row = r0 + i / nG; x = (i % nG) * 4;
+        const uint8_t* sr = ss + (row - s0 + 1) * SS + 4 + x;
+        cword = *reinterpret_cast<const uint32_t*>(sr);
+        if (cword) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(sr);
+          const int SW = SS >> 2;
+          const unsigned long long up = ((unsigned long long)w[-SW + 1] << 40) | ((unsigned long long)w[-SW] << 8) | (w[-SW - 1] >> 24);
+          const unsigned long long md = ((unsigned long long)w[1] << 40) | ((unsigned long long)cword << 8) | (w[-1] >> 24);
+          const unsigned long long dn = ((unsigned long long)w[SW + 1] << 40) | ((unsigned long long)w[SW] << 8) | (w[SW - 1] >> 24);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cc = (int)((md >> (8 * (k + 1))) & 0xFF);
+            if (cc == 0) continue;
+            const int l = (int)((md >> (8 * k)) & 0xFF), r = (int)((md >> (8 * (k + 2))) & 0xFF);
+            const int u0 = (int)((up >> (8 * k)) & 0xFF), u1 = (int)((up >> (8 * (k + 1))) & 0xFF), u2 = (int)((up >> (8 * (k + 2))) & 0xFF);
+            const int d0 = (int)((dn >> (8 * k)) & 0xFF), d1 = (int)((dn >> (8 * (k + 1))) & 0xFF), d2 = (int)((dn >> (8 * (k + 2))) & 0xFF);
+            const int m = max(max(max(l, r), max(u0, u1)), max(max(u2, d0), max(d1, d2)));
+            if (cc > m) mask |= 1u << k;
+          }
+        }
+      }
+      // ordered offsets: inclusive warp scan of the per-thread counts, then warp totals
+      const int cnt = __popc(mask);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) wcnt[par][warp] = incl;
+      __syncthreads();
+      int off = running + incl - cnt, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
+      running += tot;
+      par ^= 1;
+      if (mask) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (mask & (1u << k)) {
+            const int s = (cword >> (8 * k)) & 0xFF;
+            list[off++] = pack_xys(c.x0 + x + k, c.y0 + row, s);
+            nIni += s >= fs.iniTh;
+            nMin += s >= fs.minTh;
+          }
+      }
+    }
+    __syncthreads();   // smem is restaged by the next band
+  }
+
+  // ---- per-cell counters (+ cost-map window sum for the introspection budgets)
+  unsigned csum = 0;
+  if (fs.weighted) {
+    const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
+    const int wt = c.ww * c.wh;
+    for (int i = tid; i < wt; i += 256) {
+      const int y = i / c.ww, x = i - y * c.ww;
+      csum += __ldg(q + (size_t)(c.wy + y) * L.pitch + c.wx + x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    nIni += __shfl_xor_sync(0xffffffffu, nIni, o);
+    nMin += __shfl_xor_sync(0xffffffffu, nMin, o);
+    csum += __shfl_xor_sync(0xffffffffu, csum, o);
+  }
+  if (lane == 0) { sred[0][warp] = nIni; sred[1][warp] = nMin; sred[2][warp] = (int)csum; }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0, b = 0; unsigned s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sred[0][w]; b += sred[1][w]; s += (unsigned)sred[2][w]; }
+    fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = make_int2(b, a);   // x: corners at minTh, y: corners at iniTh
+    fs.cellCost[img * fs.nCellsTotal + blockIdx.x] = s;
   }
 }
 

@@ -2,39 +2,77 @@
 // Replaces cv::resize(INTER_LINEAR) inside ORBextractor::ComputePyramid / ComputeQualityImagePyramid
 // (introspective_ORB_SLAM/src/ORBextractor.cc:1298-1357, resize calls at :1311 and :1341).
 // Arithmetic = OpenCV's 8-bit fixed-point bilinear path: taps and Q11 coefficients are
-// precomputed on the host exactly as OpenCV derives them; the kernel does the integer part.
-// HBM-bound stencil: each thread produces 4 adjacent output pixels (one 32-bit store), source rows are read
-// through the read-only path (L1/L2 resident: a level is at most a few MB).
+// precomputed on the host exactly as OpenCV derives them; the kernel does the integer part, separably:
+//   stage       the source rectangle of a 128x32 output tile goes to shared memory with aligned 32-bit loads
+//               (every source byte is read from L2/HBM once per tile);
+//   horizontal  T[sy][d] = src[sy][sx0]*cx0 + src[sy][sx1]*cx1 for every staged source row, kept as (T >> 4) in 16 bits
+//               (the only form the vertical pass uses) — each source row is filtered once, not once per output row;
+//   vertical    dst = (((cy0*T0) >> 16) + ((cy1*T1) >> 16) + 2) >> 2, 4 pixels per thread, one aligned 32-bit store.
+// HBM-bound stencil (read level l-1, write level l); the cascade is strictly sequential across levels.
 #pragma once
 #include "common.cuh"
 
 namespace ivg {
 
+constexpr int RZ_W = 128, RZ_H = 32;
+
 __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, int which /*0 image, 1 cost-map*/) {
+  extern __shared__ __align__(16) unsigned char rsm[];
   const LevelDev& D = fs.lv[level];
   const LevelDev& S = fs.lv[level - 1];
-  const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  if (x4 >= D.w || y >= D.h) return;
+  const int x0 = blockIdx.x * RZ_W, y0 = blockIdx.y * RZ_H;
   uint8_t* plane = (which ? fs.qual : fs.pyr) + (size_t)blockIdx.z * fs.planeBytes;
   const uint8_t* src = plane + S.planeOff;
   uint8_t* dst = plane + D.planeOff;
   const ResizeTap* tx = fs.rtab + D.rtabX;
-  const ResizeTap ty = fs.rtab[D.rtabY + y];
-  const uint8_t* r0 = src + (size_t)ty.s0 * S.pitch;
-  const uint8_t* r1 = src + (size_t)ty.s1 * S.pitch;
-  const int b0 = ty.c0, b1 = ty.c1;
-  uint32_t out = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = min(x4 + i, D.w - 1);
-    const ResizeTap t = tx[x];
-    const int t0 = __ldg(r0 + t.s0) * t.c0 + __ldg(r0 + t.s1) * t.c1;
-    const int t1 = __ldg(r1 + t.s0) * t.c0 + __ldg(r1 + t.s1) * t.c1;
-    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-    out |= (uint32_t)(v & 0xFF) << (8 * i);
+  const ResizeTap* ty = fs.rtab + D.rtabY;
+  const int tid = threadIdx.x;
+  const int x1 = min(x0 + RZ_W, D.w) - 1, y1 = min(y0 + RZ_H, D.h) - 1;
+  const int sxa = tx[x0].s0 & ~3, sxe = tx[x1].s1;           // staged source columns [sxa, sxe]
+  const int sya = ty[y0].s0, sye = ty[y1].s1;                // staged source rows [sya, sye]
+  const int nW = (sxe - sxa) / 4 + 1, nR = sye - sya + 1;
+  const int SPB = D.rzPitch;                                 // staged bytes per source row (host-computed bound, multiple of 4)
+  uint8_t* spx = rsm;
+  uint16_t* sT = reinterpret_cast<uint16_t*>(rsm + (((size_t)SPB * D.rzRows + 15) & ~(size_t)15));
+
+  for (int i = tid; i < nR * nW; i += 256) {
+    const int r = i / nW, g = i - r * nW;
+    reinterpret_cast<uint32_t*>(spx + r * SPB)[g] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(sya + r) * S.pitch + sxa + 4 * g));
   }
-  *reinterpret_cast<uint32_t*>(dst + (size_t)y * D.pitch + x4) = out;
+  __syncthreads();
+  {
+    // thread owns one output column (two threads per column, interleaved rows)
+    const int d = tid & (RZ_W - 1), half = tid >> 7;
+    if (x0 + d <= x1) {
+      const ResizeTap t = tx[x0 + d];
+      const int a0 = t.s0 - sxa, a1 = t.s1 - sxa;
+      for (int r = half; r < nR; r += 2) {
+        const uint8_t* p = spx + r * SPB;
+        sT[r * RZ_W + d] = (uint16_t)((p[a0] * t.c0 + p[a1] * t.c1) >> 4);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int g = tid & 31, seg = tid >> 5;                  // 32 groups of 4 columns x 8 row segments of 4 rows
+    const int gx = x0 + 4 * g;
+    if (gx < D.pitch && gx <= x1) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int y = y0 + seg * 4 + rr;
+        if (y > y1) break;
+        const ResizeTap t = ty[y];
+        const uint2 A = *reinterpret_cast<const uint2*>(sT + (t.s0 - sya) * RZ_W + 4 * g);
+        const uint2 B = *reinterpret_cast<const uint2*>(sT + (t.s1 - sya) * RZ_W + 4 * g);
+        const int b0 = t.c0, b1 = t.c1;
+        const int v0 = (((b0 * (int)(A.x & 0xFFFF)) >> 16) + ((b1 * (int)(B.x & 0xFFFF)) >> 16) + 2) >> 2;
+        const int v1 = (((b0 * (int)(A.x >> 16)) >> 16) + ((b1 * (int)(B.x >> 16)) >> 16) + 2) >> 2;
+        const int v2 = (((b0 * (int)(A.y & 0xFFFF)) >> 16) + ((b1 * (int)(B.y & 0xFFFF)) >> 16) + 2) >> 2;
+        const int v3 = (((b0 * (int)(A.y >> 16)) >> 16) + ((b1 * (int)(B.y >> 16)) >> 16) + 2) >> 2;
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * D.pitch + gx) = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+      }
+    }
+  }
 }
 
 }  // namespace ivg

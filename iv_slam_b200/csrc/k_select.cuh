@@ -2,11 +2,9 @@
 // (introspective_ORB_SLAM/src/ORBextractor.cc:880-1213; operator() calls it at :1248, the OctTree variant at :1247
 // is commented out — SURVEY F1).
 //
-//   k_cell_scan   one CTA per FAST cell: scans the cell's detect range of the candidate map in row-major order
-//                 (= cv::FAST's emission order), ballot-compacts the corners into the cell's list, counts how many
-//                 reach iniThFAST / minThFAST (the "<= 3 keypoints => retry with minThFAST" rule, :1045-1052 —
-//                 it counts post-NMS keypoints), and sums the cost-map over the cell window for IV-SLAM's
-//                 introspection weighting (:976-984).
+//   (k_fast_cells in k_fast.cuh produced, per cell: the row-major corner list, the corner counts at iniThFAST /
+//    minThFAST for the "<= 3 keypoints => retry with minThFAST" rule (:1045-1052, post-NMS counts) and the cost-map
+//    window sum for IV-SLAM's introspection weighting (:976-984).)
 //   k_level_select one CTA per (level, frame): thread 0 replays the sequential budget logic (cell weights :942-987,
 //                 per-cell budgets :1028-1031/:1085-1096, the one-shot redistribution loop :1101-1133);
 //                 each warp then trims cells with the replayed std::nth_element (retainBest + resize, :1146-1148),
@@ -22,62 +20,6 @@ constexpr int SEL_MAX_CELLS = 1024;      // cells per level the select kernel ca
 constexpr int SEL_LEVEL_CAP = 4096;      // level list entries kept in shared memory (else global fallback)
 constexpr int SEL_CELL_CAP = 512;        // per-warp cell list entries kept in shared memory (else global fallback)
 constexpr int SEL_WARPS = 8;
-
-__global__ void __launch_bounds__(128) k_cell_scan(FrameSet fs) {
-  const CellDev c = fs.cells[blockIdx.x];
-  const LevelDev& L = fs.lv[c.level];
-  const size_t img = blockIdx.y;
-  const uint8_t* cand = fs.cand + img * fs.planeBytes + L.planeOff;
-  uint32_t* list = fs.cellList + img * fs.listCapTotal + c.listOff;
-  __shared__ int wcnt[4];
-  __shared__ int wini[4], wmin[4];
-  __shared__ unsigned wsum[4];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int total = c.cw * c.ch;
-  int running = 0, nIni = 0, nMin = 0;
-  for (int start = 0; start < total; start += 128) {
-    const int i = start + tid;
-    int s = 0, x = 0, y = 0;
-    if (i < total) {
-      y = i / c.cw; x = i - y * c.cw;
-      s = __ldg(cand + (size_t)(c.y0 + y) * L.pitch + c.x0 + x);
-    }
-    const bool is = s != 0;                      // s >= scoreTh by construction
-    nIni += (is && s >= fs.iniTh);
-    nMin += (is && s >= fs.minTh);
-    const unsigned m = __ballot_sync(0xffffffffu, is);
-    if (lane == 0) wcnt[warp] = __popc(m);
-    __syncthreads();
-    int off = running;
-    for (int w = 0; w < warp; ++w) off += wcnt[w];
-    if (is) list[off + __popc(m & ((1u << lane) - 1))] = pack_xys(c.x0 + x, c.y0 + y, s);
-    running += wcnt[0] + wcnt[1] + wcnt[2] + wcnt[3];
-    __syncthreads();
-  }
-  // block reductions of the two counters (+ cost sum)
-  unsigned csum = 0;
-  if (fs.weighted) {
-    const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
-    const int wt = c.ww * c.wh;
-    for (int i = tid; i < wt; i += 128) {
-      const int y = i / c.ww, x = i - y * c.ww;
-      csum += __ldg(q + (size_t)(c.wy + y) * L.pitch + c.wx + x);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    nIni += __shfl_xor_sync(0xffffffffu, nIni, o);
-    nMin += __shfl_xor_sync(0xffffffffu, nMin, o);
-    csum += __shfl_xor_sync(0xffffffffu, csum, o);
-  }
-  if (lane == 0) { wini[warp] = nIni; wmin[warp] = nMin; wsum[warp] = csum; }
-  __syncthreads();
-  if (tid == 0) {
-    fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = make_int2(wmin[0] + wmin[1] + wmin[2] + wmin[3], wini[0] + wini[1] + wini[2] + wini[3]);
-    fs.cellCost[img * fs.nCellsTotal + blockIdx.x] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
-    // running == number of list entries (corners at scoreTh)
-  }
-}
 
 // response weight of IV-SLAM's introspection: 2 * (1/(1 + cost/255)) - 1, all float (src/ORBextractor.cc:1070-1071)
 __device__ __forceinline__ float introspection_weight(float cost) {
