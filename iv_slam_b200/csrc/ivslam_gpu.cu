@@ -214,12 +214,16 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     // k_fast_cells shared-memory geometry: 4 B per staged pixel (two rows packed) + 1 B per score
     L.fSP = (int)align_up(L.cellW + 9, 4);
     L.fSS = (int)align_up(L.cellW, 4) + 8;
+    L.fBW = (L.cellW + 31) / 32;
+    if (L.cellW > 512) return IVG_ERR_CAPACITY;               // pair list packs x in 9 bits
     {
-      const int perRow = 4 * L.fSP + L.fSS;
+      const int perRow = 4 * L.fSP + L.fSS + 4 * L.fBW + L.cellW;   // pixels + scores + bitmap + pair list (2 B per pair)
       int bh = (int)(FAST_SMEM_BUDGET / perRow) - 8;
-      bh = std::max(bh, 4);
+      bh = std::min(std::max(bh, 4), 200);
       L.fBH = std::min(bh, L.cellH);
-      fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + (size_t)L.fSS * (L.fBH + 4));
+      const size_t ssBytes = align_up((size_t)L.fSS * (L.fBH + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (L.fBH + 2), 16);
+      const size_t listBytes = (size_t)2 * ((L.fBH + 3) / 2) * L.cellW;
+      fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + ssBytes + bitBytes + listBytes);
     }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
     const int chW = std::max(hYlast - 6, 0);                    // weighted: every row searches this many rows

@@ -1,5 +1,5 @@
 // k_fast.cuh — K2+K3a fused: per-cell FAST-9/16 score, cell-local 3x3 non-max suppression and ordered (row-major)
-// warp-ballot compaction of the surviving corners into the cell's list.
+// compaction of the surviving corners into the cell's list.
 //
 // Replaces the per-cell cv::FAST(cellImage, kps, th, true) calls of ComputeKeyPointsOld
 // (introspective_ORB_SLAM/src/ORBextractor.cc:1045 and :1051) including their emission order, and cv::sum over the
@@ -12,16 +12,20 @@
 //   * with a cost-map the detect rows shrink to the stale window height of the last cell row: that is
 //     just a different cell table.
 //
-// Work shape: integer stencil, ~60 instructions per pixel, no data-dependent branches in the score pass.
-//   stage   the cell's pixels (+3 px ring margin) are loaded with aligned 32-bit words and stored in shared memory as
-//           one 32-bit word per pixel holding TWO vertically adjacent pixels in 16-bit lanes (pix(x,y) | pix(x,y+1)<<16),
-//           so that every ring sample of a vertical pixel pair is ONE conflict-free LDS.32 already in the packed
-//           16x2 layout of the DPX min/max instructions;
-//   score   each thread scores a vertical pixel pair: 16 packed differences and a 3-input min/max network
-//           (VIMNMX3.U16x2): min over every 9-arc = min3 of three 3-minima, 80 packed ops for 2 pixels;
-//   nms     3x3 strict maximum inside the cell, 4 pixels per thread, then ballot/scan compaction in row-major order
-//           (= cv::FAST's emission order) straight into the cell list; no atomics decide any order.
-// Tall cells are processed in bands of rows (2 score rows recomputed per band) so shared memory stays bounded.
+// Work shape: integer stencil on u8 pixels, no tensor-core shape anywhere.  Phases of one CTA (per band of cell rows):
+//   A stage    the cell's pixels (+3 px ring margin) are loaded with aligned 32-bit words and stored in shared memory
+//              as one 32-bit word per pixel holding TWO vertically adjacent pixels in 16-bit lanes
+//              (pix(x,y) | pix(x,y+1)<<16): every ring sample of a vertical pixel pair is then ONE conflict-free LDS.32
+//              that is already in the packed 16x2 layout of the DPX min/max instructions (VIMNMX[3].U16x2);
+//   B reject   every pixel pair takes the opposing-pair test on 4 of the 8 ring diameters (any 9-arc contains one end
+//              of every diameter): 8 packed differences, 14 packed min/max.  ~4 % of pixels survive; their pair
+//              positions are appended to a list (order irrelevant);
+//   C score    dense loop over the list: 16 packed differences and the exact score network — min over each 9-arc as a
+//              min3 of three 3-minima, max over arcs, both polarities: 88 packed min/max for two pixels;
+//   D nms      dense loop over the list: strict 3x3 maximum inside the cell's score map; survivors set a bit;
+//   E emit     the bitmap is scanned in row-major order (= cv::FAST's emission order): popcount + scan give every
+//              corner its slot in the cell list; the two threshold counts are reduced on the way.
+// No atomics decide any order.  Tall cells are processed in bands of rows (2 score rows recomputed per band).
 #pragma once
 #include "common.cuh"
 
@@ -30,7 +34,7 @@ namespace ivg {
 __device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 
-// T = max over arcs of (min over arc of D) combined with the dark polarity, per 16-bit lane; D[k] = 256 + centre - ring[k]
+// T = S + 257 per 16-bit lane; D[k] = 256 + centre - ring[k]
 __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
   unsigned lo3[16], hi3[16];
 #pragma unroll
@@ -58,6 +62,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char fsm[];
   __shared__ int wcnt[2][8];
   __shared__ int sred[3][8];
+  __shared__ int slistN;
 
   const CellDev c = fs.cells[blockIdx.x];
   const LevelDev& L = fs.lv[c.level];
@@ -66,13 +71,18 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
   uint32_t* list = fs.cellList + img * fs.listCapTotal + c.listOff;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cw = c.cw, ch = c.ch;
-  const int SP = L.fSP, SS = L.fSS, BH = L.fBH;
+  const int SP = L.fSP, SS = L.fSS, BH = L.fBH, BW = L.fBW;
+  // shared layout: packed pixel pairs | score bytes | survivor bitmap | pair list
   uint32_t* sp = reinterpret_cast<uint32_t*>(fsm);
+  const int ssBytes = (SS * (BH + 4) + 15) & ~15, bitBytes = (4 * BW * (BH + 2) + 15) & ~15;
   uint8_t* ss = fsm + (size_t)4 * SP * (BH + 8);
+  uint32_t* sbit = reinterpret_cast<uint32_t*>(ss + ssBytes);
+  uint16_t* slist = reinterpret_cast<uint16_t*>(ss + ssBytes + bitBytes);
   const int xa = (c.x0 - 3) & ~3;          // global x of staged column 0 (word aligned)
   const int cOff = c.x0 - xa;              // staged column of detect column 0
   const int scoreTh = fs.scoreTh;
-  const int nChunks = (cw + 31) >> 5, nG = (cw + 3) >> 2;
+  const unsigned passK = 257u + (unsigned)scoreTh;
+  const int nChunks = (cw + 31) >> 5;
 
   int running = 0, nIni = 0, nMin = 0, par = 0;
 
@@ -82,80 +92,103 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
     const int nPairs = (s1 - s0 + 1) >> 1;
     const int nWR = 2 * nPairs + 5;
 
-    // ---- stage: word row q = pixel rows (q, q+1) of global row gy0 + q
+    // ---- A: stage. word row q holds pixel rows (q, q+1) counted from global row gy0
     const int gy0 = c.y0 + s0 - 3;
-    for (int i = tid; i < nWR * (SP >> 2); i += 256) {
-      const int q = i / (SP >> 2), g = i - q * (SP >> 2);
-      const int gx = xa + 4 * g;
-      uint32_t a = 0, b = 0;
-      if (gx < L.pitch) {
-        const uint8_t* p = pix + (size_t)(gy0 + q) * L.pitch + gx;
-        a = __ldg(reinterpret_cast<const uint32_t*>(p));
-        b = __ldg(reinterpret_cast<const uint32_t*>(p + L.pitch));
+    if (tid == 0) slistN = 0;
+    for (int q = warp; q < nWR; q += 8) {
+      const uint8_t* prow = pix + (size_t)(gy0 + q) * L.pitch + xa;
+      for (int g = lane; g < (SP >> 2); g += 32) {
+        uint32_t a = 0, b = 0;
+        if (xa + 4 * g < L.pitch) {
+          a = __ldg(reinterpret_cast<const uint32_t*>(prow + 4 * g));
+          b = __ldg(reinterpret_cast<const uint32_t*>(prow + L.pitch + 4 * g));
+        }
+        uint4 o;
+        o.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu;
+        o.y = __byte_perm(a, b, 0x0501) & 0x00FF00FFu;
+        o.z = __byte_perm(a, b, 0x0602) & 0x00FF00FFu;
+        o.w = __byte_perm(a, b, 0x0703) & 0x00FF00FFu;
+        *reinterpret_cast<uint4*>(sp + q * SP + 4 * g) = o;
       }
-      uint4 o;
-      o.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu;
-      o.y = __byte_perm(a, b, 0x0501) & 0x00FF00FFu;
-      o.z = __byte_perm(a, b, 0x0602) & 0x00FF00FFu;
-      o.w = __byte_perm(a, b, 0x0703) & 0x00FF00FFu;
-      *reinterpret_cast<uint4*>(sp + q * SP + 4 * g) = o;
     }
-    for (int i = tid; i < (SS >> 2) * (s1 - s0 + 2); i += 256) reinterpret_cast<uint32_t*>(ss)[i] = 0;
+    {
+      uint4* z = reinterpret_cast<uint4*>(ss);                // scores + bitmap are contiguous
+      for (int i = tid; i < ((ssBytes + bitBytes) >> 4); i += 256) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
 
-    // ---- score: one vertical pixel pair per thread
+    // ---- B: opposing-pair rejection on diameters 0-8, 2-10, 4-12, 6-14
     for (int it = warp; it < nPairs * nChunks; it += 8) {
-      const int p = it / nChunks, x = (it - p * nChunks) * 32 + lane;
-      if (x < cw) {
-        const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
-        const unsigned C = ctr[0] + 0x01000100u;
-        unsigned D[16];
-        D[0] = C - ctr[3 * SP];          D[1] = C - ctr[3 * SP + 1];      D[2] = C - ctr[2 * SP + 2];      D[3] = C - ctr[SP + 3];
-        D[4] = C - ctr[3];               D[5] = C - ctr[-SP + 3];         D[6] = C - ctr[-2 * SP + 2];     D[7] = C - ctr[-3 * SP + 1];
-        D[8] = C - ctr[-3 * SP];         D[9] = C - ctr[-3 * SP - 1];     D[10] = C - ctr[-2 * SP - 2];    D[11] = C - ctr[-SP - 3];
-        D[12] = C - ctr[-3];             D[13] = C - ctr[SP - 3];         D[14] = C - ctr[2 * SP - 2];     D[15] = C - ctr[3 * SP - 1];
-        const unsigned T = fast_score_pair(D);
-        int sA = (int)(T & 0xFFFFu) - 257, sB = (int)(T >> 16) - 257;
-        sA = sA >= scoreTh ? sA : 0;
-        sB = sB >= scoreTh ? sB : 0;
-        uint8_t* o = ss + (2 * p + 1) * SS + 4 + x;
-        o[0] = (uint8_t)sA;
-        if (s0 + 2 * p + 1 < s1) o[SS] = (uint8_t)sB;
-      }
-    }
-    __syncthreads();
-
-    // ---- NMS + ordered compaction over detect rows [r0, r1)
-    const int nItems = (r1 - r0) * nG;
-    for (int base = 0; base < nItems; base += 256) {
-      const int i = base + tid;
-      unsigned mask = 0;
-      uint32_t cword = 0;
-      int row = 0, x = 0;
-      if (i < nItems) {
-        row = r0 + i / nG; x = (i % nG) * 4;
-        const uint8_t* sr = ss + (row - s0 + 1) * SS + 4 + x;
-        cword = *reinterpret_cast<const uint32_t*>(sr);
-        if (cword) {
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(sr);
-          const int SW = SS >> 2;
-          const unsigned long long up = ((unsigned long long)w[-SW + 1] << 40) | ((unsigned long long)w[-SW] << 8) | (w[-SW - 1] >> 24);
-          const unsigned long long md = ((unsigned long long)w[1] << 40) | ((unsigned long long)cword << 8) | (w[-1] >> 24);
-          const unsigned long long dn = ((unsigned long long)w[SW + 1] << 40) | ((unsigned long long)w[SW] << 8) | (w[SW - 1] >> 24);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int cc = (int)((md >> (8 * (k + 1))) & 0xFF);
-            if (cc == 0) continue;
-            const int l = (int)((md >> (8 * k)) & 0xFF), r = (int)((md >> (8 * (k + 2))) & 0xFF);
-            const int u0 = (int)((up >> (8 * k)) & 0xFF), u1 = (int)((up >> (8 * (k + 1))) & 0xFF), u2 = (int)((up >> (8 * (k + 2))) & 0xFF);
-            const int d0 = (int)((dn >> (8 * k)) & 0xFF), d1 = (int)((dn >> (8 * (k + 1))) & 0xFF), d2 = (int)((dn >> (8 * (k + 2))) & 0xFF);
-            const int m = max(max(max(l, r), max(u0, u1)), max(max(u2, d0), max(d1, d2)));
-            if (cc > m) mask |= 1u << k;
-          }
+      const int p = it / nChunks;
+      const uint32_t* rowc = sp + (2 * p + 3) * SP + cOff;
+      {
+        const int x = (it - p * nChunks) * 32 + lane;
+        bool pass = false;
+        if (x < cw) {
+          const uint32_t* ctr = rowc + x;
+          const unsigned C = ctr[0] + 0x01000100u;
+          const unsigned D0 = C - ctr[3 * SP], D8 = C - ctr[-3 * SP];
+          const unsigned D2 = C - ctr[2 * SP + 2], D10 = C - ctr[-2 * SP - 2];
+          const unsigned D4 = C - ctr[3], D12 = C - ctr[-3];
+          const unsigned D6 = C - ctr[-2 * SP + 2], D14 = C - ctr[2 * SP - 2];
+          const unsigned a = __vminu2(vmin3(__vmaxu2(D0, D8), __vmaxu2(D2, D10), __vmaxu2(D4, D12)), __vmaxu2(D6, D14));
+          const unsigned b = __vmaxu2(vmax3(__vminu2(D0, D8), __vminu2(D2, D10), __vminu2(D4, D12)), __vminu2(D6, D14));
+          const unsigned t = __vmaxu2(a, 0x02000200u - b);
+          pass = ((t & 0xFFFFu) >= passK) | ((t >> 16) >= passK);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&slistN, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (pass) slist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(p * 512 + x);   // cw <= 512 enforced by the host
         }
       }
-      // ordered offsets: inclusive warp scan of the per-thread counts, then warp totals
-      const int cnt = __popc(mask);
+    }
+    __syncthreads();
+
+    // ---- C: exact score of the surviving pairs
+    const int nList = slistN;
+    for (int j = tid; j < nList; j += 256) {
+      const int e = slist[j], p = e >> 9, x = e & 511;
+      const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
+      const unsigned C = ctr[0] + 0x01000100u;
+      unsigned D[16];
+      D[0] = C - ctr[3 * SP];          D[1] = C - ctr[3 * SP + 1];      D[2] = C - ctr[2 * SP + 2];      D[3] = C - ctr[SP + 3];
+      D[4] = C - ctr[3];               D[5] = C - ctr[-SP + 3];         D[6] = C - ctr[-2 * SP + 2];     D[7] = C - ctr[-3 * SP + 1];
+      D[8] = C - ctr[-3 * SP];         D[9] = C - ctr[-3 * SP - 1];     D[10] = C - ctr[-2 * SP - 2];    D[11] = C - ctr[-SP - 3];
+      D[12] = C - ctr[-3];             D[13] = C - ctr[SP - 3];         D[14] = C - ctr[2 * SP - 2];     D[15] = C - ctr[3 * SP - 1];
+      const unsigned T = fast_score_pair(D);
+      int sA = (int)(T & 0xFFFFu) - 257, sB = (int)(T >> 16) - 257;
+      sA = sA >= scoreTh ? sA : 0;
+      sB = sB >= scoreTh ? sB : 0;
+      uint8_t* o = ss + (2 * p + 1) * SS + 4 + x;
+      o[0] = (uint8_t)sA;
+      if (s0 + 2 * p + 1 < s1) o[SS] = (uint8_t)sB;
+    }
+    __syncthreads();
+
+    // ---- D: 3x3 strict maximum inside the cell (zero border = "no score outside the cell")
+    for (int j = tid; j < 2 * nList; j += 256) {
+      const int e = slist[j >> 1], p = e >> 9, x = e & 511, half = j & 1;
+      const int srow = 2 * p + half;                       // score row relative to s0
+      const int row = s0 + srow;                           // detect row of the cell
+      if (row < r0 || row >= r1) continue;                 // overlap rows belong to the neighbouring band
+      const uint8_t* s = ss + (srow + 1) * SS + 4 + x;
+      const int v = s[0];
+      if (v == 0) continue;
+      const int m = max(max(max((int)s[-1], (int)s[1]), max((int)s[-SS - 1], (int)s[-SS])),
+                        max(max((int)s[-SS + 1], (int)s[SS - 1]), max((int)s[SS], (int)s[SS + 1])));
+      if (v > m) atomicOr(&sbit[(row - r0) * BW + (x >> 5)], 1u << (x & 31));
+    }
+    __syncthreads();
+
+    // ---- E: emit in row-major order
+    const int nWords = (r1 - r0) * BW;
+    for (int base = 0; base < nWords; base += 256) {
+      const int i = base + tid;
+      unsigned bits = i < nWords ? sbit[i] : 0u;
+      const int cnt = __popc(bits);
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -169,15 +202,17 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
       for (int w = 0; w < 8; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
       running += tot;
       par ^= 1;
-      if (mask) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (mask & (1u << k)) {
-            const int s = (cword >> (8 * k)) & 0xFF;
-            list[off++] = pack_xys(c.x0 + x + k, c.y0 + row, s);
-            nIni += s >= fs.iniTh;
-            nMin += s >= fs.minTh;
-          }
+      if (bits) {
+        const int row = i / BW, xb = (i - row * BW) * 32;
+        const uint8_t* srow = ss + (r0 + row - s0 + 1) * SS + 4 + xb;
+        while (bits) {
+          const int k = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int s = srow[k];
+          list[off++] = pack_xys(c.x0 + xb + k, c.y0 + r0 + row, s);
+          nIni += s >= fs.iniTh;
+          nMin += s >= fs.minTh;
+        }
       }
     }
     __syncthreads();   // smem is restaged by the next band
@@ -187,10 +222,9 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
   unsigned csum = 0;
   if (fs.weighted) {
     const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
-    const int wt = c.ww * c.wh;
-    for (int i = tid; i < wt; i += 256) {
-      const int y = i / c.ww, x = i - y * c.ww;
-      csum += __ldg(q + (size_t)(c.wy + y) * L.pitch + c.wx + x);
+    for (int y = warp; y < c.wh; y += 8) {
+      const uint8_t* qr = q + (size_t)(c.wy + y) * L.pitch + c.wx;
+      for (int x = lane; x < c.ww; x += 32) csum += __ldg(qr + x);
     }
   }
 #pragma unroll

@@ -1,0 +1,27 @@
+"""Per-kernel device time with ONE stream active (no L/R overlap): us per image for each kernel (developer tool)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from iv_slam_b200 import api, synthetic as S
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+L, R = S.make_stereo_batch(1241, 376, n, 100, distinct=16)
+a = (2000, 1.2, 8, 20, 7)
+gL, gR = api.ORBextractor(*a), api.ORBextractor(*a)
+gL.upload(L); gR.upload(R)
+def step():
+    gL.run(); gL.sync(); gR.run(); gR.sync()
+    rc = api.lib().ivg_stereo_match_batch(gL._h, gR._h, 386.1448, 718.856, None, None, gL.cap, 1)
+    assert rc == 0
+step()
+gL.profile_enable(True); gR.profile_enable(True)
+for _ in range(steps): step()
+pl, pr = gL.profile_read(), gR.profile_read()
+tot = 0
+for k in pl:
+    ms = pl[k][0] + pr[k][0]
+    per = ms * 1e3 / (steps * (n if k.startswith('k_stereo') else 2 * n))
+    tot += per * (1 if k.startswith('k_stereo') else 2)
+    print('%-20s %8.3f ms/step  %7.3f us per %s' % (k, ms / steps, per, 'pair' if k.startswith('k_stereo') else 'image'))
+print('sum per pair %.2f us -> %.0f pairs/s if serial' % (tot, 1e6 / tot))
