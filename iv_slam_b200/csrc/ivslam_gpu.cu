@@ -94,7 +94,8 @@ struct ivg_extractor {
   DevBuf<uint32_t> cellList, cellCost;
   DevBuf<int2> cellCount;
   DevBuf<uint2> workCell, workLevel, levelKp;
-  DevBuf<int> levelCount, outN, sad, nExt;
+  DevBuf<int> levelCount, outN, sad, nExt, rowStart;
+  DevBuf<uint4> sortedR;
   DevBuf<float> uRight, depth;
   // stereo on caller-supplied keypoints
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
@@ -353,7 +354,7 @@ int launch_extract(ivg_extractor* h) {
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, sizeof(SelShared), h->stream>>>(fs); }
-  { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + 7) / 8, fs.nImages), 256, 0, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs); }
   CK(cudaGetLastError());
   h->haveResults = true; h->havePyramid = true;
   return IVG_OK;
@@ -362,7 +363,14 @@ int launch_extract(ivg_extractor* h) {
 
 int init_device_constants(int device) {
   CK(cudaSetDevice(device));
-  CK(cudaMemcpyToSymbol(c_pattern, kPatternHost, sizeof(kPatternHost)));
+  {
+    std::vector<float2> pt(512);
+    for (int i = 0; i < 512; ++i) {   // pattern point i = byte*16 + k  ->  slot k*32 + byte
+      const int byte = i >> 4, k = i & 15;
+      pt[k * 32 + byte] = make_float2((float)kPatternHost[2 * i], (float)kPatternHost[2 * i + 1]);
+    }
+    CK(cudaMemcpyToSymbol(g_patternT, pt.data(), sizeof(float2) * 512));
+  }
   CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
   CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -423,9 +431,11 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
       done[device] = true;
     }
   }
-  int um[16];
-  for (int i = 0; i < 16; ++i) um[i] = h->umax[i];
-  if (cudaMemcpyToSymbol(c_umax, um, sizeof(um)) != cudaSuccess) { g_cuda_err = "cudaMemcpyToSymbol(c_umax)"; delete h; return IVG_ERR_CUDA; }
+  {
+    static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // compiled into k_orient_describe
+    for (int i = 0; i < 16; ++i)
+      if (h->umax[i] != kUmax[i]) { g_cuda_err = "umax table mismatch"; delete h; return IVG_ERR_INVALID; }
+  }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->evDone, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->evT0) != cudaSuccess || cudaEventCreate(&h->evT1) != cudaSuccess) {
@@ -443,7 +453,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
-  h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release();
+  h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->sortedR.release(); h->rowStart.release();
   for (cudaEvent_t e : h->profEv) cudaEventDestroy(e);
   if (h->evDone) cudaEventDestroy(h->evDone);
   if (h->evT0) cudaEventDestroy(h->evT0);
@@ -619,8 +629,13 @@ int ivg_get_level_keypoints(ivg_extractor* h, int index, int level, float* x, fl
 }
 
 // ---------------------------------------------------------------------------------------- stereo
-static int stereo_launch(ivg_extractor* left, ivg_extractor* right, const StereoArgs& A, int nPairs) {
+static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& A, int nPairs) {
   const FrameSet fs = active_fs(left);
+  int rc;
+  if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (A.nRows + 1)))) return rc;
+  A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
+  A.bandMargin = (int)std::ceil(2.0f * left->scale[left->nlevels - 1]) + 2;
+  { ProfScope ps(left, IVG_K_STEREO); k_stereo_index<<<nPairs, 256, (A.nRows + 1) * sizeof(int), left->stream>>>(A); }
   { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + 7) / 8, nPairs), 256, 0, left->stream>>>(fs, A); }
   { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());

@@ -1,24 +1,26 @@
-// k_describe.cuh — K4+K6 fused: intensity-centroid orientation and 256-bit rotated-BRIEF descriptor,
-// one warp per keypoint.
+// k_describe.cuh — K4+K6 fused: intensity-centroid orientation and 256-bit rotated-BRIEF descriptor.
 //
 // Replaces computeOrientation/IC_Angle (introspective_ORB_SLAM/src/ORBextractor.cc:478-485, :78-105) and
 // computeDescriptors/computeOrbDescriptor (:1215-1222, :108-148), plus the final bookkeeping of operator()
 // (:1263-1295): level-major concatenation, pt *= scale for levels > 0, size/octave/class_id fields.
-//   * IC_Angle reads the UNBLURRED level: 31 lanes each own one column u of the circular patch (rows bounded by umax),
-//     integer moments are exact and order-free, the angle is cv::fastAtan2's float polynomial without FMA;
-//   * the descriptor reads the BLURRED level: each lane owns one descriptor byte = 8 pattern pairs = 16 rotated
-//     samples; rotation uses float mul/add without contraction and cvRound = round-half-even (A.5); cos/sin are
-//     evaluated in double and rounded to float (the reference calls glibc cosf/sinf; measured disagreement of the
-//     two is ~1 descriptor bit in 5e7, SURVEY Q9 — this is the only source of non-identical descriptor bits).
-// The 37x37 footprint of one keypoint is read through L1 (read-only path); pattern table is staged in shared
-// memory transposed so that lane-strided reads are conflict-free.
+//
+// One CTA = 32 keypoint slots, one warp per keypoint (4 keypoints per warp), three phases:
+//   moments  IC_Angle reads the UNBLURRED level: 31 lanes each own one column u of the circular patch (rows bounded by
+//            the compile-time umax table), integer moments are exact and order-free;
+//   angle    ONE lane per keypoint: cv::fastAtan2's float polynomial without FMA and cos/sin of the angle
+//            evaluated in double and rounded to float — 32 keypoints share one pass through the double-precision code
+//            instead of every warp repeating it (the reference calls glibc cosf/sinf; measured disagreement of the two
+//            is ~1 descriptor bit in 5e7, SURVEY Q9 — the only source of non-identical descriptor bits);
+//   brief    the descriptor reads the BLURRED level: each lane owns one descriptor byte = 8 pattern pairs = 16 rotated
+//            samples; rotation uses float mul/add without contraction and cvRound = round-half-even (A.5).
+// The 37x37 footprint of a keypoint is read through L1 (read-only path); the pattern table is staged in shared
+// memory as float2, transposed so that lane-strided reads are conflict-free.
 #pragma once
 #include "common.cuh"
 
 namespace ivg {
 
-__constant__ int8_t c_pattern[1024];     // 256 x (x0,y0,x1,y1)
-__constant__ int c_umax[16];
+__device__ float2 g_patternT[512];       // [k*32 + byte] = pattern point (byte*16 + k) as floats, filled by the host
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   const float sc = (float)(180.0 / 3.14159265358979323846);
@@ -40,94 +42,121 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-struct KpRecord { float x, y, size, angle, response; int octave, class_id; };
+constexpr int DK_SLOTS = 32;             // keypoint slots per CTA
 
 __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs) {
-  __shared__ int16_t spat[512];          // [k][lane]: sample k (0..15) of descriptor byte `lane`, x | y<<8
+  __shared__ float2 spat[512];
+  __shared__ int sCx[DK_SLOTS], sCy[DK_SLOTS], sLevel[DK_SLOTS], sOut[DK_SLOTS];
+  __shared__ float sM01[DK_SLOTS], sM10[DK_SLOTS], sAngle[DK_SLOTS], sA[DK_SLOTS], sB[DK_SLOTS], sResp[DK_SLOTS];
+  // umax of a radius-15 circular patch (src/ORBextractor.cc:458-475); the host checks its own table against this one
+  constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 512; i += 256) {
-    const int byte = i >> 4, k = i & 15;   // pattern point index i = byte*16 + k
-    spat[k * 32 + byte] = (int16_t)((uint8_t)c_pattern[2 * i] | ((int)c_pattern[2 * i + 1] << 8));
+  const size_t img = blockIdx.y;
+  const int* lc = fs.levelCount + img * MAX_LEVELS;
+  for (int i = tid; i < 512; i += 256) spat[i] = g_patternT[i];
+
+  if (tid < DK_SLOTS) {
+    const int slot = blockIdx.x * DK_SLOTS + tid;
+    int level = -1, cx = 0, cy = 0, outIdx = 0;
+    float resp = 0.f;
+    if (slot < fs.kpCap) {
+      int l = 0;
+      for (int k = 1; k < fs.nlevels; ++k)
+        if (slot >= fs.lv[k].kpOff) l = k;
+      const int i = slot - fs.lv[l].kpOff;
+      if (i < lc[l]) {
+        int base = 0;
+        for (int k = 0; k < l; ++k) base += lc[k];
+        const uint2 rec = fs.levelKp[img * fs.kpCap + slot];
+        level = l; cx = unpack_x(rec.y); cy = unpack_y(rec.y); outIdx = base + i; resp = __uint_as_float(rec.x);
+      }
+    }
+    sLevel[tid] = level; sCx[tid] = cx; sCy[tid] = cy; sOut[tid] = outIdx; sResp[tid] = resp;
+    if (blockIdx.x == 0 && tid == 0) {
+      int n = 0;
+      for (int l = 0; l < fs.nlevels; ++l) n += lc[l];
+      fs.outN[img] = n;
+    }
   }
   __syncthreads();
 
-  const size_t img = blockIdx.y;
-  const int slot = blockIdx.x * 8 + warp;
-  if (slot >= fs.kpCap) return;
-  const int* lc = fs.levelCount + img * MAX_LEVELS;
-  int level = 0, outBase = 0;
+  // ---- moments
 #pragma unroll 1
-  for (int l = 1; l < fs.nlevels; ++l)
-    if (slot >= fs.lv[l].kpOff) level = l;
-  for (int l = 0; l < level; ++l) outBase += lc[l];
-  const LevelDev& L = fs.lv[level];
-  const int i = slot - L.kpOff;
-  if (slot == 0 && lane == 0) {
-    int n = 0;
-    for (int l = 0; l < fs.nlevels; ++l) n += lc[l];
-    fs.outN[img] = n;
-  }
-  if (i >= lc[level]) return;
-  const uint2 rec = fs.levelKp[img * fs.kpCap + slot];
-  const int cx = unpack_x(rec.y), cy = unpack_y(rec.y);
-  const size_t frameOff = img * fs.planeBytes + L.planeOff;
-
-  // ---- IC_Angle on the unblurred level
-  const uint8_t* ctr = fs.pyr + frameOff + (size_t)cy * L.pitch + cx;
-  int m10 = 0, m01 = 0;
-  {
-    const int u = lane - HALF_PATCH;
+  for (int q = 0; q < DK_SLOTS / 8; ++q) {
+    const int j = warp * (DK_SLOTS / 8) + q;
+    const int level = sLevel[j];
+    if (level < 0) continue;
+    const LevelDev& L = fs.lv[level];
+    const uint8_t* ctr = fs.pyr + img * fs.planeBytes + L.planeOff + (size_t)sCy[j] * L.pitch + sCx[j];
+    const int u = lane - HALF_PATCH, au = abs(u), pitch = L.pitch;
+    int colsum = 0, m01 = 0;
     if (lane <= 2 * HALF_PATCH) {
-      const int au = abs(u);
-#pragma unroll 1
-      for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) {
-        if (au <= c_umax[abs(v)]) {
-          const int val = __ldg(ctr + v * L.pitch + u);
-          m10 += u * val;
-          m01 += v * val;
+      colsum = __ldg(ctr + u);
+#pragma unroll
+      for (int v = 1; v <= HALF_PATCH; ++v) {
+        if (au <= UMAX[v]) {
+          const int a = __ldg(ctr + v * pitch + u), b = __ldg(ctr - v * pitch + u);
+          colsum += a + b;
+          m01 += v * (a - b);
         }
       }
     }
-  }
+    int m10 = u * colsum;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    for (int o = 16; o; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    if (lane == 0) { sM01[j] = (float)m01; sM10[j] = (float)m10; }
   }
-  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  __syncthreads();
 
-  // ---- rotated BRIEF on the blurred level
-  const float factorPI = (float)(3.14159265358979323846 / 180.f);
-  const float rad = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-  const uint8_t* bctr = fs.blur + frameOff + (size_t)cy * L.pitch + cx;
-  unsigned val = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int p0 = spat[(2 * k) * 32 + lane], p1 = spat[(2 * k + 1) * 32 + lane];
-    const float x0 = (float)(int8_t)(p0 & 0xFF), y0 = (float)(p0 >> 8);
-    const float x1 = (float)(int8_t)(p1 & 0xFF), y1 = (float)(p1 >> 8);
-    const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-    const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-    const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-    const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = __ldg(bctr + iy0 * L.pitch + ix0), t1 = __ldg(bctr + iy1 * L.pitch + ix1);
-    val |= (t0 < t1 ? 1u : 0u) << k;
+  // ---- angle, cos, sin: one lane per keypoint
+  if (tid < DK_SLOTS && sLevel[tid] >= 0) {
+    const float angle = fast_atan2_deg(sM01[tid], sM10[tid]);
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float rad = __fmul_rn(angle, factorPI);
+    double sn, cs;
+    sincos((double)rad, &sn, &cs);
+    sAngle[tid] = angle; sA[tid] = (float)cs; sB[tid] = (float)sn;
   }
-  const int outIdx = outBase + i;
-  fs.outDesc[(img * fs.kpCap + outIdx) * 32 + lane] = (uint8_t)val;
-  if (lane == 0) {
-    KpRecord r;
-    r.x = level ? __fmul_rn((float)cx, L.scale) : (float)cx;
-    r.y = level ? __fmul_rn((float)cy, L.scale) : (float)cy;
-    r.size = L.sizeField;
-    r.angle = angle;
-    r.response = __uint_as_float(rec.x);
-    r.octave = level;
-    r.class_id = -1;
-    float* o = reinterpret_cast<float*>(fs.outKp + (img * fs.kpCap + outIdx) * 28);
-    o[0] = r.x; o[1] = r.y; o[2] = r.size; o[3] = r.angle; o[4] = r.response;
-    reinterpret_cast<int*>(o)[5] = r.octave; reinterpret_cast<int*>(o)[6] = r.class_id;
+  __syncthreads();
+
+  // ---- rotated BRIEF + output record
+#pragma unroll 1
+  for (int q = 0; q < DK_SLOTS / 8; ++q) {
+    const int j = warp * (DK_SLOTS / 8) + q;
+    const int level = sLevel[j];
+    if (level < 0) continue;
+    const LevelDev& L = fs.lv[level];
+    const int cx = sCx[j], cy = sCy[j], pitch = L.pitch;
+    const uint8_t* bctr = fs.blur + img * fs.planeBytes + L.planeOff + (size_t)cy * pitch + cx;
+    const float a = sA[j], b = sB[j];
+    unsigned val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 p0 = spat[(2 * k) * 32 + lane], p1 = spat[(2 * k + 1) * 32 + lane];
+      const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(p0.x, b), __fmul_rn(p0.y, a)));
+      const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)));
+      const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)));
+      const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(p1.x, a), __fmul_rn(p1.y, b)));
+      const int t0 = __ldg(bctr + iy0 * pitch + ix0), t1 = __ldg(bctr + iy1 * pitch + ix1);
+      val |= (t0 < t1 ? 1u : 0u) << k;
+    }
+    const int outIdx = sOut[j];
+    fs.outDesc[(img * fs.kpCap + outIdx) * 32 + lane] = (uint8_t)val;
+    if (lane < 7) {
+      float f;
+      if (lane == 0) f = level ? __fmul_rn((float)cx, L.scale) : (float)cx;
+      else if (lane == 1) f = level ? __fmul_rn((float)cy, L.scale) : (float)cy;
+      else if (lane == 2) f = L.sizeField;
+      else if (lane == 3) f = sAngle[j];
+      else if (lane == 4) f = sResp[j];
+      else if (lane == 5) f = __int_as_float(level);
+      else f = __int_as_float(-1);
+      reinterpret_cast<float*>(fs.outKp + (img * fs.kpCap + outIdx) * 28)[lane] = f;
+    }
   }
 }
 

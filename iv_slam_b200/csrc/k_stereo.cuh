@@ -1,12 +1,15 @@
 // k_stereo.cuh — K7-K10: Frame::ComputeStereoMatches (introspective_ORB_SLAM/src/Frame.cc:758-932).
 //
+//   k_stereo_index   one CTA per stereo pair: counting sort of the right keypoints by image row (int)y into a CSR
+//       table (the reference's vRowIndices build, :768-785, stores every keypoint in all rows of its band; here each
+//       keypoint is stored once and the band test is applied by the searcher).
 //   k_stereo_match   one warp per left keypoint.
-//     * candidate search (:787-841): the reference builds vRowIndices (for every image row, the right keypoints whose
-//       band [floor(y-r), ceil(y+r)], r = 2*scale[octave], covers it; :768-785) and scans the list of row (int)vL.
-//       Candidate membership is a pure predicate of (left kp, right kp), and the winner is the minimum of
-//       (Hamming distance, iR) because the list is in ascending iR and the update is a strict '<' starting from
-//       TH_HIGH=100 (src/ORBmatcher.cc:37) — so lanes test right keypoints in parallel and a warp arg-min over the
-//       packed (dist<<16 | iR) reproduces the result exactly.  Distance = popcount of 8 xor-ed words
+//     * candidate search (:787-841): the reference scans the list of row (int)vL, i.e. the right keypoints whose
+//       band [floor(y-r), ceil(y+r)], r = 2*scale[octave], covers that row.  Candidate membership is a pure predicate
+//       of (left kp, right kp), and the winner is the minimum of (Hamming distance, iR) because the list is in
+//       ascending iR and the update is a strict '<' starting from TH_HIGH=100 (src/ORBmatcher.cc:37) — so lanes test
+//       the right keypoints of the rows within the widest possible band in parallel (any order) and a warp arg-min
+//       over the packed (dist<<16 | iR) reproduces the result exactly.  Distance = popcount of 8 xor-ed words
 //       (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1700-1716).
 //     * SAD refinement (:843-915): 11x11 window around the rounded level coordinates in the left keypoint's octave of
 //       the UNBLURRED pyramids, 11 horizontal shifts, each patch minus its own centre, L1 norm (integers, exact),
@@ -30,9 +33,49 @@ struct StereoArgs {
   float mbf, maxD;
   float* uRight; float* depth; int* sad;                     // [nPairs][cap]
   int* bestDist;                                             // optional debug [nPairs][cap] or null
+  uint4* sorted;                                             // [nPairs][cap] right keypoints bucketed by row: (x bits, y bits, octave, iR)
+  int* rowStart;                                             // [nPairs][nRows + 1]
+  int bandMargin;                                            // rows to scan either side of (int)vL: ceil(2*scale[last]) + 2
 };
 
 constexpr int TH_HIGH = 100, TH_LOW = 50;
+
+__global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
+  extern __shared__ int ssh[];               // nRows + 1 counters, then the scatter cursors in place
+  __shared__ int wsum[8];
+  const size_t pair = blockIdx.x;
+  const int Nr = A.nR[pair], nRows = A.nRows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t* kr0 = A.kpR + pair * A.cap * 28;
+  for (int i = tid; i <= nRows; i += 256) ssh[i] = 0;
+  __syncthreads();
+  for (int iR = tid; iR < Nr; iR += 256) {
+    const float y = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28)[1];
+    atomicAdd(&ssh[min(max((int)y, 0), nRows - 1)], 1);
+  }
+  __syncthreads();
+  // exclusive scan over nRows+1 entries: each thread owns a contiguous chunk
+  const int per = (nRows + 1 + 255) / 256, b0 = tid * per, b1 = min(b0 + per, nRows + 1);
+  int local = 0;
+  for (int i = b0; i < b1; ++i) local += ssh[i];
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int base = incl - local;
+  for (int w = 0; w < warp; ++w) base += wsum[w];
+  int* rs = A.rowStart + pair * (size_t)(nRows + 1);
+  for (int i = b0; i < b1; ++i) { const int c = ssh[i]; ssh[i] = base; rs[i] = base; base += c; }
+  __syncthreads();
+  uint4* out = A.sorted + pair * A.cap;
+  for (int iR = tid; iR < Nr; iR += 256) {
+    const float* kr = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28);
+    const float x = kr[0], y = kr[1];
+    const int oct = reinterpret_cast<const int*>(kr)[5];
+    const int pos = atomicAdd(&ssh[min(max((int)y, 0), nRows - 1)], 1);   // order inside a row is irrelevant (arg-min is order-free)
+    out[pos] = make_uint4(__float_as_uint(x), __float_as_uint(y), (unsigned)oct, (unsigned)iR);
+  }
+}
 
 __global__ void __launch_bounds__(256) k_stereo_match(FrameSet fs, StereoArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -57,23 +100,25 @@ __global__ void __launch_bounds__(256) k_stereo_match(FrameSet fs, StereoArgs A)
 #pragma unroll
     for (int k = 0; k < 8; ++k) dl[k] = __ldg(d + k);
   }
-  if (row >= 0 && row < A.nRows && !(maxU < 0)) {
-    const uint8_t* kr0 = A.kpR + pair * A.cap * 28;
+  if (row >= 0 && row < A.nRows && !(maxU < 0) && Nr > 0) {
     const uint8_t* dr0 = A.descR + pair * A.cap * 32;
-    for (int iR = lane; iR < Nr; iR += 32) {
-      const float* kr = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28);
-      const int octR = reinterpret_cast<const int*>(kr)[5];
+    const int* rs = A.rowStart + pair * (size_t)(A.nRows + 1);
+    const uint4* srt = A.sorted + pair * A.cap;
+    const int jb = __ldg(rs + max(row - A.bandMargin, 0)), je = __ldg(rs + min(row + A.bandMargin + 1, A.nRows));
+    for (int j = jb + lane; j < je; j += 32) {
+      const uint4 e = __ldg(srt + j);
+      const int octR = (int)e.z;
       if (octR < levelL - 1 || octR > levelL + 1) continue;
-      const float uR = kr[0], kpY = kr[1];
+      const float uR = __uint_as_float(e.x), kpY = __uint_as_float(e.y);
       if (!(uR >= minU && uR <= maxU)) continue;
       const float r = __fmul_rn(2.0f, fs.lv[octR].scale);
       const int maxr = (int)ceilf(__fadd_rn(kpY, r)), minr = (int)floorf(__fsub_rn(kpY, r));
       if (row < minr || row > maxr) continue;
-      const uint32_t* d = reinterpret_cast<const uint32_t*>(dr0 + (size_t)iR * 32);
-      int dist = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dist += __popc(dl[k] ^ __ldg(d + k));
-      if (dist < TH_HIGH) best = min(best, ((unsigned)dist << 16) | (unsigned)iR);
+      const uint4* d = reinterpret_cast<const uint4*>(dr0 + (size_t)e.w * 32);
+      const uint4 da = __ldg(d), db = __ldg(d + 1);
+      const int dist = __popc(dl[0] ^ da.x) + __popc(dl[1] ^ da.y) + __popc(dl[2] ^ da.z) + __popc(dl[3] ^ da.w) +
+                       __popc(dl[4] ^ db.x) + __popc(dl[5] ^ db.y) + __popc(dl[6] ^ db.z) + __popc(dl[7] ^ db.w);
+      if (dist < TH_HIGH) best = min(best, ((unsigned)dist << 16) | e.w);
     }
   }
 #pragma unroll
