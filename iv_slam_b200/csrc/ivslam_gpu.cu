@@ -87,7 +87,7 @@ struct ivg_extractor {
   bool curWeighted = false;
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
-  DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc;
+  DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
   size_t fastSmem = 0, resizeSmem = 0;
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
@@ -218,12 +218,13 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.fBW = (L.cellW + 31) / 32;
     if (L.cellW > 512) return IVG_ERR_CAPACITY;               // pair list packs x in 9 bits
     {
-      const int perRow = 4 * L.fSP + L.fSS + 4 * L.fBW + L.cellW;   // pixels + scores + bitmap + pair list (2 B per pair)
+      const int perRow = 4 * L.fSP + L.fSS + 4 * L.fBW + 32 * L.fBW + 32;   // pixels + scores + bitmap + pair list (2 B per pair)
       int bh = (int)(FAST_SMEM_BUDGET / perRow) - 8;
       bh = std::min(std::max(bh, 4), 200);
       L.fBH = std::min(bh, L.cellH);
       const size_t ssBytes = align_up((size_t)L.fSS * (L.fBH + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (L.fBH + 2), 16);
-      const size_t listBytes = (size_t)2 * ((L.fBH + 3) / 2) * L.cellW;
+      L.fSeg = ((((L.fBH + 3) / 2) * L.fBW + 7) / 8) * 32;
+      const size_t listBytes = (size_t)2 * 8 * L.fSeg;
       fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + ssBytes + bitBytes + listBytes);
     }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
@@ -449,7 +450,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release();
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release();
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
@@ -500,9 +501,21 @@ int ivg_device_input(ivg_extractor* h, int index, int which, void** dev_ptr, siz
   return IVG_OK;
 }
 
-static int copy_frames_in(ivg_extractor* h, uint8_t* plane, int n, const uint8_t* src, size_t stride, size_t frame_bytes) {
+static int copy_frames_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& stage, int n, const uint8_t* src, size_t stride, size_t frame_bytes) {
   const FrameSet& fs = h->fs;
   const size_t dpitch = fs.lv[0].pitch;
+  if (stride == (size_t)h->W && frame_bytes == (size_t)h->W * h->H) {
+    // contiguous frames: one linear DMA + on-device re-pitch
+    const size_t bytes = (size_t)n * frame_bytes;
+    int rc = stage.alloc(bytes + 16);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid(((h->W + 3) / 4 + 255) / 256, h->H, n);
+    k_ingest<<<grid, 256, 0, h->stream>>>(stage.p, plane, fs.planeBytes, h->W, h->H, (int)dpitch);
+    h->launches++;
+    CK(cudaGetLastError());
+    return IVG_OK;
+  }
   if (n > 1 && stride > 0 && frame_bytes % stride == 0 && fs.planeBytes % dpitch == 0) {
     cudaMemcpy3DParms p{};
     p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(src), stride, h->W, frame_bytes / stride);
@@ -524,10 +537,10 @@ int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, 
   int rc = ivg_set_batch(h, n, width, height, costs != nullptr);
   if (rc) return rc;
   if ((rc = honour_wait(h))) return rc;
-  if ((rc = copy_frames_in(h, h->pyr.p, n, images, stride, frame_bytes))) return rc;
+  if ((rc = copy_frames_in(h, h->pyr.p, h->stageImg, n, images, stride, frame_bytes))) return rc;
   if (h->curWeighted) {
     if (cost_stride < (size_t)width) return IVG_ERR_INVALID;
-    if ((rc = copy_frames_in(h, h->qual.p, n, costs, cost_stride, cost_frame_bytes))) return rc;
+    if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, costs, cost_stride, cost_frame_bytes))) return rc;
   }
   return IVG_OK;
 }

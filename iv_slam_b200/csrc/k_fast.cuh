@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char fsm[];
   __shared__ int wcnt[2][8];
   __shared__ int sred[3][8];
-  __shared__ int slistN;
 
   const CellDev c = fs.cells[blockIdx.x];
   const LevelDev& L = fs.lv[c.level];
@@ -71,7 +70,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
   uint32_t* list = fs.cellList + img * fs.listCapTotal + c.listOff;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cw = c.cw, ch = c.ch;
-  const int SP = L.fSP, SS = L.fSS, BH = L.fBH, BW = L.fBW;
+  const int SP = L.fSP, SS = L.fSS, BH = L.fBH, BW = L.fBW, pitch = L.pitch, segCap = L.fSeg;
   // shared layout: packed pixel pairs | score bytes | survivor bitmap | pair list
   uint32_t* sp = reinterpret_cast<uint32_t*>(fsm);
   const int ssBytes = (SS * (BH + 4) + 15) & ~15, bitBytes = (4 * BW * (BH + 2) + 15) & ~15;
@@ -94,21 +93,33 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
 
     // ---- A: stage. word row q holds pixel rows (q, q+1) counted from global row gy0
     const int gy0 = c.y0 + s0 - 3;
-    if (tid == 0) slistN = 0;
-    for (int q = warp; q < nWR; q += 8) {
-      const uint8_t* prow = pix + (size_t)(gy0 + q) * L.pitch + xa;
-      for (int g = lane; g < (SP >> 2); g += 32) {
-        uint32_t a = 0, b = 0;
-        if (xa + 4 * g < L.pitch) {
-          a = __ldg(reinterpret_cast<const uint32_t*>(prow + 4 * g));
-          b = __ldg(reinterpret_cast<const uint32_t*>(prow + L.pitch + 4 * g));
+    {
+      // thread = (column group g, row segment): rows are walked top to bottom with the previous row carried in a
+      // register, so every global word is loaded once
+      const int nG4 = SP >> 2;
+      const int nSeg = max(256 / nG4, 1);
+      const int segRows = (nWR + nSeg - 1) / nSeg;
+      for (int t = tid; t < nG4 * nSeg; t += 256) {
+        const int seg = t / nG4, g = t - seg * nG4;
+        const int q0 = seg * segRows, q1 = min(q0 + segRows, nWR);
+        if (q0 < q1) {
+          const bool in = xa + 4 * g < pitch;
+          const uint8_t* prow = pix + (size_t)(gy0 + q0) * pitch + xa + 4 * g;
+          uint32_t a = in ? __ldg(reinterpret_cast<const uint32_t*>(prow)) : 0u;
+          uint32_t* dst = sp + q0 * SP + 4 * g;
+          for (int q = q0; q < q1; ++q) {
+            prow += pitch;
+            const uint32_t b = in ? __ldg(reinterpret_cast<const uint32_t*>(prow)) : 0u;
+            uint4 o;
+            o.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu;
+            o.y = __byte_perm(a, b, 0x0501) & 0x00FF00FFu;
+            o.z = __byte_perm(a, b, 0x0602) & 0x00FF00FFu;
+            o.w = __byte_perm(a, b, 0x0703) & 0x00FF00FFu;
+            *reinterpret_cast<uint4*>(dst) = o;
+            dst += SP;
+            a = b;
+          }
         }
-        uint4 o;
-        o.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu;
-        o.y = __byte_perm(a, b, 0x0501) & 0x00FF00FFu;
-        o.z = __byte_perm(a, b, 0x0602) & 0x00FF00FFu;
-        o.w = __byte_perm(a, b, 0x0703) & 0x00FF00FFu;
-        *reinterpret_cast<uint4*>(sp + q * SP + 4 * g) = o;
       }
     }
     {
@@ -118,14 +129,15 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
     __syncthreads();
 
     // ---- B: opposing-pair rejection on diameters 0-8, 2-10, 4-12, 6-14
-    for (int it = warp; it < nPairs * nChunks; it += 8) {
-      const int p = it / nChunks;
-      const uint32_t* rowc = sp + (2 * p + 3) * SP + cOff;
-      {
-        const int x = (it - p * nChunks) * 32 + lane;
+    uint16_t* wlist = slist + warp * segCap;        // this warp's private segment: no atomics, no ordering needed
+    int wn = 0;
+    {
+      int p = warp / nChunks, xc = warp - p * nChunks;
+      while (p < nPairs) {
+        const int x = xc * 32 + lane;
         bool pass = false;
         if (x < cw) {
-          const uint32_t* ctr = rowc + x;
+          const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
           const unsigned C = ctr[0] + 0x01000100u;
           const unsigned D0 = C - ctr[3 * SP], D8 = C - ctr[-3 * SP];
           const unsigned D2 = C - ctr[2 * SP + 2], D10 = C - ctr[-2 * SP - 2];
@@ -137,20 +149,17 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
           pass = ((t & 0xFFFFu) >= passK) | ((t >> 16) >= passK);
         }
         const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&slistN, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (pass) slist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(p * 512 + x);   // cw <= 512 enforced by the host
-        }
+        if (pass) wlist[wn + __popc(m & ((1u << lane) - 1))] = (uint16_t)(p * 512 + x);   // cw <= 512 enforced by the host
+        wn += __popc(m);
+        xc += 8;
+        while (xc >= nChunks) { xc -= nChunks; ++p; }
       }
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- C: exact score of the surviving pairs
-    const int nList = slistN;
-    for (int j = tid; j < nList; j += 256) {
-      const int e = slist[j], p = e >> 9, x = e & 511;
+    for (int j = lane; j < wn; j += 32) {
+      const int e = wlist[j], p = e >> 9, x = e & 511;
       const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
       const unsigned C = ctr[0] + 0x01000100u;
       unsigned D[16];
@@ -169,8 +178,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
     __syncthreads();
 
     // ---- D: 3x3 strict maximum inside the cell (zero border = "no score outside the cell")
-    for (int j = tid; j < 2 * nList; j += 256) {
-      const int e = slist[j >> 1], p = e >> 9, x = e & 511, half = j & 1;
+    for (int j = lane; j < 2 * wn; j += 32) {
+      const int e = wlist[j >> 1], p = e >> 9, x = e & 511, half = j & 1;
       const int srow = 2 * p + half;                       // score row relative to s0
       const int row = s0 + srow;                           // detect row of the cell
       if (row < r0 || row >= r1) continue;                 // overlap rows belong to the neighbouring band

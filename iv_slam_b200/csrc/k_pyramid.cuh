@@ -16,6 +16,21 @@ namespace ivg {
 
 constexpr int RZ_W = 128, RZ_H = 32;
 
+// Level-0 ingest: frames arrive from the host as ONE contiguous copy (row-pitched DMA of 1241-byte rows runs at a third
+// of the PCIe rate); this kernel lays them out in the row-pitched level-0 plane.  One aligned 32-bit store per thread,
+// source bytes come from two aligned words and a funnel shift (rows of an unpitched frame are not word aligned).
+__global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ stage, uint8_t* __restrict__ plane, size_t planeBytes,
+                                                int w, int h, int pitch) {
+  const int xw = blockIdx.x * 256 + threadIdx.x;     // destination word of the row
+  const int y = blockIdx.y;
+  const size_t f = blockIdx.z;
+  if (4 * xw >= w) return;
+  const size_t a = f * (size_t)w * h + (size_t)y * w + 4 * xw;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(stage) + (a >> 2);
+  const uint32_t v = __funnelshift_r(__ldg(s), __ldg(s + 1), 8 * (int)(a & 3));
+  *reinterpret_cast<uint32_t*>(plane + f * planeBytes + (size_t)y * pitch + 4 * xw) = v;
+}
+
 __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, int which /*0 image, 1 cost-map*/) {
   extern __shared__ __align__(16) unsigned char rsm[];
   const LevelDev& D = fs.lv[level];
