@@ -172,7 +172,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from iv_slam_b200 import api, synthetic as S
+    from iv_slam_b200 import api, sharding, synthetic as S
     from iv_slam_b200.frontend import StereoFrontend
 
     torch.cuda.set_device(local)
@@ -186,8 +186,10 @@ def main():
 
     B, W, H = args.batch, KITTI["w"], KITTI["h"]
     params = {k: KITTI[k] for k in ("nfeatures", "scaleFactor", "nlevels", "iniThFAST", "minThFAST")}
-    # this rank's contiguous frame range of the global synthetic sequence
-    Lh, Rh = S.make_stereo_batch(W, H, B, 100 + rank * B, distinct=args.distinct)
+    # this rank's contiguous frame range [f0, f1) of the global synthetic sequence of world*B pairs (weak scaling)
+    f0, f1 = sharding.frame_range(rank, world, world * B)
+    assert f1 - f0 == B
+    Lh, Rh = S.make_stereo_batch(W, H, B, 100 + f0, distinct=args.distinct)
     pinL, pinR = api.PinnedArray(Lh.shape, np.uint8), api.PinnedArray(Rh.shape, np.uint8)
     pinL.array[...] = Lh
     pinR.array[...] = Rh
@@ -233,10 +235,7 @@ def main():
         prof[k][1] += cnt
     resL.profile_enable(False), resR.profile_enable(False)
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = sharding.reduce_max(ms_total, "cuda") / args.steps       # max over ranks
     value = world * B / (ms_step * 1e-3)
 
     # ------------------------------------------------------------------ end-to-end arm (`e2e`)
@@ -250,10 +249,7 @@ def main():
     fe.finish()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
+    e2e_value = world * B * args.steps / sharding.reduce_max(e2e_s, "cuda")
     h2d = int(pinL.array.nbytes + pinR.array.nbytes)
     d2h = int(sum(out[k].nbytes for k in ("kL", "dL", "nL", "kR", "dR", "nR", "uRight", "depth")))
     n_kp = int(out["nL"].sum())

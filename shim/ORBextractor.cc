@@ -1,0 +1,70 @@
+/* shim/ORBextractor.cc — ORB_SLAM2::ORBextractor on the B200 C ABI (include/ivslam_gpu.h).
+ * Replaces introspective_ORB_SLAM/src/ORBextractor.cc (constructor :411-476, operator() :1224-1296). */
+#include "ORBextractor.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "ivslam_gpu.h"
+
+namespace ORB_SLAM2 {
+
+static void check(int rc, const char* what) {
+  if (rc != IVG_OK)
+    throw std::runtime_error(std::string(what) + ": " + ivg_strerror(rc) + " " + ivg_last_cuda_error());
+}
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST,
+                           bool enableIntrospection)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
+      minThFAST(_minThFAST), benableIntrospection(enableIntrospection) {
+  check(ivg_extractor_create(&mHandle, /*device*/ 0, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST,
+                             enableIntrospection ? 1 : 0), "ivg_extractor_create");
+  mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
+  mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+  ivg_get_scale_table(mHandle, 0, mvScaleFactor.data());
+  ivg_get_scale_table(mHandle, 1, mvInvScaleFactor.data());
+  ivg_get_scale_table(mHandle, 2, mvLevelSigma2.data());
+  ivg_get_scale_table(mHandle, 3, mvInvLevelSigma2.data());
+  mvImagePyramid.resize(nlevels);
+  mvQualityImagePyramid.resize(nlevels);
+  static_assert(sizeof(cv::KeyPoint) == sizeof(ivg_keypoint), "ivg_keypoint must mirror cv::KeyPoint");
+}
+
+ORBextractor::~ORBextractor() { ivg_extractor_destroy(mHandle); }
+
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                              cv::OutputArray _descriptors) {
+  if (_image.empty()) return;                                   // src/ORBextractor.cc:1227-1228
+  cv::Mat image = _image.getMat();
+  cv::Mat mask;
+  bqualityScoresAvailable = !_mask.empty() && benableIntrospection;   // :1231
+  if (bqualityScoresAvailable) mask = _mask.getMat();
+
+  const int cap = ivg_max_keypoints(mHandle);
+  _keypoints.resize(cap);
+  cv::Mat desc(cap, 32, CV_8U);
+  int n = 0;
+  check(ivg_extract(mHandle, image.data, image.cols, image.rows, image.step,
+                    bqualityScoresAvailable ? mask.data : nullptr, bqualityScoresAvailable ? (size_t)mask.step : 0,
+                    reinterpret_cast<ivg_keypoint*>(_keypoints.data()), desc.data, cap, &n), "ivg_extract");
+  _keypoints.resize(n);
+  if (n == 0) _descriptors.release();                           // :1255-1256
+  else desc.rowRange(0, n).copyTo(_descriptors);
+}
+
+void ORBextractor::SyncPyramidsToHost() {
+  for (int l = 0; l < nlevels; ++l) {
+    int w = 0, h = 0;
+    check(ivg_level_size(mHandle, l, &w, &h), "ivg_level_size");
+    mvImagePyramid[l].create(h, w, CV_8UC1);
+    check(ivg_get_pyramid_level(mHandle, 0, l, 0, mvImagePyramid[l].data, mvImagePyramid[l].step), "ivg_get_pyramid_level");
+    if (bqualityScoresAvailable) {
+      mvQualityImagePyramid[l].create(h, w, CV_8UC1);
+      check(ivg_get_pyramid_level(mHandle, 0, l, 2, mvQualityImagePyramid[l].data, mvQualityImagePyramid[l].step), "ivg_get_pyramid_level");
+    }
+  }
+}
+
+}  // namespace ORB_SLAM2

@@ -1,0 +1,82 @@
+/* shim/ORBextractor.h — source-compatible replacement for introspective_ORB_SLAM/include/ORBextractor.h.
+ *
+ * Same namespace, class name, constructor, operator(), getters and public pyramid members as the reference
+ * (introspective_ORB_SLAM/include/ORBextractor.h:54-128), implemented on the C ABI of include/ivslam_gpu.h.
+ * Drop this header + ORBextractor.cc into introspective_ORB_SLAM/{include,src} in place of the originals and link
+ * libivslam_gpu.so.  Needs OpenCV headers to compile, like the file it replaces; in this repo it
+ * is compile-checked against the minimal stand-in under tests/fake_opencv/.
+ *
+ * Differences a maintainer should know (all documented in DESIGN.md):
+ *  - there is no CPU fallback: the constructor throws std::runtime_error if no sm_100 GPU is usable;
+ *  - mvImagePyramid / mvQualityImagePyramid are filled lazily by SyncPyramidsToHost() (the device keeps the master
+ *    copy; the GPU stereo matcher never needs them on the host).  Code that reads the pyramids directly, like the
+ *    reference's Frame::ComputeStereoMatches, must call it first — the shim's ComputeStereoMatches does not need to;
+ *  - the dead ComputeKeyPointsOctTree / DistributeOctTree / ExtractorNode members are not provided.
+ */
+#ifndef ORBEXTRACTOR_H
+#define ORBEXTRACTOR_H
+
+#include <vector>
+
+#include <opencv2/core/core.hpp>
+
+struct ivg_extractor;
+
+namespace ORB_SLAM2 {
+
+class ORBextractor {
+ public:
+  enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+  ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+               bool enableIntrospection = false);
+  ~ORBextractor();
+  ORBextractor(const ORBextractor&) = delete;
+  ORBextractor& operator=(const ORBextractor&) = delete;
+
+  // Compute the ORB features and descriptors on an image; `mask` is the IV-SLAM cost-map (or empty).
+  void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
+                  cv::OutputArray descriptors);
+
+  int inline GetLevels() { return nlevels; }
+  float inline GetScaleFactor() { return (float)scaleFactor; }
+  std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+  std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+  std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+  std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+  std::vector<cv::Mat> mvImagePyramid;
+  std::vector<cv::Mat> mvQualityImagePyramid;
+
+  // Copies the device pyramids of the last operator() call into mvImagePyramid / mvQualityImagePyramid.
+  void SyncPyramidsToHost();
+  // The underlying C-ABI handle (used by the GPU Frame::ComputeStereoMatches replacement).
+  ivg_extractor* handle() const { return mHandle; }
+
+ protected:
+  int nfeatures;
+  double scaleFactor;
+  int nlevels;
+  int iniThFAST;
+  int minThFAST;
+  bool benableIntrospection = false;
+  bool bqualityScoresAvailable = false;
+
+  std::vector<float> mvScaleFactor;
+  std::vector<float> mvInvScaleFactor;
+  std::vector<float> mvLevelSigma2;
+  std::vector<float> mvInvLevelSigma2;
+
+  ivg_extractor* mHandle = nullptr;
+  std::vector<unsigned char> mKeypointStage;   // ivg_keypoint records (same layout as cv::KeyPoint)
+};
+
+// Replacement body for Frame::ComputeStereoMatches (introspective_ORB_SLAM/src/Frame.cc:758-932): fills mvuRight /
+// mvDepth for the N keypoints the left extractor produced in its last call.  maxD is what the reference computes as
+// mbf/mb (it reads mb before assigning it; pass fx).  See shim/Frame_ComputeStereoMatches.cc.
+void ComputeStereoMatchesGPU(ORBextractor* left, ORBextractor* right, int N, float mbf, float maxD,
+                             std::vector<float>& mvuRight, std::vector<float>& mvDepth);
+
+}  // namespace ORB_SLAM2
+
+#endif  // ORBEXTRACTOR_H

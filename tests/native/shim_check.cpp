@@ -1,0 +1,41 @@
+// Drives shim/ORBextractor.{h,cc} + shim/Frame_ComputeStereoMatches.cc (compiled against tests/fake_opencv) exactly the
+// way Frame::Frame does in the reference (src/Frame.cc:115-125, :193): two extractor objects, operator() on each eye,
+// then ComputeStereoMatches.  Built and called by tests/test_shim.py.
+#include <cstring>
+#include <exception>
+#include <vector>
+
+#include "ORBextractor.h"
+
+extern "C" int shim_stereo_frame(const unsigned char* left, const unsigned char* right, int w, int h, int nfeatures, int iniTh,
+                                 int minTh, float mbf, float maxD, void* kpsL, unsigned char* descL, int* nL, float* uRight,
+                                 float* depth, int* levels, float* scale1, unsigned char* pyr1, int* pyr1w, int* pyr1h) {
+  try {
+    ORB_SLAM2::ORBextractor exL(nfeatures, 1.2f, 8, iniTh, minTh), exR(nfeatures, 1.2f, 8, iniTh, minTh);
+    cv::Mat imL(h, w, CV_8UC1, (void*)left, (size_t)w), imR(h, w, CV_8UC1, (void*)right, (size_t)w), none;
+    std::vector<cv::KeyPoint> kL, kR;
+    cv::Mat dL, dR;
+    exL(imL, none, kL, dL);
+    exR(imR, none, kR, dR);
+    std::vector<float> u, d;
+    ORB_SLAM2::ComputeStereoMatchesGPU(&exL, &exR, (int)kL.size(), mbf, maxD, u, d);
+    *nL = (int)kL.size();
+    std::memcpy(kpsL, kL.data(), kL.size() * sizeof(cv::KeyPoint));
+    for (int i = 0; i < dL.rows; ++i) std::memcpy(descL + 32 * i, dL.data + (size_t)i * dL.step, 32);
+    std::memcpy(uRight, u.data(), u.size() * sizeof(float));
+    std::memcpy(depth, d.data(), d.size() * sizeof(float));
+    *levels = exL.GetLevels();
+    *scale1 = exL.GetScaleFactors()[1];
+    exL.SyncPyramidsToHost();
+    *pyr1w = exL.mvImagePyramid[1].cols; *pyr1h = exL.mvImagePyramid[1].rows;
+    for (int y = 0; y < *pyr1h; ++y) std::memcpy(pyr1 + (size_t)y * *pyr1w, exL.mvImagePyramid[1].data + (size_t)y * exL.mvImagePyramid[1].step, *pyr1w);
+    return 0;
+  } catch (const std::exception& e) {
+    return -1;
+  }
+}
+
+extern "C" int shim_construct_only() {
+  try { ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7); return 0; }
+  catch (const std::exception&) { return -1; }
+}
