@@ -55,6 +55,7 @@ struct FrameSet {
   int iniTh, minTh, scoreTh;
   int nCellsTotal, kpCap;
   int btTotal;
+  int selLevelCap, selCellCap, selCells;   // k_level_select shared-memory capacities
   unsigned listCapTotal;
   size_t planeBytes;
   uint8_t* pyr; uint8_t* blur; uint8_t* qual;                    // [nImages][planeBytes]

@@ -88,7 +88,7 @@ struct ivg_extractor {
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
-  size_t fastSmem = 0, resizeSmem = 0;
+  size_t fastSmem = 0, resizeSmem = 0, selSmem = 0;
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
   DevBuf<uint32_t> cellList, cellCost;
@@ -218,12 +218,12 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.fBW = (L.cellW + 31) / 32;
     if (L.cellW > 512) return IVG_ERR_CAPACITY;               // pair list packs x in 9 bits
     {
-      const int perRow = 4 * L.fSP + L.fSS + 4 * L.fBW + 32 * L.fBW + 32;   // pixels + scores + bitmap + pair list (2 B per pair)
+      const int perRow = 4 * L.fSP + L.fSS + 4 * L.fBW + 128 * ((L.fBW + 3) / 4) + 64;   // pixels + scores + bitmap + pair list (2 B per pair)
       int bh = (int)(FAST_SMEM_BUDGET / perRow) - 8;
       bh = std::min(std::max(bh, 4), 200);
       L.fBH = std::min(bh, L.cellH);
       const size_t ssBytes = align_up((size_t)L.fSS * (L.fBH + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (L.fBH + 2), 16);
-      L.fSeg = ((((L.fBH + 3) / 2) * L.fBW + 7) / 8) * 32;
+      L.fSeg = ((((L.fBH + 3) / 2) * ((L.fBW + 3) / 4) + 7) / 8) * 128;   // per-warp pair list: items of up to 4 chunks x 32 lanes
       const size_t listBytes = (size_t)2 * 8 * L.fSeg;
       fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + ssBytes + bitBytes + listBytes);
     }
@@ -272,6 +272,16 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   fs.nCellsTotal = (int)h->cellsPlain.size();
   fs.kpCap = kpOff;
   fs.btTotal = btBase;
+  {
+    // k_level_select shared memory: level list up to 2x the largest per-level budget (the reference itself reserves
+    // nDesired*2, :1136), a modest per-warp cell list, per-cell scalars; longer lists fall back to global memory
+    int maxDesired = 1, maxCells = 1;
+    for (int l = 0; l < nl; ++l) { maxDesired = std::max(maxDesired, fs.lv[l].nDesired); maxCells = std::max(maxCells, fs.lv[l].nCells); }
+    fs.selLevelCap = std::min((int)align_up(2 * maxDesired + 64, 64), 8192);
+    fs.selCellCap = 128;
+    fs.selCells = (int)align_up(maxCells, 4);
+    h->selSmem = sel_smem_bytes(fs.selLevelCap, fs.selCellCap, fs.selCells);
+  }
   h->fastSmem = fastSmem; h->resizeSmem = resizeSmem;
   if (fastSmem > 200 * 1024 || resizeSmem > 200 * 1024) return IVG_ERR_CAPACITY;
   if (fs.kpCap > 65535) return IVG_ERR_CAPACITY;           // stereo packs the right index in 16 bits
@@ -354,7 +364,7 @@ int launch_extract(ivg_extractor* h) {
   if (rc) return rc;
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
-  { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, sizeof(SelShared), h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs); }
   CK(cudaGetLastError());
   h->haveResults = true; h->havePyramid = true;
@@ -372,7 +382,7 @@ int init_device_constants(int device) {
     }
     CK(cudaMemcpyToSymbol(g_patternT, pt.data(), sizeof(float2) * 512));
   }
-  CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
+  CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return IVG_OK;

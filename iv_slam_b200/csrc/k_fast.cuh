@@ -58,7 +58,7 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
   return __vmaxu2(best, 0x02000200u - worst);
 }
 
-__global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
+__global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char fsm[];
   __shared__ int wcnt[2][8];
   __shared__ int sred[3][8];
@@ -132,27 +132,35 @@ __global__ void __launch_bounds__(256) k_fast_cells(FrameSet fs) {
     uint16_t* wlist = slist + warp * segCap;        // this warp's private segment: no atomics, no ordering needed
     int wn = 0;
     {
-      int p = warp / nChunks, xc = warp - p * nChunks;
-      while (p < nPairs) {
-        const int x = xc * 32 + lane;
-        bool pass = false;
-        if (x < cw) {
-          const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
-          const unsigned C = ctr[0] + 0x01000100u;
-          const unsigned D0 = C - ctr[3 * SP], D8 = C - ctr[-3 * SP];
-          const unsigned D2 = C - ctr[2 * SP + 2], D10 = C - ctr[-2 * SP - 2];
-          const unsigned D4 = C - ctr[3], D12 = C - ctr[-3];
-          const unsigned D6 = C - ctr[-2 * SP + 2], D14 = C - ctr[2 * SP - 2];
-          const unsigned a = __vminu2(vmin3(__vmaxu2(D0, D8), __vmaxu2(D2, D10), __vmaxu2(D4, D12)), __vmaxu2(D6, D14));
-          const unsigned b = __vmaxu2(vmax3(__vminu2(D0, D8), __vminu2(D2, D10), __vminu2(D4, D12)), __vminu2(D6, D14));
-          const unsigned t = __vmaxu2(a, 0x02000200u - b);
-          pass = ((t & 0xFFFFu) >= passK) | ((t >> 16) >= passK);
+      // work item = (row pair p, segment of up to 4 chunks of 32 columns); the inner loop only bumps pointers
+      const int nSegs = (nChunks + 3) >> 2;
+      const unsigned ltmask = (1u << lane) - 1u;
+      for (int it = warp; it < nPairs * nSegs; it += 8) {
+        const int p = it / nSegs, sg = it - p * nSegs;
+        int x = sg * 128 + lane;
+        const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
+        const uint32_t* cp3 = ctr + 3 * SP;  const uint32_t* cm3 = ctr - 3 * SP;     // ring rows +-3, +-2 (row 0 via ctr)
+        const uint32_t* cp2 = ctr + 2 * SP;  const uint32_t* cm2 = ctr - 2 * SP;
+        const int xend = min(cw, sg * 128 + 128);
+        const int ebase = p * 512;
+#pragma unroll 1
+        for (; x - lane < xend; x += 32, ctr += 32, cp3 += 32, cm3 += 32, cp2 += 32, cm2 += 32) {
+          bool pass = false;
+          if (x < xend) {
+            const unsigned C = ctr[0] + 0x01000100u;
+            const unsigned D0 = C - cp3[0], D8 = C - cm3[0];
+            const unsigned D2 = C - cp2[2], D10 = C - cm2[-2];
+            const unsigned D4 = C - ctr[3], D12 = C - ctr[-3];
+            const unsigned D6 = C - cm2[2], D14 = C - cp2[-2];
+            const unsigned a = __vminu2(vmin3(__vmaxu2(D0, D8), __vmaxu2(D2, D10), __vmaxu2(D4, D12)), __vmaxu2(D6, D14));
+            const unsigned b = __vmaxu2(vmax3(__vminu2(D0, D8), __vminu2(D2, D10), __vminu2(D4, D12)), __vminu2(D6, D14));
+            const unsigned t = __vmaxu2(a, 0x02000200u - b);
+            pass = max(t & 0xFFFFu, t >> 16) >= passK;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + x);   // cw <= 512 enforced by the host
+          wn += __popc(m);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) wlist[wn + __popc(m & ((1u << lane) - 1))] = (uint16_t)(p * 512 + x);   // cw <= 512 enforced by the host
-        wn += __popc(m);
-        xc += 8;
-        while (xc >= nChunks) { xc -= nChunks; ++p; }
       }
     }
     __syncwarp();

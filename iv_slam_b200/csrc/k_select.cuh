@@ -16,10 +16,10 @@
 
 namespace ivg {
 
-constexpr int SEL_MAX_CELLS = 1024;      // cells per level the select kernel can hold in shared memory
-constexpr int SEL_LEVEL_CAP = 4096;      // level list entries kept in shared memory (else global fallback)
-constexpr int SEL_CELL_CAP = 512;        // per-warp cell list entries kept in shared memory (else global fallback)
+constexpr int SEL_MAX_CELLS = 1024;      // cells per level the select kernel supports (host check)
 constexpr int SEL_WARPS = 8;
+// Shared memory is sized per handle (dynamic): FrameSet::selLevelCap level-list entries, selCellCap entries per warp for
+// a cell list, selCells per-cell scalars.  Lists longer than the caps are processed in global memory (same code).
 
 // response weight of IV-SLAM's introspection: 2 * (1/(1 + cost/255)) - 1, all float (src/ORBextractor.cc:1070-1071)
 __device__ __forceinline__ float introspection_weight(float cost) {
@@ -27,23 +27,36 @@ __device__ __forceinline__ float introspection_weight(float cost) {
   return __fsub_rn(__fmul_rn(2.0f, q), 1.0f);
 }
 
-struct SelShared {
-  SelItem levelBuf[SEL_LEVEL_CAP];
-  SelItem cellBuf[SEL_WARPS][SEL_CELL_CAP];
-  int nTotal[SEL_MAX_CELLS];
-  int nStored[SEL_MAX_CELLS];
-  int nRetain[SEL_MAX_CELLS];
-  int prefix[SEL_MAX_CELLS];
-  float nfc[SEL_MAX_CELLS];
-  unsigned char thr[SEL_MAX_CELLS];
-  unsigned char noMore[SEL_MAX_CELLS];
-  int total;
-  int count;
+struct SelShared {           // views into the dynamic shared memory block
+  SelItem* levelBuf;
+  SelItem* cellBuf;          // [SEL_WARPS][selCellCap]
+  int* nTotal; int* nStored; int* nRetain; int* prefix;
+  float* nfc;
+  unsigned char* thr; unsigned char* noMore;
 };
+
+__host__ __device__ inline size_t sel_smem_bytes(int levelCap, int cellCap, int cells) {
+  return (size_t)8 * levelCap + (size_t)8 * SEL_WARPS * cellCap + (size_t)cells * (5 * 4 + 2) + 16;
+}
 
 __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SelShared& S = *reinterpret_cast<SelShared*>(smem_raw);
+  __shared__ int sTotal, sCount;
+  const int SEL_LEVEL_CAP = fs.selLevelCap, SEL_CELL_CAP = fs.selCellCap;
+  SelShared S;
+  {
+    unsigned char* p = smem_raw;
+    S.levelBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * SEL_LEVEL_CAP;
+    S.cellBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * SEL_WARPS * SEL_CELL_CAP;
+    const int nc = fs.selCells;
+    S.nTotal = reinterpret_cast<int*>(p); p += 4 * nc;
+    S.nStored = reinterpret_cast<int*>(p); p += 4 * nc;
+    S.nRetain = reinterpret_cast<int*>(p); p += 4 * nc;
+    S.prefix = reinterpret_cast<int*>(p); p += 4 * nc;
+    S.nfc = reinterpret_cast<float*>(p); p += 4 * nc;
+    S.thr = p; p += nc;
+    S.noMore = p;
+  }
   const int level = blockIdx.x;
   const size_t img = blockIdx.y;
   const LevelDev& L = fs.lv[level];
@@ -102,11 +115,11 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
     }
     int run = 0;
     for (int c = 0; c < nCells; ++c) { S.prefix[c] = run; run += min(max(S.nRetain[c], 0), S.nTotal[c]); }
-    S.total = run;
+    sTotal = run;
   }
   __syncthreads();
 
-  const int total = S.total;
+  const int total = sTotal;
   SelItem* levelBuf = total <= SEL_LEVEL_CAP ? S.levelBuf
                                              : reinterpret_cast<SelItem*>(fs.workLevel + img * fs.listCapTotal + L.listBase);
   const uint8_t* qual = fs.qual + img * fs.planeBytes + L.planeOff;
@@ -117,7 +130,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
     if (keep == 0) continue;
     const int stored = S.nStored[c], thr = S.thr[c];
     const uint32_t* list = fs.cellList + img * fs.listCapTotal + cells[c].listOff;
-    SelItem* buf = n <= SEL_CELL_CAP ? S.cellBuf[warp]
+    SelItem* const wbuf = S.cellBuf + (size_t)warp * SEL_CELL_CAP;
+    SelItem* buf = n <= SEL_CELL_CAP ? wbuf
                                      : reinterpret_cast<SelItem*>(fs.workCell + img * fs.listCapTotal + cells[c].listOff);
     int run = 0;
     for (int base = 0; base < stored; base += 32) {
@@ -137,10 +151,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
       run += __popc(m);
     }
     __syncwarp();
-    if (buf != S.cellBuf[warp]) __threadfence_block();
+    if (buf != wbuf) __threadfence_block();
     if (lane == 0 && n > keep) sel_nth_element(buf, keep - 1, n);
     __syncwarp();
-    if (buf != S.cellBuf[warp]) __threadfence_block();
+    if (buf != wbuf) __threadfence_block();
     const int dst = S.prefix[c];
     for (int i = lane; i < keep; i += 32) levelBuf[dst + i] = buf[i];
     __syncwarp();
@@ -154,12 +168,12 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
       if (L.nDesired == 0) count = 0;
       else { sel_nth_element(levelBuf, L.nDesired - 1, total); count = L.nDesired; }
     }
-    S.count = count;
+    sCount = count;
     fs.levelCount[img * MAX_LEVELS + level] = count;
   }
   __threadfence_block();
   __syncthreads();
-  const int count = S.count;
+  const int count = sCount;
   uint2* out = fs.levelKp + img * fs.kpCap + L.kpOff;
   for (int i = tid; i < count; i += blockDim.x) out[i] = make_uint2(levelBuf[i].key, levelBuf[i].val);
 }
