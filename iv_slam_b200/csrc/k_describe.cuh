@@ -89,17 +89,22 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs) {
     if (level < 0) continue;
     const LevelDev& L = fs.lv[level];
     const uint8_t* ctr = fs.pyr + img * fs.planeBytes + L.planeOff + (size_t)sCy[j] * L.pitch + sCx[j];
-    const int u = lane - HALF_PATCH, au = abs(u), pitch = L.pitch;
+    // every lane loads its column of the 31x31 bounding square unconditionally (always inside the level: keypoints are
+    // >= 19 px from the border) so all 31 loads are in flight together; rows outside the circle are masked to zero
+    const int u = min(lane, 2 * HALF_PATCH) - HALF_PATCH, au = abs(u), pitch = L.pitch;
+    const bool live = lane <= 2 * HALF_PATCH;
     int colsum = 0, m01 = 0;
-    if (lane <= 2 * HALF_PATCH) {
-      colsum = __ldg(ctr + u);
+    {
+      int vals[2 * HALF_PATCH + 1];
+#pragma unroll
+      for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) vals[v + HALF_PATCH] = __ldg(ctr + v * pitch + u);
+      colsum = live ? vals[HALF_PATCH] : 0;
 #pragma unroll
       for (int v = 1; v <= HALF_PATCH; ++v) {
-        if (au <= UMAX[v]) {
-          const int a = __ldg(ctr + v * pitch + u), b = __ldg(ctr - v * pitch + u);
-          colsum += a + b;
-          m01 += v * (a - b);
-        }
+        const bool in = live && au <= UMAX[v];
+        const int a = in ? vals[HALF_PATCH + v] : 0, b = in ? vals[HALF_PATCH - v] : 0;
+        colsum += a + b;
+        m01 += v * (a - b);
       }
     }
     int m10 = u * colsum;
