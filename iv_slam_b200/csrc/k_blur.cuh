@@ -40,19 +40,28 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs) {
   const uint8_t* img = fs.pyr + frameOff;
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < BL_PH * BL_PW; i += 256) {
-    const int r = i / BL_PW, g = i - r * BL_PW;
-    const int gy = reflect101(min(y0 - 3 + r, L.h + 2), L.h);
-    const int gx = x0 - 4 + 4 * g;
-    const uint8_t* row = img + (size_t)gy * L.pitch;
-    uint32_t v;
-    if (gx >= 0 && gx + 3 < L.w) v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-    else {
-      v = 0;
+  {
+    const int w = L.w, h = L.h, pitch = L.pitch;
+    for (int i = tid; i < BL_PH * BL_PW; i += 256) {
+      const int r = i / BL_PW, g = i - r * BL_PW;
+      // reflect-101 of a row index in [-3, h+2]: one reflection suffices (h >= 4)
+      int gy = min(y0 - 3 + r, h + 2);
+      gy = abs(gy);
+      gy = min(gy, 2 * h - 2 - gy);
+      const int gx = x0 - 4 + 4 * g;
+      const uint8_t* row = img + (size_t)gy * pitch;
+      uint32_t v = 0;
+      if (gx >= 0 && gx + 3 < w) v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+      else if (gx <= w + 2) {                        // straddles an image edge; columns past w+2 are never used
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + reflect101(min(gx + k, L.w + 2), L.w)) << (8 * k);
+        for (int k = 0; k < 4; ++k) {
+          int x = abs(min(gx + k, w + 2));
+          x = min(x, 2 * w - 2 - x);
+          v |= (uint32_t)__ldg(row + x) << (8 * k);
+        }
+      }
+      spx[i] = v;
     }
-    spx[i] = v;
   }
   __syncthreads();
 
