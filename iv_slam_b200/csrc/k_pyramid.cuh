@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ stag
   if (4 * xw >= w) return;
   const size_t a = f * (size_t)w * h + (size_t)y * w + 4 * xw;
   const uint32_t* s = reinterpret_cast<const uint32_t*>(stage) + (a >> 2);
-  const uint32_t v = __funnelshift_r(__ldg(s), __ldg(s + 1), 8 * (int)(a & 3));
+  const int sh = (int)(a & 3);
+  const uint32_t lo = __ldg(s), hi = sh ? __ldg(s + 1) : 0u;     // the second word is only touched when the row is misaligned
+  const uint32_t v = __funnelshift_r(lo, hi, 8 * sh);
   *reinterpret_cast<uint32_t*>(plane + f * planeBytes + (size_t)y * pitch + 4 * xw) = v;
 }
 

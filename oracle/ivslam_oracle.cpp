@@ -23,6 +23,7 @@
 // =====================================================================================
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -31,14 +32,22 @@
 #include <thread>
 #include <utility>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
 // ------------------------------------------------------------------------------------
 // cvRound: round-half-to-even (x86 cvtss2si / cvtsd2si under the default MXCSR mode).
 // ------------------------------------------------------------------------------------
+#if defined(__SSE2__)
+inline int cv_round(float v) { return _mm_cvtss_si32(_mm_set_ss(v)); }     // exactly OpenCV's cvRound on SSE2
+inline int cv_round(double v) { return _mm_cvtsd_si32(_mm_set_sd(v)); }
+#else
 inline int cv_round(float v) { return (int)lrintf(v); }
 inline int cv_round(double v) { return (int)lrint(v); }
+#endif
 
 // ------------------------------------------------------------------------------------
 // cv::resize(src, dst, INTER_LINEAR) for CV_8UC1 (call site src/ORBextractor.cc:1311,
@@ -108,28 +117,31 @@ inline int reflect101(int p, int n) {
 
 void gauss7_u8(const uint8_t* src, int w, int h, size_t sstride, uint8_t* dst, size_t dstride) {
   static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
-  std::vector<uint16_t> tmp((size_t)w * h);
-  std::vector<int> xi((size_t)w + 6);
-  for (int x = -3; x < w + 3; ++x) xi[x + 3] = reflect101(x, w);
-  for (int y = 0; y < h; ++y) {
+  thread_local std::vector<uint16_t> tmp;
+  thread_local std::vector<uint8_t> pad;
+  tmp.resize((size_t)w * h);
+  pad.resize((size_t)w + 6);
+  for (int y = 0; y < h; ++y) {                       // horizontal pass on a reflect-101 padded copy of the row
     const uint8_t* s = src + (size_t)y * sstride;
+    uint8_t* p = pad.data();
+    for (int x = -3; x < 0; ++x) p[x + 3] = s[reflect101(x, w)];
+    std::memcpy(p + 3, s, w);
+    for (int x = w; x < w + 3; ++x) p[x + 3] = s[reflect101(x, w)];
     uint16_t* t = &tmp[(size_t)y * w];
-    for (int x = 0; x < w; ++x) {
-      int acc = 0;
-      for (int k = 0; k < 7; ++k) acc += K[k] * s[xi[x + k]];
-      t[x] = (uint16_t)acc;
-    }
+    for (int x = 0; x < w; ++x)
+      t[x] = (uint16_t)(18 * (p[x] + p[x + 6]) + 34 * (p[x + 1] + p[x + 5]) + 48 * (p[x + 2] + p[x + 4]) + 56 * p[x + 3]);
   }
   for (int y = 0; y < h; ++y) {
     const uint16_t* r[7];
     for (int k = 0; k < 7; ++k) r[k] = &tmp[(size_t)reflect101(y + k - 3, h) * w];
     uint8_t* o = dst + (size_t)y * dstride;
+    const uint16_t *r0 = r[0], *r1 = r[1], *r2 = r[2], *r3 = r[3], *r4 = r[4], *r5 = r[5], *r6 = r[6];
     for (int x = 0; x < w; ++x) {
-      uint32_t acc = 0;
-      for (int k = 0; k < 7; ++k) acc += (uint32_t)K[k] * r[k][x];
+      const uint32_t acc = 18u * ((uint32_t)r0[x] + r6[x]) + 34u * ((uint32_t)r1[x] + r5[x]) + 48u * ((uint32_t)r2[x] + r4[x]) + 56u * r3[x];
       o[x] = (uint8_t)((acc + 32768u) >> 16);
     }
   }
+  (void)K;
 }
 
 // ------------------------------------------------------------------------------------
@@ -154,7 +166,7 @@ inline int corner_score(const int d[16]) {
   return best - 1;
 }
 
-struct FastScratch { std::vector<uint8_t> score; };
+struct FastScratch { std::vector<uint8_t> score; std::vector<int> pos; };
 
 void fast9_nms(const uint8_t* img, int w, int h, size_t stride, int th, bool nms,
                std::vector<Corner>& out, FastScratch& sc) {
@@ -164,51 +176,80 @@ void fast9_nms(const uint8_t* img, int w, int h, size_t stride, int th, bool nms
   int off[16];
   for (int k = 0; k < 16; ++k) off[k] = RING_DY[k] * (int)stride + RING_DX[k];
   sc.score.assign((size_t)w * h, 0);
+  sc.pos.clear();
   uint8_t* S = sc.score.data();
+  auto test_pixel = [&](const uint8_t* p, int x, int y) {
+    const int v = p[0], hi = v + th, lo = v - th;
+    // every arc of 9 contains one pixel of each opposing pair (k, k+8): cheap rejection
+    int br = 0, dk = 0;  // bit k set if ring[k] brighter / darker than the band
+    bool alive_b = true, alive_d = true;
+    for (int k = 0; k < 8 && (alive_b || alive_d); ++k) {
+      int a = p[off[k]], b = p[off[k + 8]];
+      if (a > hi) br |= 1 << k;
+      if (b > hi) br |= 1 << (k + 8);
+      if (a < lo) dk |= 1 << k;
+      if (b < lo) dk |= 1 << (k + 8);
+      alive_b = alive_b && (a > hi || b > hi);
+      alive_d = alive_d && (a < lo || b < lo);
+    }
+    if (!alive_b && !alive_d) return;
+    auto has_arc9 = [](int m) {
+      unsigned r = (unsigned)m | ((unsigned)m << 16);
+      unsigned t = r & (r >> 1);
+      t &= t >> 2;
+      t &= t >> 4;
+      t &= r >> 8;
+      return t != 0;
+    };
+    if (!((alive_b && has_arc9(br)) || (alive_d && has_arc9(dk)))) return;
+    int d[16];
+    for (int k = 0; k < 16; ++k) d[k] = v - p[off[k]];
+    int s = corner_score(d);
+    if (!nms) out.push_back({x, y, s});
+    else { S[(size_t)y * w + x] = (uint8_t)s; sc.pos.push_back(y * w + x); }
+  };
   for (int y = 3; y < h - 3; ++y) {
     const uint8_t* row = img + (size_t)y * stride;
-    for (int x = 3; x < w - 3; ++x) {
+    int x = 3;
+#if defined(__SSE2__)
+    // 16 pixels at a time (the reference's OpenCV FAST is SIMD too): reject blocks where no pixel passes the
+    // compass test on diameters 0-8 and 4-12, run the scalar test only on the pixels that do.
+    const __m128i delta = _mm_set1_epi8((char)-128), tv = _mm_set1_epi8((char)th);
+    for (; x + 16 <= w - 3; x += 16) {
       const uint8_t* p = row + x;
-      const int v = p[0], hi = v + th, lo = v - th;
-      // every arc of 9 contains one pixel of each opposing pair (k, k+8): cheap rejection
-      int br = 0, dk = 0;  // bit k set if ring[k] brighter / darker than the band
-      bool alive_b = true, alive_d = true;
-      for (int k = 0; k < 8 && (alive_b || alive_d); ++k) {
-        int a = p[off[k]], b = p[off[k + 8]];
-        if (a > hi) br |= 1 << k;
-        if (b > hi) br |= 1 << (k + 8);
-        if (a < lo) dk |= 1 << k;
-        if (b < lo) dk |= 1 << (k + 8);
-        alive_b = alive_b && (a > hi || b > hi);
-        alive_d = alive_d && (a < lo || b < lo);
+      const __m128i c = _mm_loadu_si128((const __m128i*)p);
+      const __m128i v0 = _mm_xor_si128(_mm_adds_epu8(c, tv), delta), v1 = _mm_xor_si128(_mm_subs_epu8(c, tv), delta);
+      auto ld = [&](int k) { return _mm_xor_si128(_mm_loadu_si128((const __m128i*)(p + off[k])), delta); };
+      const __m128i x0 = ld(0), x8 = ld(8), x4 = ld(4), x12 = ld(12);
+      __m128i mb = _mm_and_si128(_mm_or_si128(_mm_cmpgt_epi8(x0, v0), _mm_cmpgt_epi8(x8, v0)),
+                                 _mm_or_si128(_mm_cmpgt_epi8(x4, v0), _mm_cmpgt_epi8(x12, v0)));
+      __m128i md = _mm_and_si128(_mm_or_si128(_mm_cmpgt_epi8(v1, x0), _mm_cmpgt_epi8(v1, x8)),
+                                 _mm_or_si128(_mm_cmpgt_epi8(v1, x4), _mm_cmpgt_epi8(v1, x12)));
+      int m = _mm_movemask_epi8(_mm_or_si128(mb, md));
+      if (m) {   // two more diameters before falling back to the scalar test
+        const __m128i x2 = ld(2), x10 = ld(10), x6 = ld(6), x14 = ld(14);
+        mb = _mm_and_si128(mb, _mm_and_si128(_mm_or_si128(_mm_cmpgt_epi8(x2, v0), _mm_cmpgt_epi8(x10, v0)),
+                                             _mm_or_si128(_mm_cmpgt_epi8(x6, v0), _mm_cmpgt_epi8(x14, v0))));
+        md = _mm_and_si128(md, _mm_and_si128(_mm_or_si128(_mm_cmpgt_epi8(v1, x2), _mm_cmpgt_epi8(v1, x10)),
+                                             _mm_or_si128(_mm_cmpgt_epi8(v1, x6), _mm_cmpgt_epi8(v1, x14))));
+        m = _mm_movemask_epi8(_mm_or_si128(mb, md));
       }
-      if (!alive_b && !alive_d) continue;
-      auto has_arc9 = [](int m) {
-        unsigned r = (unsigned)m | ((unsigned)m << 16);
-        unsigned t = r & (r >> 1);
-        t &= t >> 2;
-        t &= t >> 4;
-        t &= r >> 8;
-        return t != 0;
-      };
-      if (!((alive_b && has_arc9(br)) || (alive_d && has_arc9(dk)))) continue;
-      int d[16];
-      for (int k = 0; k < 16; ++k) d[k] = v - p[off[k]];
-      int s = corner_score(d);
-      if (!nms) out.push_back({x, y, s});
-      else S[(size_t)y * w + x] = (uint8_t)s;
+      while (m) {
+        const int i = __builtin_ctz(m);
+        m &= m - 1;
+        test_pixel(p + i, x + i, y);
+      }
     }
+#endif
+    for (; x < w - 3; ++x) test_pixel(row + x, x, y);
   }
   if (!nms) return;
-  for (int y = 3; y < h - 3; ++y) {
-    const uint8_t* r = S + (size_t)y * w;
-    for (int x = 3; x < w - 3; ++x) {
-      int s = r[x];
-      if (s == 0) continue;  // stored 0 == not a corner at th; a corner scoring 0 never beats its neighbours
-      if (s > r[x - 1] && s > r[x + 1] && s > r[x - w - 1] && s > r[x - w] && s > r[x - w + 1] &&
-          s > r[x + w - 1] && s > r[x + w] && s > r[x + w + 1])
-        out.push_back({x, y, s});
-    }
+  for (int idx : sc.pos) {     // detection order is row-major, so is the emission order
+    const uint8_t* r = S + idx;
+    const int s = r[0];
+    if (s == 0) continue;      // stored 0 == not a corner at th; a corner scoring 0 never beats its neighbours
+    if (s > r[-1] && s > r[1] && s > r[-w - 1] && s > r[-w] && s > r[-w + 1] && s > r[w - 1] && s > r[w] && s > r[w + 1])
+      out.push_back({idx % w, idx / w, s});
   }
 }
 
@@ -283,6 +324,7 @@ struct Extractor {
   std::vector<std::vector<KeyPoint>> levelKeys;   // per level, level coordinates, after orientation
   FastScratch fs;
   long n_fast_calls = 0, n_raw = 0;
+  double t_stage[6] = {0, 0, 0, 0, 0, 0};   // seconds: pyramid, FAST, selection, orientation, blur, descriptors
 
   Extractor(int nf, float sf, int nl, int ini, int mn, bool intro)
       : nfeatures(nf), scaleFactor(sf), nlevels(nl), iniThFAST(ini), minThFAST(mn), enableIntrospection(intro) {
@@ -462,8 +504,10 @@ int compute_keypoints_old(Extractor& e) {
         const int x0 = (int)iniX, y0 = (int)iniY, ww = (int)(iniX + hX) - x0, wh = (int)(iniY + hY) - y0;
         if (x0 < 0 || y0 < 0 || x0 + ww > L.w || y0 + wh > L.h) return -2;
         const uint8_t* win = &L.img[(size_t)y0 * L.w + x0];
+        const auto tf0 = std::chrono::steady_clock::now();
         fast9_nms(win, ww, wh, L.w, e.iniThFAST, true, corners, e.fs); e.n_fast_calls++;
         if (corners.size() <= 3) { fast9_nms(win, ww, wh, L.w, e.minThFAST, true, corners, e.fs); e.n_fast_calls++; }
+        e.t_stage[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();
         std::vector<KeyPoint>& kc = cellKP[c];
         kc.resize(corners.size());
         for (size_t k = 0; k < corners.size(); ++k)
@@ -511,8 +555,10 @@ int compute_keypoints_old(Extractor& e) {
       }
     if ((int)keypoints.size() > nDesired) retain_best_resize(keypoints, nDesired);   // :1162-1166
   }
+  const auto ta0 = std::chrono::steady_clock::now();
   for (int level = 0; level < e.nlevels; ++level)   // :1208-1210
     for (KeyPoint& kp : e.levelKeys[level]) kp.angle = ic_angle(e.lv[level], kp.x, kp.y, e.umax);
+  e.t_stage[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - ta0).count();
   return 0;
 }
 
@@ -523,9 +569,17 @@ int extract(Extractor& e, const uint8_t* img, int w, int h, size_t stride, const
   if (!img || w <= 0 || h <= 0) return 0;   // :1227-1228 empty image => silent return
   if (cost && e.enableIntrospection) { e.qualityAvailable = true; compute_pyramid(e, cost, w, h, cost_stride, true); }
   else e.qualityAvailable = false;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t0 = now();
   compute_pyramid(e, img, w, h, stride, false);
+  const auto t1 = now();
+  const double fast_before = e.t_stage[1], ang_before = e.t_stage[3];
   int rc = compute_keypoints_old(e);
   if (rc) return rc;
+  const auto t2 = now();
+  e.t_stage[0] += secs(t0, t1);
+  e.t_stage[2] += secs(t1, t2) - (e.t_stage[1] - fast_before) - (e.t_stage[3] - ang_before);
   int n = 0;
   for (int l = 0; l < e.nlevels; ++l) n += (int)e.levelKeys[l].size();
   if (n > cap) return -3;
@@ -535,7 +589,10 @@ int extract(Extractor& e, const uint8_t* img, int w, int h, size_t stride, const
     Level& L = e.lv[l];
     if (keys.empty()) { L.blur.clear(); continue; }
     L.blur.resize((size_t)L.w * L.h);
+    const auto tb0 = now();
     gauss7_u8(L.img.data(), L.w, L.h, L.w, L.blur.data(), L.w);
+    const auto tb1 = now();
+    e.t_stage[4] += secs(tb0, tb1);
     for (size_t i = 0; i < keys.size(); ++i) {
       orb_descriptor(e, L, keys[i], desc + (size_t)(offset + i) * 32);
       KeyPoint k = keys[i];
@@ -543,6 +600,7 @@ int extract(Extractor& e, const uint8_t* img, int w, int h, size_t stride, const
       kps[offset + i] = k;
     }
     offset += (int)keys.size();
+    e.t_stage[5] += secs(tb1, now());
   }
   *n_out = n;
   return 0;
@@ -729,6 +787,7 @@ int orc_level_grid(void* h, int level, int* out /*cols,rows,cellW,cellH*/) {
   Grid g; if (!level_grid(*(Extractor*)h, level, g)) return -2;
   out[0] = g.cols; out[1] = g.rows; out[2] = g.cellW; out[3] = g.cellH; return 0;
 }
+void orc_stage_seconds(void* h, double* out6) { Extractor* e = (Extractor*)h; for (int i = 0; i < 6; ++i) out6[i] = e->t_stage[i]; }
 void orc_stats(void* h, long* n_fast_calls, long* n_raw) { Extractor* e = (Extractor*)h; *n_fast_calls = e->n_fast_calls; *n_raw = e->n_raw; }
 
 int orc_stereo_match(void* left, void* right, const void* kL, int N, const uint8_t* dL, const void* kR, int Nr,

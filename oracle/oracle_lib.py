@@ -92,6 +92,8 @@ def lib():
     L.orc_level_grid.restype = C.c_int
     L.orc_stats.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     L.orc_stats.restype = None
+    L.orc_stage_seconds.argtypes = [vp, vp]
+    L.orc_stage_seconds.restype = None
     L.orc_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]
     L.orc_stereo_match.restype = C.c_int
     L.orc_stereo_frame.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_float,
@@ -227,6 +229,12 @@ class OracleExtractor:
         out = np.zeros(4, np.int32)
         rc = lib().orc_level_grid(self.h, level, _p(out))
         return None if rc else tuple(int(v) for v in out)
+
+    def stage_seconds(self):
+        """Accumulated seconds per stage: pyramid, FAST, selection, orientation, blur, descriptors."""
+        out = np.zeros(6, np.float64)
+        lib().orc_stage_seconds(self.h, _p(out))
+        return dict(zip(("pyramid", "fast", "select", "orient", "blur", "describe"), out.tolist()))
 
     def stats(self):
         a, b = C.c_long(), C.c_long()
