@@ -200,6 +200,7 @@ def main():
     # ------------------------------------------------------------------ device-resident arm (`value`)
     a = (params["nfeatures"], params["scaleFactor"], params["nlevels"], params["iniThFAST"], params["minThFAST"])
     resL, resR = api.ORBextractor(*a, False, device=local), api.ORBextractor(*a, False, device=local)
+    resR.share_stream(resL)     # one kernel stream: left and right extraction run back to back, not interleaved
     resL.upload(pinL.array)
     resR.upload(pinR.array)
     resL.sync(), resR.sync()

@@ -102,6 +102,10 @@ int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, 
 int ivg_run_batch(ivg_extractor* h);
 int ivg_download_batch(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
 int ivg_sync(ivg_extractor* h);
+/* Makes `h` launch its kernels on `owner`'s stream (same device; `owner` must outlive `h`).  Handles that share a
+ * stream never run kernels concurrently — measured ~20 % faster at large batches than letting the left and right
+ * extraction overlap — while their H2D/D2H copies, which use per-handle copy streams, still overlap the kernels. */
+int ivg_share_stream(ivg_extractor* h, ivg_extractor* owner);
 
 /* Device-side level-0 input plane of frame `index` (pitch in *pitch): lets a producer already on the GPU (e.g. the
  * introspection CNN's cost-map) write inputs without a host round trip.  which: 0 image, 2 cost-map.

@@ -65,6 +65,7 @@ def lib():
         "ivg_run_batch": (C.c_int, [vp]),
         "ivg_download_batch": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "ivg_sync": (C.c_int, [vp]),
+        "ivg_share_stream": (C.c_int, [vp, vp]),
         "ivg_set_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "ivg_device_input": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(sz)]),
         "ivg_level_size": (C.c_int, [vp, C.c_int, i32p, i32p]),
@@ -238,6 +239,11 @@ class ORBextractor:
 
     def sync(self):
         _ck(lib().ivg_sync(self._h), "ivg_sync")
+
+    def share_stream(self, owner):
+        """Run this extractor's kernels on `owner`'s stream (no kernel overlap between the two; copies still overlap)."""
+        _ck(lib().ivg_share_stream(self._h, owner._h), "ivg_share_stream")
+        self._stream_owner = owner      # keep the owner alive
 
     def compute_pyramid(self, image):
         _ck(lib().ivg_compute_pyramid(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0]), "ivg_compute_pyramid")

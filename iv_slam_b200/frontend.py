@@ -22,6 +22,12 @@ class StereoFrontend:
             right = api.ORBextractor(*a, False, device=device)
             left.reserve(width, height, chunk)
             right.reserve(width, height, chunk)
+            # one kernel stream for everything on this device: kernels of different chunks / eyes never co-run (that
+            # costs ~20 % at these sizes); the per-handle copy streams keep H2D/D2H overlapped with the kernels
+            owner = self.slots[0][0] if self.slots else left
+            if left is not owner:
+                left.share_stream(owner)
+            right.share_stream(owner)
             self.slots.append((left, right))
         self.cap = self.slots[0][0].cap
 
@@ -64,7 +70,7 @@ class StereoFrontend:
         return sum(l.launch_count() + r.launch_count() for l, r in self.slots)
 
     def close(self):
-        for l, r in self.slots:
-            l.close()
+        for l, r in reversed(self.slots):       # the stream owner (slot 0, left) goes last
             r.close()
+            l.close()
         self.slots = []
