@@ -119,7 +119,7 @@ def cpu_frontend_fps(imgsL, imgsR, workers, reps=1):
     return len(imgsL) * reps / dt, dt, int(nL.sum()), int(nM.sum())
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """Reference arm: the reference's CPU path (oracle port) on all host threads, frame-parallel; rank 0 only."""
     if rank != 0:
         return
@@ -144,18 +144,27 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": workers, "kind": "port",
                              "sample": "%d pairs per step, %d steps" % (sample, args.steps)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout, so everything
+    # else is sent to stderr and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="stereo pairs per GPU per step")
-    ap.add_argument("--chunk", type=int, default=128, help="stereo pairs per launch group")
-    ap.add_argument("--slots", type=int, default=3)
+    ap.add_argument("--chunk", type=int, default=256, help="stereo pairs per launch group")
+    ap.add_argument("--slots", type=int, default=2)
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic base images per rank")
     ap.add_argument("--cpu-sample", type=int, default=256, help="pairs in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=128, help="pairs per step for --impl reference")
@@ -167,7 +176,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -262,13 +271,22 @@ def main():
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         shares = {k: v[0] / tot_ms for k, v in prof.items()}
         dom = max(prof, key=lambda k: prof[k][0])
-        units = B * 2 if dom not in ("k_stereo_match", "k_stereo_median") else B      # images (or pairs) per launch
+        units = B      # images (extractor kernels: one launch per eye) or pairs (stereo kernels) per launch
         per_launch_ms = prof[dom][0] / max(prof[dom][1], 1)
         if dom == "k_resize_level":
-            # 7 launches per image set: per-launch bytes = total / 7
-            bytes_per_launch = alg[dom] * units / 7.0
+            bytes_per_launch = alg[dom] * units / 7.0      # 7 launches per eye: per-launch bytes = total / 7
+        elif dom == "k_stereo_match":
+            bytes_per_launch = alg[dom] * units / 2.0      # index + match launches are accounted under one id
         else:
             bytes_per_launch = alg[dom] * units
+        traffic = None
+        try:     # measured DRAM bytes per image of the same kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "ncu_dram_bytes_per_image.json")) as f:
+                per_img = json.load(f).get(dom)
+            if per_img:
+                traffic = per_img * units
+        except Exception:
+            pass
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
         pair_bytes = 21.9e6
         line = {
@@ -283,13 +301,27 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_kind, "bytes_per_launch": bytes_per_launch,
+                         "traffic": traffic, "peak_source": peak_kind, "bytes_per_launch": bytes_per_launch,
                          "ms_per_launch": per_launch_ms, "share_of_device_time": shares[dom],
                          "whole_pipeline_GBps": pair_bytes * value / world / 1e9},
             "kernel_shares": {k: round(v, 4) for k, v in shares.items()},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "check": {"keypoints_per_pair_left": n_kp / B, "stereo_matches_per_pair": n_match / B},
         }
+        # drop-in usage (one frame at a time, two extractor objects driven from two host threads, then the matcher)
+        lL, lR = api.ORBextractor(*a, False, device=local), api.ORBextractor(*a, False, device=local)
+        def one_pair(i):
+            tl = threading.Thread(target=lambda: lL(Lh[i % B]))
+            tr = threading.Thread(target=lambda: lR(Rh[i % B]))
+            tl.start(); tr.start(); tl.join(); tr.join()
+            api.compute_stereo_matches(lL, lR, KITTI["mbf"], KITTI["maxD"])
+        for i in range(5):
+            one_pair(i)
+        t1 = time.perf_counter()
+        for i in range(50):
+            one_pair(i)
+        line["single_pair_latency_ms"] = 1e3 * (time.perf_counter() - t1) / 50
+        lL.close(); lR.close()
         if not args.no_cpu_baseline:
             ncpu = os.cpu_count() or 1
             n_s = min(args.cpu_sample, B)
@@ -306,7 +338,7 @@ def main():
                                     "sample": "first %d pairs of the workload, frame-parallel over %d threads, %.1f s wall" % (n_s, ncpu, dt_all),
                                     "reference_threading_2plus1": {"value": fps_ref_threads, "cores": 2,
                                                                    "note": "one frame at a time, 2 extraction threads + matching, as src/Frame.cc:115-125,:193"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     if world > 1:
         dist.destroy_process_group()

@@ -294,6 +294,10 @@ class ORBextractor:
         _ck(lib().ivg_profile_read(self._h, _p(ms), _p(cnt)), "ivg_profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_NAMES)}
 
+    def set_graph_mode(self, on=True):
+        """Replay the kernel sequence of a run as one CUDA graph (single-frame latency)."""
+        _ck(lib().ivg_set_graph_mode(self._h, int(on)), "ivg_set_graph_mode")
+
     def flush_l2(self, nbytes=256 << 20):
         _ck(lib().ivg_flush_l2(self._h, nbytes), "ivg_flush_l2")
 

@@ -110,6 +110,9 @@ struct ivg_extractor {
   // stereo on caller-supplied keypoints
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
   bool graphMode = false;
+  cudaGraphExec_t graphExec = nullptr;   // captured kernel sequence of one run (re-captured when batch / mode / buffers change)
+  int graphBatch = 0, graphLaunches = 0;
+  bool graphWeighted = false;
   // per-kernel CUDA-event profile (bench.py roofline): events bracket every launch while enabled
   bool profile = false;
   std::vector<cudaEvent_t> profEv;     // pairs
@@ -136,6 +139,10 @@ struct ProfScope {   // brackets one kernel launch with two events when profilin
   }
   ~ProfScope() { if (on) cudaEventRecord(h->profEv[slot + 1], h->stream); }
 };
+
+void drop_graph(ivg_extractor* h) {
+  if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
+}
 
 int build_tables(ivg_extractor* h) {
   // src/ORBextractor.cc:417-432 (float tables; the scaleFactor member is double, include/ORBextractor.h:108)
@@ -342,6 +349,7 @@ int ensure_shape(ivg_extractor* h, int W, int H, int batch) {
   CK(cudaStreamSynchronize(h->stream));
   const int b = (h->shapeReady && h->W == W && h->H == H) ? std::max(batch, h->maxBatch) : batch;
   h->shapeReady = false;
+  drop_graph(h);
   return build_shape(h, W, H, b);
 }
 
@@ -368,8 +376,7 @@ int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
   return IVG_OK;
 }
 
-int launch_extract(ivg_extractor* h) {
-  const FrameSet fs = active_fs(h);
+int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   int rc = launch_pyramid(h, fs);
   if (rc) return rc;
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
@@ -377,10 +384,38 @@ int launch_extract(ivg_extractor* h) {
   { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs); }
   CK(cudaGetLastError());
-  h->haveResults = true; h->havePyramid = true;
   return IVG_OK;
 }
 
+int launch_extract(ivg_extractor* h) {
+  const FrameSet fs = active_fs(h);
+  if (h->graphMode && !h->profile) {
+    // one graph launch instead of ~11 kernel launches: matters for the one-frame-at-a-time (drop-in) use
+    if (!h->graphExec || h->graphBatch != fs.nImages || h->graphWeighted != (fs.weighted != 0)) {
+      drop_graph(h);
+      cudaGraph_t g = nullptr;
+      const long long before = h->launches;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = launch_extract_kernels(h, fs);
+      cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) { g_cuda_err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return IVG_ERR_CUDA; }
+      e = cudaGraphInstantiate(&h->graphExec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { g_cuda_err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); h->graphExec = nullptr; return IVG_ERR_CUDA; }
+      h->graphLaunches = (int)(h->launches - before);
+      h->launches = before;
+      h->graphBatch = fs.nImages; h->graphWeighted = fs.weighted != 0;
+    }
+    CK(cudaGraphLaunch(h->graphExec, h->stream));
+    h->launches += h->graphLaunches;
+  } else {
+    int rc = launch_extract_kernels(h, fs);
+    if (rc) return rc;
+  }
+  h->haveResults = true; h->havePyramid = true;
+  return IVG_OK;
+}
 
 int init_device_constants(int device) {
   CK(cudaSetDevice(device));
@@ -482,6 +517,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
   h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->sortedR.release(); h->rowStart.release();
   for (cudaEvent_t e : h->profEv) cudaEventDestroy(e);
+  drop_graph(h);
   if (h->evDone) cudaEventDestroy(h->evDone);
   if (h->evT0) cudaEventDestroy(h->evT0);
   if (h->evT1) cudaEventDestroy(h->evT1);
@@ -614,6 +650,7 @@ int ivg_sync(ivg_extractor* h) {
 int ivg_share_stream(ivg_extractor* h, ivg_extractor* owner) {
   if (!h || !owner || h == owner || h->device != owner->device) return IVG_ERR_INVALID;
   CK(cudaStreamSynchronize(h->stream));
+  drop_graph(h);
   if (h->ownsStream) cudaStreamDestroy(h->stream);
   h->stream = owner->stream;
   h->ownsStream = false;
@@ -826,6 +863,11 @@ int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches) {
   for (int k = 0; k < IVG_NUM_KERNELS; ++k) { if (ms) ms[k] = h->profMs[k]; if (launches) launches[k] = h->profCnt[k]; }
   return IVG_OK;
 }
-int ivg_set_graph_mode(ivg_extractor* h, int enable) { if (!h) return IVG_ERR_INVALID; h->graphMode = enable != 0; return IVG_OK; }
+int ivg_set_graph_mode(ivg_extractor* h, int enable) {
+  if (!h) return IVG_ERR_INVALID;
+  h->graphMode = enable != 0;
+  if (!h->graphMode) drop_graph(h);
+  return IVG_OK;
+}
 
 }  // extern "C"

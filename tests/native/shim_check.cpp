@@ -1,8 +1,10 @@
 // Drives shim/ORBextractor.{h,cc} + shim/Frame_ComputeStereoMatches.cc (compiled against tests/fake_opencv) exactly the
 // way Frame::Frame does in the reference (src/Frame.cc:115-125, :193): two extractor objects, operator() on each eye,
 // then ComputeStereoMatches.  Built and called by tests/test_shim.py.
+#include <chrono>
 #include <cstring>
 #include <exception>
+#include <thread>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -38,4 +40,32 @@ extern "C" int shim_stereo_frame(const unsigned char* left, const unsigned char*
 extern "C" int shim_construct_only() {
   try { ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7); return 0; }
   catch (const std::exception&) { return -1; }
+}
+
+// Drop-in latency: one stereo frame at a time exactly like the reference's Frame constructor — two std::threads run the
+// two extractor objects (src/Frame.cc:115-125), join, then ComputeStereoMatches (:193).  Returns mean milliseconds.
+#include "ivslam_gpu.h"
+extern "C" double shim_frame_latency_ms(const unsigned char* left, const unsigned char* right, int w, int h, int nfeatures,
+                                        int iniTh, int minTh, float mbf, float maxD, int iters, int graph) {
+  try {
+    ORB_SLAM2::ORBextractor exL(nfeatures, 1.2f, 8, iniTh, minTh), exR(nfeatures, 1.2f, 8, iniTh, minTh);
+    ivg_set_graph_mode(exL.handle(), graph);
+    ivg_set_graph_mode(exR.handle(), graph);
+    cv::Mat imL(h, w, CV_8UC1, (void*)left, (size_t)w), imR(h, w, CV_8UC1, (void*)right, (size_t)w), none;
+    std::vector<cv::KeyPoint> kL, kR;
+    cv::Mat dL, dR;
+    std::vector<float> u, d;
+    auto frame = [&] {
+      std::thread tl([&] { exL(imL, none, kL, dL); });
+      std::thread tr([&] { exR(imR, none, kR, dR); });
+      tl.join(); tr.join();
+      ORB_SLAM2::ComputeStereoMatchesGPU(&exL, &exR, (int)kL.size(), mbf, maxD, u, d);
+    };
+    for (int i = 0; i < 5; ++i) frame();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < iters; ++i) frame();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+  } catch (const std::exception&) {
+    return -1.0;
+  }
 }

@@ -239,3 +239,15 @@ def test_two_handles_from_two_threads(gpu_api, oracle):
     r = oracle.stereo_frame(oL, oR, left, right, None, 386.1448, 718.856)
     assert_keypoints_equal(out["L"][0], r["kL"]), assert_keypoints_equal(out["R"][0], r["kR"])
     assert_stereo_close(u[:r["kL"].size], d[:r["kL"].size], r["uRight"], r["depth"])
+
+
+def test_graph_mode_is_bit_identical(gpu_api):
+    """CUDA-graph replay of the kernel sequence (single-frame latency mode) must not change a byte, across shape changes."""
+    a = S.make_image(1241, 376, 21)
+    b = S.make_image(960, 600, 22)
+    plain, graph = gpu_api.ORBextractor(2000, 1.2, 8, 20, 7), gpu_api.ORBextractor(2000, 1.2, 8, 20, 7)
+    graph.set_graph_mode(True)
+    for img in (a, a, b, a):
+        k1, d1 = plain(img)
+        k2, d2 = graph(img)
+        assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
