@@ -16,6 +16,7 @@
 
 #include "../../include/ivslam_gpu.h"
 #include "common.cuh"
+#include "tma.cuh"
 #include "k_blur.cuh"
 #include "k_describe.cuh"
 #include "k_fast.cuh"
@@ -99,6 +100,7 @@ struct ivg_extractor {
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
   size_t fastSmem = 0, resizeSmem = 0, selSmem = 0;
+  TmaMaps blurMaps{};                   // per level: 144 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
   DevBuf<uint32_t> cellList, cellCost;
@@ -139,6 +141,32 @@ struct ProfScope {   // brackets one kernel launch with two events when profilin
   }
   ~ProfScope() { if (on) cudaEventRecord(h->profEv[slot + 1], h->stream); }
 };
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// u8 tensor (x, y, frame) over one pyramid level of a plane: TMA boxes of boxW x boxH x 1, zero fill outside the image
+int make_level_map(CUtensorMap* out, uint8_t* base, int w, int h, int pitch, size_t planeBytes, int frames, int boxW, int boxH) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+      g_cuda_err = "cuTensorMapEncodeTiled entry point not available";
+      return IVG_ERR_CUDA;
+    }
+    fn = (PFN_encodeTiled)p;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)planeBytes};
+  const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return IVG_ERR_CUDA; }
+  return IVG_OK;
+}
 
 void drop_graph(ivg_extractor* h) {
   if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
@@ -336,6 +364,10 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   fs.cellList = h->cellList.p; fs.cellCount = h->cellCount.p; fs.cellCost = h->cellCost.p;
   fs.workCell = h->workCell.p; fs.workLevel = h->workLevel.p; fs.levelKp = h->levelKp.p;
   fs.levelCount = h->levelCount.p; fs.outKp = h->outKp.p; fs.outDesc = h->outDesc.p; fs.outN = h->outN.p;
+  for (int l = 0; l < nl; ++l)
+    if ((rc = make_level_map(&h->blurMaps.m[l], h->pyr.p + fs.lv[l].planeOff, fs.lv[l].w, fs.lv[l].h, fs.lv[l].pitch, fs.planeBytes,
+                             batch, BL_BOXW, BL_PH)))
+      return rc;
   h->fs = fs;
   h->W = W; h->H = H; h->maxBatch = batch; h->shapeReady = true;
   h->haveResults = false; h->havePyramid = false; h->curBatch = 0;
@@ -380,7 +412,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   int rc = launch_pyramid(h, fs);
   if (rc) return rc;
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
-  { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
   { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs); }
   CK(cudaGetLastError());

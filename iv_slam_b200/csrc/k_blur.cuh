@@ -4,19 +4,23 @@
 // (SURVEY Appendix A.2): Q8 kernel {18,34,48,56,48,34,18}, 16-bit horizontal sums, (v + 2^15) >> 16.
 //
 // Separable, one CTA per 128x32 tile (tile table spans all levels and frames: one launch per batch).
-//   stage       tile + 3 px halo into shared memory with aligned 32-bit loads (reflection applied while loading; only
-//               words that straddle the image edge take the per-byte path);
+//   stage       tile + halo (160 x 38 bytes) lands in shared memory through ONE TMA box load (cp.async.bulk.tensor.3d over
+//               x, y, frame; out-of-image bytes arrive as zeros) signalled on an mbarrier; only tiles that touch an image
+//               edge then patch their halo by reflection from the bytes already in shared memory;
 //   horizontal  4 pixels per thread in packed 16-bit lanes: the row sums are < 2^16, so one IMAD on a register holding
 //               two pixels (x, x+2) is two exact multiply-adds — 8 masked funnel-shifted windows feed both the even
 //               and the odd pixel pair (28 instructions per 4 pixels);
 //   vertical    4 pixels x 4 rows per thread from the packed 16-bit plane, one aligned 32-bit store per row.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ivg {
 
 constexpr int BL_W = 128, BL_H = 32;
-constexpr int BL_PW = (BL_W + 8) / 4;     // staged words per row: x0-4 .. x0+131
+constexpr int BL_BOXW = 160;              // TMA box width in bytes: x0-16 .. x0+143 (the box must start 16-byte aligned)
+constexpr int BL_X0 = 16;                 // staged byte index of tile column 0
+constexpr int BL_PW = BL_BOXW / 4;        // staged words per row
 constexpr int BL_PH = BL_H + 6;
 
 __device__ __forceinline__ int reflect101(int p, int n) {
@@ -25,8 +29,9 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_gauss7(FrameSet fs) {
-  __shared__ __align__(16) uint32_t spx[BL_PH * BL_PW];
+__global__ void __launch_bounds__(256) k_gauss7(FrameSet fs, const __grid_constant__ TmaMaps maps) {
+  __shared__ __align__(128) uint32_t spx[BL_PH * BL_PW];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) uint2 shs[BL_PH * (BL_W / 4)];
 
   int level = 0;
@@ -37,30 +42,44 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs) {
   const int t = blockIdx.x - L.btBase;
   const int x0 = (t % L.btX) * BL_W, y0 = (t / L.btX) * BL_H;
   const size_t frameOff = (size_t)blockIdx.y * fs.planeBytes + L.planeOff;
-  const uint8_t* img = fs.pyr + frameOff;
   const int tid = threadIdx.x;
 
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, BL_PH * BL_BOXW);
+    tma_load_3d(spx, &maps.m[level], &bar, x0 - BL_X0, y0 - 3, (int)blockIdx.y);
+  }
+  mbar_wait(&bar, 0);
   {
-    const int w = L.w, h = L.h, pitch = L.pitch;
-    for (int i = tid; i < BL_PH * BL_PW; i += 256) {
-      const int r = i / BL_PW, g = i - r * BL_PW;
-      // reflect-101 of a row index in [-3, h+2]: one reflection suffices (h >= 4)
-      int gy = min(y0 - 3 + r, h + 2);
-      gy = abs(gy);
-      gy = min(gy, 2 * h - 2 - gy);
-      const int gx = x0 - 4 + 4 * g;
-      const uint8_t* row = img + (size_t)gy * pitch;
-      uint32_t v = 0;
-      if (gx >= 0 && gx + 3 < w) v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-      else if (gx <= w + 2) {                        // straddles an image edge; columns past w+2 are never used
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int x = abs(min(gx + k, w + 2));
-          x = min(x, 2 * w - 2 - x);
-          v |= (uint32_t)__ldg(row + x) << (8 * k);
+    // reflect-101 patches, only where the box left the image (block-uniform conditions): rows first, then columns
+    const int w = L.w, h = L.h;
+    uint8_t* sb = reinterpret_cast<uint8_t*>(spx);
+    const bool top = y0 == 0, bottom = y0 + BL_H + 3 > h;
+    if (top || bottom) {
+      for (int i = tid; i < 6 * BL_PW; i += 256) {
+        const int k = i / BL_PW, g = i - k * BL_PW;
+        if (k < 3) {                       // rows -3..-1 <- rows 3..1
+          if (top) spx[k * BL_PW + g] = spx[(6 - k) * BL_PW + g];
+        } else if (bottom) {               // rows h..h+2 <- rows h-2..h-4
+          const int gy = h + (k - 3), r = gy - (y0 - 3);
+          if (r < BL_PH) spx[r * BL_PW + g] = spx[(2 * h - 2 - gy - (y0 - 3)) * BL_PW + g];
         }
       }
-      spx[i] = v;
+      __syncthreads();
+    }
+    const bool left = x0 == 0, right = x0 + BL_W + 3 > w;
+    if (left || right) {
+      for (int i = tid; i < 6 * BL_PH; i += 256) {
+        const int r = i / 6, k = i - r * 6;
+        uint8_t* row = sb + r * BL_BOXW;
+        if (k < 3) {                       // columns -3..-1 <- columns 3..1   (staged index = column - x0 + BL_X0)
+          if (left) row[BL_X0 - 3 + k] = row[BL_X0 + 3 - k];
+        } else if (right) {                // columns w..w+2 <- columns w-2..w-4
+          const int gx = w + (k - 3), c = gx - x0 + BL_X0;
+          if (c < BL_BOXW) row[c] = row[2 * w - 2 - gx - x0 + BL_X0];
+        }
+      }
     }
   }
   __syncthreads();
@@ -68,7 +87,7 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs) {
   const uint32_t M = 0x00FF00FFu;
   for (int i = tid; i < BL_PH * (BL_W / 4); i += 256) {
     const int r = i / (BL_W / 4), g = i - r * (BL_W / 4);
-    const uint32_t* w = spx + r * BL_PW + g;
+    const uint32_t* w = spx + r * BL_PW + (BL_X0 / 4 - 1) + g;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];        // pixels x-4..x-1, x..x+3, x+4..x+7
     const uint32_t G0 = __funnelshift_r(w0, w1, 8) & M, G1 = __funnelshift_r(w0, w1, 16) & M, G2 = __funnelshift_r(w0, w1, 24) & M;
     const uint32_t G3 = w1 & M;
