@@ -100,7 +100,9 @@ struct ivg_extractor {
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
   size_t fastSmem = 0, resizeSmem = 0, selSmem = 0;
-  TmaMaps blurMaps{};                   // per level: 144 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
+  TmaMaps blurMaps{};                   // per level: 160 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
+  TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
+  bool resizeTma[MAX_LEVELS] = {false};
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
   DevBuf<uint32_t> cellList, cellCost;
@@ -300,15 +302,15 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
       int maxW = 1, maxR = 1;
       for (int x0 = 0; x0 < L.w; x0 += RZ_W) {
         const int x1 = std::min(x0 + RZ_W, L.w) - 1;
-        const int sxa = taps[L.rtabX + x0].s0 & ~3, sxe = taps[L.rtabX + x1].s1;
+        const int sxa = taps[L.rtabX + x0].s0 & ~15, sxe = taps[L.rtabX + x1].s1;
         maxW = std::max(maxW, (sxe - sxa) / 4 + 1);
       }
       for (int y0 = 0; y0 < L.h; y0 += RZ_H) {
         const int y1 = std::min(y0 + RZ_H, L.h) - 1;
         maxR = std::max(maxR, taps[L.rtabY + y1].s1 - taps[L.rtabY + y0].s0 + 1);
       }
-      L.rzPitch = maxW * 4; L.rzRows = maxR;
-      resizeSmem = std::max(resizeSmem, align_up((size_t)L.rzPitch * L.rzRows, 16) + (size_t)L.rzRows * RZ_W * 2);
+      L.rzPitch = (int)align_up((size_t)maxW * 4, 16); L.rzRows = maxR;        // = TMA box (bytes x rows)
+      resizeSmem = std::max(resizeSmem, align_up((size_t)L.rzPitch * L.rzRows, 128) + (size_t)L.rzRows * RZ_W * 2);
     }
   }
   fs.planeBytes = align_up(planeOff, (size_t)fs.lv[0].pitch * 4);   // multiple of the level-0 pitch: batched 3-D copies
@@ -364,6 +366,16 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   fs.cellList = h->cellList.p; fs.cellCount = h->cellCount.p; fs.cellCost = h->cellCost.p;
   fs.workCell = h->workCell.p; fs.workLevel = h->workLevel.p; fs.levelKp = h->levelKp.p;
   fs.levelCount = h->levelCount.p; fs.outKp = h->outKp.p; fs.outDesc = h->outDesc.p; fs.outN = h->outN.p;
+  for (int l = 1; l < nl; ++l) {
+    const LevelDev& D = fs.lv[l];
+    const LevelDev& S = fs.lv[l - 1];
+    h->resizeTma[l] = D.rzPitch <= 256 && D.rzRows <= 256;
+    if (!h->resizeTma[l]) continue;
+    if ((rc = make_level_map(&h->resizeMaps.m[l], h->pyr.p + S.planeOff, S.w, S.h, S.pitch, fs.planeBytes, batch, D.rzPitch, D.rzRows))) return rc;
+    if (h->enableIntrospection &&
+        (rc = make_level_map(&h->resizeMapsQ.m[l], h->qual.p + S.planeOff, S.w, S.h, S.pitch, fs.planeBytes, batch, D.rzPitch, D.rzRows)))
+      return rc;
+  }
   for (int l = 0; l < nl; ++l)
     if ((rc = make_level_map(&h->blurMaps.m[l], h->pyr.p + fs.lv[l].planeOff, fs.lv[l].w, fs.lv[l].h, fs.lv[l].pitch, fs.planeBytes,
                              batch, BL_BOXW, BL_PH)))
@@ -401,8 +413,8 @@ FrameSet active_fs(const ivg_extractor* h) {
 int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
   for (int l = 1; l < fs.nlevels; ++l) {
     dim3 grid((fs.lv[l].w + RZ_W - 1) / RZ_W, (fs.lv[l].h + RZ_H - 1) / RZ_H, fs.nImages);
-    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 0); }
-    if (fs.weighted) { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 1); }
+    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 0, h->resizeMaps, h->resizeTma[l] ? 1 : 0); }
+    if (fs.weighted) { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 1, h->resizeMapsQ, h->resizeTma[l] ? 1 : 0); }
   }
   CK(cudaGetLastError());
   return IVG_OK;

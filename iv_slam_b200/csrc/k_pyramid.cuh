@@ -3,14 +3,17 @@
 // (introspective_ORB_SLAM/src/ORBextractor.cc:1298-1357, resize calls at :1311 and :1341).
 // Arithmetic = OpenCV's 8-bit fixed-point bilinear path: taps and Q11 coefficients are
 // precomputed on the host exactly as OpenCV derives them; the kernel does the integer part, separably:
-//   stage       the source rectangle of a 128x32 output tile goes to shared memory with aligned 32-bit loads
-//               (every source byte is read from L2/HBM once per tile);
+//   stage       the source rectangle of a 128x32 output tile lands in shared memory through ONE TMA box load
+//               (cp.async.bulk.tensor.3d over x, y, frame of the source level, signalled on an mbarrier; every source
+//               byte is read from L2/HBM once per tile).  Scale factors whose source box would exceed the 256-element
+//               TMA box limit use a plain 32-bit load loop instead;
 //   horizontal  T[sy][d] = src[sy][sx0]*cx0 + src[sy][sx1]*cx1 for every staged source row, kept as (T >> 4) in 16 bits
 //               (the only form the vertical pass uses) — each source row is filtered once, not once per output row;
 //   vertical    dst = (((cy0*T0) >> 16) + ((cy1*T1) >> 16) + 2) >> 2, 4 pixels per thread, one aligned 32-bit store.
 // HBM-bound stencil (read level l-1, write level l); the cascade is strictly sequential across levels.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ivg {
 
@@ -33,8 +36,10 @@ __global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ stag
   *reinterpret_cast<uint32_t*>(plane + f * planeBytes + (size_t)y * pitch + 4 * xw) = v;
 }
 
-__global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, int which /*0 image, 1 cost-map*/) {
-  extern __shared__ __align__(16) unsigned char rsm[];
+__global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, int which /*0 image, 1 cost-map*/,
+                                                      const __grid_constant__ TmaMaps maps, int useTma) {
+  extern __shared__ __align__(128) unsigned char rsm[];
+  __shared__ __align__(8) uint64_t bar;
   const LevelDev& D = fs.lv[level];
   const LevelDev& S = fs.lv[level - 1];
   const int x0 = blockIdx.x * RZ_W, y0 = blockIdx.y * RZ_H;
@@ -45,18 +50,29 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, in
   const ResizeTap* ty = fs.rtab + D.rtabY;
   const int tid = threadIdx.x;
   const int x1 = min(x0 + RZ_W, D.w) - 1, y1 = min(y0 + RZ_H, D.h) - 1;
-  const int sxa = tx[x0].s0 & ~3, sxe = tx[x1].s1;           // staged source columns [sxa, sxe]
+  const int sxa = tx[x0].s0 & ~15, sxe = tx[x1].s1;          // staged source columns [sxa, sxe] (16-byte aligned start for TMA)
   const int sya = ty[y0].s0, sye = ty[y1].s1;                // staged source rows [sya, sye]
   const int nW = (sxe - sxa) / 4 + 1, nR = sye - sya + 1;
   const int SPB = D.rzPitch;                                 // staged bytes per source row (host-computed bound, multiple of 4)
   uint8_t* spx = rsm;
   uint16_t* sT = reinterpret_cast<uint16_t*>(rsm + (((size_t)SPB * D.rzRows + 15) & ~(size_t)15));
 
-  for (int i = tid; i < nR * nW; i += 256) {
-    const int r = i / nW, g = i - r * nW;
-    reinterpret_cast<uint32_t*>(spx + r * SPB)[g] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(sya + r) * S.pitch + sxa + 4 * g));
+  if (useTma) {
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, (uint32_t)(SPB * D.rzRows));
+      tma_load_3d(spx, &maps.m[level], &bar, sxa, sya, (int)blockIdx.z);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int i = tid; i < nR * nW; i += 256) {
+      const int r = i / nW, g = i - r * nW;
+      const int gx = sxa + 4 * g;
+      reinterpret_cast<uint32_t*>(spx + r * SPB)[g] = gx < S.pitch ? __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(sya + r) * S.pitch + gx)) : 0u;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   {
     // thread owns one output column (two threads per column, interleaved rows)
     const int d = tid & (RZ_W - 1), half = tid >> 7;
