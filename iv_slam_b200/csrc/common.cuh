@@ -61,6 +61,7 @@ struct FrameSet {
   uint8_t* pyr; uint8_t* blur; uint8_t* qual;                    // [nImages][planeBytes]
   const CellDev* cells;                                           // active variant
   const ResizeTap* rtab;
+  const uint32_t* blurTiles;                                      // [btTotal] level<<28 | tileX<<14 | tileY
   uint32_t* cellList;      // [nImages][listCapTotal]
   int2* cellCount;         // [nImages][nCellsTotal]
   uint32_t* cellCost;      // [nImages][nCellsTotal]

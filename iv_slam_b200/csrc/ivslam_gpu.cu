@@ -105,7 +105,7 @@ struct ivg_extractor {
   bool resizeTma[MAX_LEVELS] = {false};
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
-  DevBuf<uint32_t> cellList, cellCost;
+  DevBuf<uint32_t> cellList, cellCost, blurTiles;
   DevBuf<int2> cellCount;
   DevBuf<uint2> workCell, workLevel, levelKp;
   DevBuf<int> levelCount, outN, sad, nExt, rowStart;
@@ -341,6 +341,11 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   if ((rc = h->dCellsPlain.alloc(h->cellsPlain.size()))) return rc;
   if ((rc = h->dCellsWeighted.alloc(h->cellsWeighted.size()))) return rc;
   if ((rc = h->rtab.alloc(taps.size()))) return rc;
+  std::vector<uint32_t> btab;
+  for (int l = 0; l < nl; ++l)
+    for (int ty = 0; ty < fs.lv[l].btY; ++ty)
+      for (int tx = 0; tx < fs.lv[l].btX; ++tx) btab.push_back(((uint32_t)l << 28) | ((uint32_t)tx << 14) | (uint32_t)ty);
+  if ((rc = h->blurTiles.alloc(btab.size()))) return rc;
   if ((rc = h->cellList.alloc(B * fs.listCapTotal))) return rc;
   if ((rc = h->cellCost.alloc(B * fs.nCellsTotal))) return rc;
   if ((rc = h->cellCount.alloc(B * fs.nCellsTotal))) return rc;
@@ -356,13 +361,14 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   if ((rc = h->sad.alloc(B * fs.kpCap))) return rc;
   CK(cudaMemcpyAsync(h->dCellsPlain.p, h->cellsPlain.data(), h->cellsPlain.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->dCellsWeighted.p, h->cellsWeighted.data(), h->cellsWeighted.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->blurTiles.p, btab.data(), btab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   if (!taps.empty()) CK(cudaMemcpyAsync(h->rtab.p, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->outN.p, 0, B * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->levelCount.p, 0, B * MAX_LEVELS * sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
 
   fs.pyr = h->pyr.p; fs.blur = h->blur.p; fs.qual = h->qual.p;
-  fs.rtab = h->rtab.p;
+  fs.rtab = h->rtab.p; fs.blurTiles = h->blurTiles.p;
   fs.cellList = h->cellList.p; fs.cellCount = h->cellCount.p; fs.cellCost = h->cellCost.p;
   fs.workCell = h->workCell.p; fs.workLevel = h->workLevel.p; fs.levelKp = h->levelKp.p;
   fs.levelCount = h->levelCount.p; fs.outKp = h->outKp.p; fs.outDesc = h->outDesc.p; fs.outN = h->outN.p;
@@ -556,7 +562,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
   h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release();
-  h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release();
+  h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
   h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->sortedR.release(); h->rowStart.release();

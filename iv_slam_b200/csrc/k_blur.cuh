@@ -34,13 +34,10 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs, const __grid_consta
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) uint2 shs[BL_PH * (BL_W / 4)];
 
-  int level = 0;
-#pragma unroll 1
-  for (int l = 1; l < fs.nlevels; ++l)
-    if ((int)blockIdx.x >= fs.lv[l].btBase) level = l;
+  const uint32_t tt = __ldg(fs.blurTiles + blockIdx.x);       // host-built tile table: level | tile x | tile y
+  const int level = tt >> 28;
   const LevelDev& L = fs.lv[level];
-  const int t = blockIdx.x - L.btBase;
-  const int x0 = (t % L.btX) * BL_W, y0 = (t / L.btX) * BL_H;
+  const int x0 = (int)((tt >> 14) & 0x3FFF) * BL_W, y0 = (int)(tt & 0x3FFF) * BL_H;
   const size_t frameOff = (size_t)blockIdx.y * fs.planeBytes + L.planeOff;
   const int tid = threadIdx.x;
 
