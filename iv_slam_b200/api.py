@@ -85,6 +85,7 @@ def lib():
         "ivg_set_graph_mode": (C.c_int, [vp, C.c_int]),
         "ivg_profile_enable": (C.c_int, [vp, C.c_int]),
         "ivg_profile_read": (C.c_int, [vp, vp, vp]),
+        "ivg_debug_nth_element": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -330,3 +331,11 @@ def compute_stereo_matches_keypoints(left, right, kL, dL, kR, dR, mbf, maxD):
     _ck(lib().ivg_stereo_match_keypoints(left._h, right._h, _p(kL), kL.size, _p(dL), _p(kR), kR.size, _p(dR), mbf, maxD, _p(u), _p(d)),
         "ivg_stereo_match_keypoints")
     return u, d
+
+
+def debug_nth_element(keys, nth, device=0):
+    """Permutation produced by the GPU's warp-parallel nth_element replay (test hook)."""
+    keys = np.ascontiguousarray(keys, np.uint32)
+    order = np.zeros(keys.size, np.uint32)
+    _ck(lib().ivg_debug_nth_element(device, _p(keys), keys.size, int(nth), _p(order)), "ivg_debug_nth_element")
+    return order

@@ -892,6 +892,23 @@ int ivg_flush_l2(ivg_extractor* h, size_t bytes) {
   CK(cudaMemsetAsync(scratch.p, 0x5a, bytes, h->stream));
   return IVG_OK;
 }
+int ivg_debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order) {
+  if (!keys || !order || n < 1 || n > 4000 || nth < 0 || nth >= n) return IVG_ERR_INVALID;
+  int rc = ivg_device_info(device, nullptr, 0, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaSetDevice(device));
+  DevBuf<uint32_t> dk, dord;
+  if ((rc = dk.alloc(n)) || (rc = dord.alloc(n))) return rc;
+  CK(cudaMemcpy(dk.p, keys, (size_t)n * 4, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)n * 8 + (size_t)n * 4 + 16;
+  CK(cudaFuncSetAttribute(k_debug_nth_element, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  k_debug_nth_element<<<1, 32, smem>>>(dk.p, n, nth, dord.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(order, dord.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  dk.release(); dord.release();
+  return IVG_OK;
+}
+
 int ivg_profile_enable(ivg_extractor* h, int enable) {
   if (!h) return IVG_ERR_INVALID;
   CK(cudaStreamSynchronize(h->stream));

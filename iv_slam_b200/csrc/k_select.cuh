@@ -21,6 +21,99 @@ constexpr int SEL_WARPS = 8;
 // Shared memory is sized per handle (dynamic): FrameSet::selLevelCap level-list entries, selCellCap entries per warp for
 // a cell list, selCells per-cell scalars.  Lists longer than the caps are processed in global memory (same code).
 
+// std::nth_element as libstdc++ runs it, executed by a WARP.  Same introselect skeleton as introselect.h (median-of-3 to
+// the front, unguarded Hoare partition, narrow, 3-element insertion sort, heap-select when the depth limit trips); only
+// the O(n) partition is parallel.  The sequential partition pairs the i-th element from the left that is not before
+// the pivot ("L-stopper", key <= pivot) with the i-th element from the right that the pivot is not before ("R-stopper",
+// key >= pivot) and swaps them while the left position is below the right one; scans between swaps only visit
+// positions no swap has touched, so both stopper sequences can be read off the ORIGINAL array: ranks by ballot/popcount,
+// positions scattered by rank into two scratch arrays, m = #{i : F[i] < R[i]} swaps done in parallel, and the cut is
+// F[m] if it lies below R[m-1] (the sequential left scan finds it first) else R[m-1] (the scan stops on the element the
+// last swap put there).  Produces the identical permutation (tests/test_gpu_parity.py::test_warp_nth_element).
+__device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int lane) {
+  if (n == 0 || nth == n) return;
+  int first = 0, last = n;
+  int depth = 2 * (31 - __clz(n));
+  const unsigned lt = (1u << lane) - 1u;
+  while (last - first > 3) {
+    if (depth == 0) {
+      if (lane == 0) { sel_heap_select(a + first, nth + 1 - first, last - first); sel_swap(a, first, nth); }
+      __syncwarp();
+      return;
+    }
+    --depth;
+    if (lane == 0) {
+      const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
+      if (sel_before(a[A], a[B])) {
+        if (sel_before(a[B], a[C])) sel_swap(a, first, B);
+        else if (sel_before(a[A], a[C])) sel_swap(a, first, C);
+        else sel_swap(a, first, A);
+      } else if (sel_before(a[A], a[C])) sel_swap(a, first, A);
+      else if (sel_before(a[B], a[C])) sel_swap(a, first, C);
+      else sel_swap(a, first, B);
+    }
+    __syncwarp();
+    const uint32_t pkey = a[first].key;
+    const int lo = first + 1, hi = last;
+    int TL = 0, TR = 0;
+    for (int base = lo; base < hi; base += 32) {
+      const int j = base + lane;
+      const bool v = j < hi;
+      const uint32_t k = v ? a[j].key : 0u;
+      const bool isL = v && !(k > pkey), isR = v && !(pkey > k);
+      const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
+      if (isL) sF[TL + __popc(mL & lt)] = (uint16_t)j;
+      if (isR) sR[TR + __popc(mR & lt)] = (uint16_t)j;
+      TL += __popc(mL); TR += __popc(mR);
+    }
+    __syncwarp();
+    int m = 0;
+    const int lim = min(TL, TR);
+    for (int base = 0; base < lim; base += 32) {
+      const int i = base + lane;
+      const bool ok = i < lim && sF[i] < sR[TR - 1 - i];
+      const unsigned b = __ballot_sync(0xffffffffu, ok);
+      m += __popc(b);
+      if (b != 0xffffffffu) break;
+    }
+    for (int i = lane; i < m; i += 32) {
+      const int x = sF[i], y = sR[TR - 1 - i];
+      const SelItem t = a[x]; a[x] = a[y]; a[y] = t;
+    }
+    const int rprev = m > 0 ? (int)sR[TR - m] : hi;
+    const int cut = (m < TL && (int)sF[m] < rprev) ? (int)sF[m] : rprev;
+    __syncwarp();
+    if (cut <= nth) first = cut; else last = cut;
+  }
+  if (lane == 0) {
+    for (int i = first + 1; i < last; ++i) {
+      const SelItem v = a[i];
+      if (sel_before(v, a[first])) {
+        for (int j = i; j > first; --j) a[j] = a[j - 1];
+        a[first] = v;
+      } else {
+        int j = i;
+        while (sel_before(v, a[j - 1])) { a[j] = a[j - 1]; --j; }
+        a[j] = v;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// test hook: one warp runs warp_nth_element on n (key, index) items staged in shared memory
+__global__ void k_debug_nth_element(const uint32_t* keys, int n, int nth, uint32_t* order) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  SelItem* a = reinterpret_cast<SelItem*>(dsm);
+  uint16_t* sF = reinterpret_cast<uint16_t*>(a + n);
+  uint16_t* sR = sF + n;
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n; i += 32) a[i] = SelItem{keys[i], (uint32_t)i};
+  __syncwarp();
+  warp_nth_element(a, nth, n, sF, sR, lane);
+  for (int i = lane; i < n; i += 32) order[i] = a[i].val;
+}
+
 // response weight of IV-SLAM's introspection: 2 * (1/(1 + cost/255)) - 1, all float (src/ORBextractor.cc:1070-1071)
 __device__ __forceinline__ float introspection_weight(float cost) {
   const float q = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fdiv_rn(cost, 255.0f)));
@@ -33,10 +126,13 @@ struct SelShared {           // views into the dynamic shared memory block
   int* nTotal; int* nStored; int* nRetain; int* prefix;
   float* nfc;
   unsigned char* thr; unsigned char* noMore;
+  uint16_t* cellScratch;     // [SEL_WARPS][2 * selCellCap]
+  uint16_t* levelScratch;    // [2 * selLevelCap]
 };
 
 __host__ __device__ inline size_t sel_smem_bytes(int levelCap, int cellCap, int cells) {
-  return (size_t)8 * levelCap + (size_t)8 * SEL_WARPS * cellCap + (size_t)cells * (5 * 4 + 2) + 16;
+  return (size_t)8 * levelCap + (size_t)8 * SEL_WARPS * cellCap + (size_t)cells * (5 * 4 + 2) + 16 +
+         (size_t)4 * SEL_WARPS * cellCap + (size_t)4 * levelCap + 16;
 }
 
 __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
@@ -55,7 +151,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
     S.prefix = reinterpret_cast<int*>(p); p += 4 * nc;
     S.nfc = reinterpret_cast<float*>(p); p += 4 * nc;
     S.thr = p; p += nc;
-    S.noMore = p;
+    S.noMore = p; p += nc;
+    p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+    S.cellScratch = reinterpret_cast<uint16_t*>(p); p += (size_t)4 * SEL_WARPS * SEL_CELL_CAP;
+    S.levelScratch = reinterpret_cast<uint16_t*>(p);
   }
   const int level = blockIdx.x;
   const size_t img = blockIdx.y;
@@ -152,7 +251,11 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
     }
     __syncwarp();
     if (buf != wbuf) __threadfence_block();
-    if (lane == 0 && n > keep) sel_nth_element(buf, keep - 1, n);
+    if (n > keep) {
+      if (buf == wbuf) warp_nth_element(buf, keep - 1, n, S.cellScratch + (size_t)warp * 2 * SEL_CELL_CAP,
+                                        S.cellScratch + (size_t)warp * 2 * SEL_CELL_CAP + SEL_CELL_CAP, lane);
+      else if (lane == 0) sel_nth_element(buf, keep - 1, n);      // oversized list in global memory: sequential replay
+    }
     __syncwarp();
     if (buf != wbuf) __threadfence_block();
     const int dst = S.prefix[c];
@@ -162,14 +265,17 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
   __threadfence_block();
   __syncthreads();
 
-  if (tid == 0) {
+  if (warp == 0) {
     int count = total;
     if (total > L.nDesired) {
       if (L.nDesired == 0) count = 0;
-      else { sel_nth_element(levelBuf, L.nDesired - 1, total); count = L.nDesired; }
+      else {
+        if (levelBuf == S.levelBuf) warp_nth_element(levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, lane);
+        else if (lane == 0) sel_nth_element(levelBuf, L.nDesired - 1, total);
+        count = L.nDesired;
+      }
     }
-    sCount = count;
-    fs.levelCount[img * MAX_LEVELS + level] = count;
+    if (lane == 0) { sCount = count; fs.levelCount[img * MAX_LEVELS + level] = count; }
   }
   __threadfence_block();
   __syncthreads();

@@ -251,3 +251,25 @@ def test_graph_mode_is_bit_identical(gpu_api):
         k1, d1 = plain(img)
         k2, d2 = graph(img)
         assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
+
+
+def test_warp_nth_element_matches_libstdcxx(gpu_api, oracle):
+    """The warp-parallel nth_element replay must leave exactly the permutation std::nth_element leaves (ties included)."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for _ in range(150):
+        n = int(rng.integers(2, 120))
+        cases.append((rng.integers(7, 7 + int(rng.integers(1, 40)), n), int(rng.integers(0, n - 1))))   # retainBest only sorts when it trims
+    for _ in range(40):
+        n = int(rng.integers(200, 2500))
+        cases.append((rng.integers(7, 7 + int(rng.integers(1, 120)), n), int(rng.integers(0, n - 1))))
+    cases.append((np.full(500, 20), 123))                                   # all equal
+    cases.append((np.arange(1000) % 17 + 7, 400))                           # sawtooth
+    cases.append((np.arange(1500)[::-1] + 7, 700))                          # sorted descending
+    cases.append((np.arange(1500) + 7, 700))                                # sorted ascending
+    for vals, nth in cases:
+        resp = vals.astype(np.float32)
+        keys = resp.view(np.uint32)
+        got = gpu_api.debug_nth_element(keys, nth)
+        want = oracle.retain_best(resp, nth + 1)      # first nth+1 survivors of nth_element(begin, begin+nth, end)
+        assert np.array_equal(got[:nth + 1], want), (vals.size, nth)
