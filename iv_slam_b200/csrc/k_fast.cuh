@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
   const int xa = (c.x0 - 3) & ~3;          // global x of staged column 0 (word aligned)
   const int cOff = c.x0 - xa;              // staged column of detect column 0
   const int scoreTh = fs.scoreTh;
-  const unsigned passK = 257u + (unsigned)scoreTh;
+  const unsigned kK2 = ((unsigned)scoreTh + 1u) * 0x00010001u;      // th + 1 in both 16-bit lanes
   const int nChunks = (cw + 31) >> 5;
 
   int running = 0, nIni = 0, nMin = 0, par = 0;
@@ -147,15 +147,17 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
         for (; x - lane < xend; x += 32, ctr += 32, cp3 += 32, cm3 += 32, cp2 += 32, cm2 += 32) {
           bool pass = false;
           if (x < xend) {
-            const unsigned C = ctr[0] + 0x01000100u;
-            const unsigned D0 = C - cp3[0], D8 = C - cm3[0];
-            const unsigned D2 = C - cp2[2], D10 = C - cm2[-2];
-            const unsigned D4 = C - ctr[3], D12 = C - ctr[-3];
-            const unsigned D6 = C - cm2[2], D14 = C - cp2[-2];
-            const unsigned a = __vminu2(vmin3(__vmaxu2(D0, D8), __vmaxu2(D2, D10), __vmaxu2(D4, D12)), __vmaxu2(D6, D14));
-            const unsigned b = __vmaxu2(vmax3(__vminu2(D0, D8), __vminu2(D2, D10), __vminu2(D4, D12)), __vminu2(D6, D14));
-            const unsigned t = __vmaxu2(a, 0x02000200u - b);
-            pass = max(t & 0xFFFFu, t >> 16) >= passK;
+            // directly on the packed pixels (no differences needed for a reject test):
+            //   bright possible  <=>  min over diameters of max(ring_k, ring_k+8) >= centre + th + 1
+            //   dark possible    <=>  max over diameters of min(ring_k, ring_k+8) <= centre - th - 1
+            const unsigned C = ctr[0];
+            const unsigned r0 = cp3[0], r8 = cm3[0], r2 = cp2[2], r10 = cm2[-2], r4 = ctr[3], r12 = ctr[-3], r6 = cm2[2], r14 = cp2[-2];
+            const unsigned a = __vminu2(vmin3(__vmaxu2(r0, r8), __vmaxu2(r2, r10), __vmaxu2(r4, r12)), __vmaxu2(r6, r14));
+            const unsigned b = __vmaxu2(vmax3(__vminu2(r0, r8), __vminu2(r2, r10), __vminu2(r4, r12)), __vminu2(r6, r14));
+            // bit 15 of each 16-bit lane: (a >= C + K) and (C >= b + K), K = th + 1; no borrow can cross lanes
+            const unsigned X = a + (0x80008000u - kK2) - C;
+            const unsigned Y = C + (0x80008000u - kK2) - b;
+            pass = ((X | Y) & 0x80008000u) != 0u;
           }
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + x);   // cw <= 512 enforced by the host
