@@ -61,6 +61,12 @@ int ivg_device_info(int device, char* name, int name_cap, int* sm, int* sm_count
 int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float scaleFactor, int nlevels,
                          int iniThFAST, int minThFAST, int enableIntrospection);
 void ivg_extractor_destroy(ivg_extractor* h);
+/* Keypoint-selection path.  mode 0 (default) = ComputeKeyPointsOld, the path the reference actually runs
+ * (src/ORBextractor.cc:1248).  mode 1 = ComputeKeyPointsOctTree + DistributeOctTree (src/ORBextractor.cc:771-878,
+ * :545-769), which the reference compiles but never calls (:1247 is commented out).  In mode 1 the reference's one
+ * nondeterministic tie-break (sorting nodes by heap address, :690) is replaced by creation order; a level may emit up
+ * to 3 keypoints more than its budget, as in the reference.  Changes ivg_max_keypoints(); call before extracting. */
+int ivg_extractor_set_mode(ivg_extractor* h, int mode);
 
 /* Pre-allocates the device workspace for `max_batch` images of width x height (otherwise done lazily on the
  * first call and whenever the shape or batch grows). */

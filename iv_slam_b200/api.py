@@ -53,6 +53,7 @@ def lib():
         "ivg_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, i32p, i32p]),
         "ivg_extractor_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
         "ivg_extractor_destroy": (None, [vp]),
+        "ivg_extractor_set_mode": (C.c_int, [vp, C.c_int]),
         "ivg_extractor_reserve": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "ivg_get_levels": (C.c_int, [vp]),
         "ivg_get_scale_factor": (C.c_float, [vp]),
@@ -162,6 +163,11 @@ class ORBextractor:
             self.close()
         except Exception:
             pass
+
+    def set_keypoint_mode(self, mode):
+        """0: ComputeKeyPointsOld (the reference's live path, default); 1: ComputeKeyPointsOctTree (dead code there)."""
+        _ck(lib().ivg_extractor_set_mode(self._h, int(mode)), "ivg_extractor_set_mode")
+        self.cap = lib().ivg_max_keypoints(self._h)
 
     # -- getters of the reference class (ORBextractor.h:69-91)
     def GetLevels(self):

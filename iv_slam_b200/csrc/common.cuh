@@ -29,7 +29,8 @@ struct LevelDev {
   int nfeaturesCell;      // ceil(nDesired / nCells)
   int cols, rows, cellW, cellH, nCells;
   int cellBase;           // first cell index of this level in the cell tables
-  int kpOff;              // offset of this level inside levelKp (prefix sum of nDesired)
+  int kpOff;              // offset of this level inside levelKp (prefix sum of kpCapLevel)
+  int kpCapLevel;         // keypoints this level can emit: nDesired (live path) or nDesired + 3 (OctTree mode)
   int fSP, fSS, fBH, fBW, fSeg; // k_fast_cells: staged words per row, score bytes per row, rows per band, bitmap words per row, list entries per warp
   int btBase, btX, btY;   // blur tile numbering
   int rzPitch, rzRows;    // k_resize_level: staged source bytes per row / rows of one output tile (this level as destination)
@@ -54,6 +55,7 @@ struct FrameSet {
   int nlevels, nImages, weighted;
   int iniTh, minTh, scoreTh;
   int nCellsTotal, kpCap;
+  int cellCostStride;      // entries per frame in cellCost (nCellsTotal + slack used by the OctTree gather)
   int btTotal;
   int selLevelCap, selCellCap, selCells;   // k_level_select shared-memory capacities
   unsigned listCapTotal;

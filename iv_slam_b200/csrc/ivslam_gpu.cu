@@ -22,6 +22,7 @@
 #include "k_fast.cuh"
 #include "k_pyramid.cuh"
 #include "k_select.cuh"
+#include "k_octree.cuh"
 #include "k_stereo.cuh"
 
 using namespace ivg;
@@ -71,6 +72,7 @@ struct ivg_extractor {
   int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
   double scaleFactor = 1.2;
   bool enableIntrospection = false;
+  int kpMode = 0;                       // 0: ComputeKeyPointsOld (live in the reference), 1: ComputeKeyPointsOctTree (dead there)
   std::vector<float> scale, invScale, sigma2, invSigma2;
   std::vector<int> nPerLevel, umax;
   int kpCap = 0;
@@ -244,18 +246,29 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.scale = h->scale[l]; L.invScale = h->invScale[l];
     L.sizeField = (float)(int)(PATCH * h->scale[l]);
     L.nDesired = h->nPerLevel[l];
-    L.kpOff = kpOff; kpOff += L.nDesired;
+    L.kpCapLevel = L.nDesired + (h->kpMode == 1 ? 3 : 0);
+    L.kpOff = kpOff; kpOff += L.kpCapLevel;
     // grid
-    L.cols = (int)std::sqrt((float)L.nDesired / (5 * imageRatio));
-    L.rows = (int)(imageRatio * L.cols);
     L.maxBX = L.w - EDGE; L.maxBY = L.h - EDGE;
     const int Wd = L.maxBX - EDGE, Hd = L.maxBY - EDGE;
-    if (L.cols < 1 || L.rows < 1 || Wd < 1 || Hd < 1) return IVG_ERR_GEOMETRY;
-    L.cellW = (int)std::ceil((float)Wd / L.cols);
-    L.cellH = (int)std::ceil((float)Hd / L.rows);
-    L.nCells = L.rows * L.cols;
-    if ((L.cols - 1) * L.cellW > Wd || (L.rows - 1) * L.cellH > Hd) return IVG_ERR_GEOMETRY;
-    if (L.nCells > SEL_MAX_CELLS) return IVG_ERR_CAPACITY;
+    if (h->kpMode == 1) {
+      // ComputeKeyPointsOctTree (:771-797): 30-px cells over the area inset by 16; the detect ranges (window minus its
+      // 3-px FAST margin) tile [19, dim-19) exactly like the live path, trailing cells may be empty
+      const float width = (float)(L.w - 2 * (EDGE - 3)), height = (float)(L.h - 2 * (EDGE - 3));
+      L.cols = (int)(width / 30.f); L.rows = (int)(height / 30.f);
+      if (L.cols < 1 || L.rows < 1 || Wd < 1 || Hd < 1) return IVG_ERR_GEOMETRY;
+      L.cellW = (int)std::ceil(width / L.cols); L.cellH = (int)std::ceil(height / L.rows);
+      L.nCells = L.rows * L.cols;
+    } else {
+      L.cols = (int)std::sqrt((float)L.nDesired / (5 * imageRatio));
+      L.rows = (int)(imageRatio * L.cols);
+      if (L.cols < 1 || L.rows < 1 || Wd < 1 || Hd < 1) return IVG_ERR_GEOMETRY;
+      L.cellW = (int)std::ceil((float)Wd / L.cols);
+      L.cellH = (int)std::ceil((float)Hd / L.rows);
+      L.nCells = L.rows * L.cols;
+      if ((L.cols - 1) * L.cellW > Wd || (L.rows - 1) * L.cellH > Hd) return IVG_ERR_GEOMETRY;
+      if (L.nCells > SEL_MAX_CELLS) return IVG_ERR_CAPACITY;
+    }
     L.nfeaturesCell = (int)std::ceil((float)L.nDesired / L.nCells);
     L.cellBase = (int)h->cellsPlain.size();
     L.btX = (L.w + BL_W - 1) / BL_W; L.btY = (L.h + BL_H - 1) / BL_H;
@@ -285,10 +298,16 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
         c.level = l;
         c.x0 = EDGE + j * L.cellW; c.cw = (j < L.cols - 1 ? c.x0 + L.cellW : L.maxBX) - c.x0;
         c.y0 = EDGE + i * L.cellH; c.ch = (i < L.rows - 1 ? c.y0 + L.cellH : L.maxBY) - c.y0;
+        if (h->kpMode == 1) {   // every cell is clipped at the search area; cells past it are empty (their windows are skipped, :801,:810)
+          c.cw = std::max(0, std::min(c.x0 + L.cellW, L.maxBX) - c.x0);
+          c.ch = std::max(0, std::min(c.y0 + L.cellH, L.maxBY) - c.y0);
+          if (c.cw == 0 || c.ch == 0) { c.cw = 0; c.ch = 0; c.x0 = EDGE; c.y0 = EDGE; }
+        }
         c.wx = c.x0 - 3; c.ww = j < L.cols - 1 ? L.cellW + 6 : L.maxBX + 3 - c.wx;
         c.wy = c.y0 - 3; c.wh = i < L.rows - 1 ? L.cellH + 6 : L.maxBY + 3 - c.wy;
         c.listOff = listOff;
         c.listCap = (unsigned)(((c.cw + 1) / 2) * ((c.ch + 1) / 2));
+        if (h->kpMode == 1 && c.cw == 0) { c.ww = 1; c.wh = 1; c.wx = EDGE; c.wy = EDGE; }
         listOff += c.listCap;
         h->cellsPlain.push_back(c);
         CellDev cw = c;
@@ -317,6 +336,11 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   fs.planeBytes = align_up(planeOff, (size_t)fs.lv[0].pitch * 4);   // multiple of the level-0 pitch: batched 3-D copies
   while (fs.planeBytes % fs.lv[0].pitch) fs.planeBytes += 256;
   fs.listCapTotal = listOff;
+  if (h->kpMode == 1)
+    for (int l = 0; l < nl; ++l) {   // k_octree_select: oversized budgets keep their node tables in the level's work area
+      const LevelDev& L = fs.lv[l];
+      if (L.nDesired + 16 > OCT_SMEM_NODES && (size_t)L.listCap * 4 < (size_t)(L.nDesired + 16) * (sizeof(OctNodeDev) + 8)) return IVG_ERR_CAPACITY;
+    }
   fs.nCellsTotal = (int)h->cellsPlain.size();
   fs.kpCap = kpOff;
   fs.btTotal = btBase;
@@ -348,7 +372,8 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
       for (int tx = 0; tx < fs.lv[l].btX; ++tx) btab.push_back(((uint32_t)l << 28) | ((uint32_t)tx << 14) | (uint32_t)ty);
   if ((rc = h->blurTiles.alloc(btab.size()))) return rc;
   if ((rc = h->cellList.alloc(B * fs.listCapTotal))) return rc;
-  if ((rc = h->cellCost.alloc(B * fs.nCellsTotal))) return rc;
+  fs.cellCostStride = fs.nCellsTotal + MAX_LEVELS + 1;
+  if ((rc = h->cellCost.alloc(B * fs.cellCostStride))) return rc;
   if ((rc = h->cellCount.alloc(B * fs.nCellsTotal))) return rc;
   if ((rc = h->workCell.alloc(B * fs.listCapTotal))) return rc;
   if ((rc = h->workLevel.alloc(B * fs.listCapTotal))) return rc;
@@ -392,6 +417,7 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
                              batch, BL_BOXW, BL_PH)))
       return rc;
   h->fs = fs;
+  h->kpCap = fs.kpCap;
   h->W = W; h->H = H; h->maxBatch = batch; h->shapeReady = true;
   h->haveResults = false; h->havePyramid = false; h->curBatch = 0;
   return IVG_OK;
@@ -401,6 +427,7 @@ int ensure_shape(ivg_extractor* h, int W, int H, int batch) {
   if (W <= 0 || H <= 0 || batch <= 0) return IVG_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   if (h->shapeReady && h->W == W && h->H == H && batch <= h->maxBatch) return IVG_OK;
+  if (!h->shapeReady && h->W == W && h->H == H) batch = std::max(batch, h->maxBatch);   // mode change: keep the reserved batch
   CK(cudaStreamSynchronize(h->stream));
   const int b = (h->shapeReady && h->W == W && h->H == H) ? std::max(batch, h->maxBatch) : batch;
   h->shapeReady = false;
@@ -417,7 +444,7 @@ FrameSet active_fs(const ivg_extractor* h) {
   FrameSet fs = h->fs;
   fs.nImages = h->curBatch;
   fs.weighted = h->curWeighted ? 1 : 0;
-  fs.cells = h->curWeighted ? h->dCellsWeighted.p : h->dCellsPlain.p;
+  fs.cells = (h->curWeighted && h->kpMode == 0) ? h->dCellsWeighted.p : h->dCellsPlain.p;
   return fs;
 }
 
@@ -436,7 +463,8 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   if (rc) return rc;
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
-  { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }
+  if (h->kpMode == 1) { ProfScope ps(h, IVG_K_SELECT); k_octree_select<<<dim3(fs.nlevels, fs.nImages), 256, sizeof(OctShared), h->stream>>>(fs); }
+  else { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps); }
   CK(cudaGetLastError());
   return IVG_OK;
@@ -484,6 +512,7 @@ int init_device_constants(int device) {
   }
   CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_octree_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OctShared)));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return IVG_OK;
 }
@@ -602,6 +631,20 @@ int ivg_get_features_per_level(const ivg_extractor* h, int* out) {
   return IVG_OK;
 }
 int ivg_max_keypoints(const ivg_extractor* h) { return h ? h->kpCap : 0; }
+
+int ivg_extractor_set_mode(ivg_extractor* h, int mode) {
+  if (!h || (mode != 0 && mode != 1)) return IVG_ERR_INVALID;
+  if (mode == h->kpMode) return IVG_OK;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->kpMode = mode;
+  h->kpCap = 0;
+  for (int l = 0; l < h->nlevels; ++l) h->kpCap += h->nPerLevel[l] + (mode == 1 ? 3 : 0);
+  h->shapeReady = false;      // tables and capacities are rebuilt on the next call
+  h->haveResults = false;
+  drop_graph(h);
+  return IVG_OK;
+}
 
 int ivg_set_batch(ivg_extractor* h, int n, int width, int height, int with_cost) {
   if (!h) return IVG_ERR_INVALID;

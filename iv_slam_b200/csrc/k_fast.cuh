@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) { a += sred[0][w]; b += sred[1][w]; s += (unsigned)sred[2][w]; }
     fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = make_int2(b, a);   // x: corners at minTh, y: corners at iniTh
-    fs.cellCost[img * fs.nCellsTotal + blockIdx.x] = s;
+    fs.cellCost[img * fs.cellCostStride + blockIdx.x] = s;
   }
 }
 

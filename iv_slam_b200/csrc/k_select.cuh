@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
     const int nDesired = L.nDesired;
     if (fs.weighted) {
       // cell weights, row-major, float accumulation order as in the reference (:942-987)
-      const uint32_t* cost = fs.cellCost + img * fs.nCellsTotal + L.cellBase;
+      const uint32_t* cost = fs.cellCost + img * fs.cellCostStride + L.cellBase;
       float wsum = 0.0f;
       for (int c = 0; c < nCells; ++c) {
         const float area = __fmul_rn((float)cells[c].ww, (float)cells[c].wh);

@@ -224,6 +224,128 @@ class Cv2Extractor:
             k["angle"] = np.array([self.ic_angle(pyr[level], k["x"][i], k["y"][i]) for i in range(k["x"].size)], f32)
         return allk
 
+    # ---- optional mode: ComputeKeyPointsOctTree + DistributeOctTree + DivideNode (src/ORBextractor.cc:771-878, :545-769,
+    # :487-543; dead code in the reference).  Ties in the (size, node) sort are broken by creation order (the reference
+    # uses heap addresses) — the same deterministic rule as oracle/ivslam_oracle.cpp.
+    def keypoints_octree(self, pyr):
+        allk = []
+        for level in range(self.nlevels):
+            img = pyr[level]
+            H_, W_ = img.shape
+            minB = EDGE - 3
+            maxBX, maxBY = W_ - EDGE + 3, H_ - EDGE + 3
+            width, height = f32(maxBX - minB), f32(maxBY - minB)
+            nCols, nRows = int(width / f32(30)), int(height / f32(30))
+            wCell, hCell = int(np.ceil(width / f32(nCols))), int(np.ceil(height / f32(nRows)))
+            keys = []      # (x, y, response) relative to (minB, minB)
+            for i in range(nRows):
+                iniY = minB + i * hCell
+                maxY = iniY + hCell + 6
+                if iniY >= maxBY - 3:
+                    continue
+                maxY = min(maxY, maxBY)
+                for j in range(nCols):
+                    iniX = minB + j * wCell
+                    maxX = iniX + wCell + 6
+                    if iniX >= maxBX - 6:
+                        continue
+                    maxX = min(maxX, maxBX)
+                    win = img[iniY:maxY, iniX:maxX]
+                    k = self._fast(win, self.iniTh)
+                    if not k:
+                        k = self._fast(win, self.minTh)
+                    keys += [(f32(t[0]) + f32(j * wCell), f32(t[1]) + f32(i * hCell), f32(t[2])) for t in k]
+            sel = self._distribute_octree(keys, minB, maxBX, minB, maxBY, self.nper[level])
+            lx = np.array([keys[i][0] + f32(minB) for i in sel], f32)
+            ly = np.array([keys[i][1] + f32(minB) for i in sel], f32)
+            lr = np.array([keys[i][2] for i in sel], f32)
+            allk.append(dict(x=lx, y=ly, response=lr, size=f32(int(f32(PATCH) * self.scale[level]))))
+        for level in range(self.nlevels):
+            k = allk[level]
+            k["angle"] = np.array([self.ic_angle(pyr[level], k["x"][i], k["y"][i]) for i in range(k["x"].size)], f32)
+        return allk
+
+    @staticmethod
+    def _distribute_octree(K, minX, maxX, minY, maxY, N):
+        nIni = int(math.floor(float(f32(maxX - minX) / f32(maxY - minY)) + 0.5))
+        hX = f32(maxX - minX) / f32(nIni)
+        seq = [0]
+
+        def node(ulx, uly, brx, bry, keys):
+            seq[0] += 1
+            return dict(ulx=ulx, uly=uly, brx=brx, bry=bry, keys=keys, noMore=len(keys) == 1, seq=seq[0])
+
+        def divide(n):
+            halfX = int(math.ceil(float(f32(n["brx"] - n["ulx"]) / f32(2))))
+            halfY = int(math.ceil(float(f32(n["bry"] - n["uly"]) / f32(2))))
+            mx, my = n["ulx"] + halfX, n["uly"] + halfY
+            ks = [[], [], [], []]
+            for k in n["keys"]:
+                x, y = K[k][0], K[k][1]
+                if x < mx:
+                    ks[0 if y < my else 2].append(k)
+                else:
+                    ks[1 if y < my else 3].append(k)
+            boxes = [(n["ulx"], n["uly"], mx, my), (mx, n["uly"], n["brx"], my), (n["ulx"], my, mx, n["bry"]), (mx, my, n["brx"], n["bry"])]
+            return [node(*boxes[c], ks[c]) for c in range(4)]
+
+        ini = [node(int(hX * f32(i)), 0, int(hX * f32(i + 1)), maxY - minY, []) for i in range(nIni)]
+        for i, kp in enumerate(K):
+            ini[int(kp[0] / hX)]["keys"].append(i)
+        nodes = []          # python list used as std::list: index 0 = front
+        for n in ini:
+            if len(n["keys"]) == 1:
+                n["noMore"] = True
+                nodes.append(n)
+            elif n["keys"]:
+                n["noMore"] = False
+                nodes.append(n)
+        finish = False
+        while not finish:
+            prevSize = len(nodes)
+            nToExpand = 0
+            expand = []
+            i = 0
+            while i < len(nodes):
+                n = nodes[i]
+                if n["noMore"]:
+                    i += 1
+                    continue
+                for c in divide(n):
+                    if c["keys"]:
+                        nodes.insert(0, c)
+                        i += 1
+                        if len(c["keys"]) > 1:
+                            nToExpand += 1
+                            expand.append(c)
+                del nodes[i]
+            if len(nodes) >= N or len(nodes) == prevSize:
+                finish = True
+            elif len(nodes) + nToExpand * 3 > N:
+                while not finish:
+                    prev2 = len(nodes)
+                    prev = sorted(expand, key=lambda n: (len(n["keys"]), n["seq"]))
+                    expand = []
+                    for n in reversed(prev):
+                        for c in divide(n):
+                            if c["keys"]:
+                                nodes.insert(0, c)
+                                if len(c["keys"]) > 1:
+                                    expand.append(c)
+                        nodes.remove(n)
+                        if len(nodes) >= N:
+                            break
+                    if len(nodes) >= N or len(nodes) == prev2:
+                        finish = True
+        out = []
+        for n in nodes:
+            best = n["keys"][0]
+            for k in n["keys"][1:]:
+                if K[k][2] > K[best][2]:
+                    best = k
+            out.append(best)
+        return out
+
     def ic_angle(self, img, px, py):
         cx, cy = cv_round(px), cv_round(py)
         m01 = m10 = 0
@@ -249,7 +371,7 @@ class Cv2Extractor:
     def __call__(self, image, mask=None):
         qpyr = self.pyramid(mask) if (mask is not None and self.intro) else None
         pyr = self.pyramid(image)
-        allk = self.keypoints_old(pyr, qpyr)
+        allk = self.keypoints_octree(pyr) if getattr(self, "kp_mode", 0) == 1 else self.keypoints_old(pyr, qpyr)
         kps, descs, blurs = [], [], []
         for level in range(self.nlevels):
             k = allk[level]

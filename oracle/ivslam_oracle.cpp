@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <list>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -317,6 +318,7 @@ struct Extractor {
   int nfeatures; double scaleFactor; int nlevels, iniThFAST, minThFAST;
   bool enableIntrospection;
   bool qualityAvailable = false;
+  int kp_mode = 0;     // 0: ComputeKeyPointsOld (live in the reference), 1: ComputeKeyPointsOctTree (compiled but dead there)
   int trig_mode = 0;   // 0: glibc cosf/sinf (the reference, src/ORBextractor.cc:114); 1: (float)cos((double)x)
   std::vector<float> scale, invScale, sigma2, invSigma2;
   std::vector<int> nPerLevel, umax;
@@ -562,6 +564,160 @@ int compute_keypoints_old(Extractor& e) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// ComputeKeyPointsOctTree + DistributeOctTree + ExtractorNode::DivideNode
+// (src/ORBextractor.cc:771-878, :545-769, :487-543).  This path is compiled but DEAD in the reference (operator() calls
+// ComputeKeyPointsOld, :1247-1248); it is provided as an optional mode because the north star names it.
+// One deliberate difference: the reference sorts (size, ExtractorNode*) pairs (:690), so ties between nodes of equal
+// size are broken by heap addresses — nondeterministic across runs.  Here a tie is broken by creation
+// order (the node created later counts as the larger one), which makes the result a pure function of the image.
+// The per-cell quality score the reference parks in KeyPoint::size (:826-849) is overwritten before anyone reads it
+// (:861) and is not computed.
+// ------------------------------------------------------------------------------------
+struct OctNode {
+  int ulx, uly, brx, bry;          // UL and BR corners (UR.x == BR.x, BL.y == BR.y)
+  std::vector<int> keys;           // indices into the level's key list, in insertion order
+  bool noMore = false;
+  long seq = 0;                    // creation order (stands in for the pointer in the reference's sort)
+};
+
+void divide_node(const OctNode& n, const std::vector<KeyPoint>& K, OctNode out[4]) {
+  const int halfX = (int)std::ceil(static_cast<float>(n.brx - n.ulx) / 2);
+  const int halfY = (int)std::ceil(static_cast<float>(n.bry - n.uly) / 2);
+  const int mx = n.ulx + halfX, my = n.uly + halfY;
+  out[0].ulx = n.ulx; out[0].uly = n.uly; out[0].brx = mx;    out[0].bry = my;
+  out[1].ulx = mx;    out[1].uly = n.uly; out[1].brx = n.brx; out[1].bry = my;
+  out[2].ulx = n.ulx; out[2].uly = my;    out[2].brx = mx;    out[2].bry = n.bry;
+  out[3].ulx = mx;    out[3].uly = my;    out[3].brx = n.brx; out[3].bry = n.bry;
+  for (int k : n.keys) {
+    const KeyPoint& kp = K[k];
+    if (kp.x < mx) { if (kp.y < my) out[0].keys.push_back(k); else out[2].keys.push_back(k); }
+    else if (kp.y < my) out[1].keys.push_back(k);
+    else out[3].keys.push_back(k);
+  }
+  for (int c = 0; c < 4; ++c) out[c].noMore = out[c].keys.size() == 1;
+}
+
+std::vector<KeyPoint> distribute_octree(const std::vector<KeyPoint>& K, int minX, int maxX, int minY, int maxY, int N) {
+  std::vector<KeyPoint> result;
+  const int nIni = (int)std::round(static_cast<float>(maxX - minX) / (maxY - minY));
+  if (nIni < 1) return result;     // the reference divides by zero here (taller-than-wide levels); defined as "no keypoints"
+  const float hX = static_cast<float>(maxX - minX) / nIni;
+  std::list<OctNode> nodes;
+  long seq = 0;
+  std::vector<OctNode*> ini(nIni);
+  for (int i = 0; i < nIni; ++i) {
+    OctNode n;
+    n.ulx = (int)(hX * static_cast<float>(i)); n.uly = 0;
+    n.brx = (int)(hX * static_cast<float>(i + 1)); n.bry = maxY - minY;
+    n.seq = seq++;
+    nodes.push_back(n);
+    ini[i] = &nodes.back();
+  }
+  for (size_t i = 0; i < K.size(); ++i) {
+    const int b = (int)(K[i].x / hX);
+    if (b < 0 || b >= nIni) continue;   // cannot happen for coordinates inside the level
+    ini[b]->keys.push_back((int)i);
+  }
+  for (auto it = nodes.begin(); it != nodes.end();) {
+    if (it->keys.size() == 1) { it->noMore = true; ++it; }
+    else if (it->keys.empty()) it = nodes.erase(it);
+    else ++it;
+  }
+  typedef std::list<OctNode>::iterator It;
+  std::vector<std::pair<int, It>> expand;   // (size, node); order key = (size, seq)
+  auto add_children = [&](OctNode ch[4], int* nToExpand) {
+    for (int c = 0; c < 4; ++c)
+      if (!ch[c].keys.empty()) {
+        ch[c].seq = seq++;
+        nodes.push_front(ch[c]);
+        if (ch[c].keys.size() > 1) { if (nToExpand) ++*nToExpand; expand.push_back(std::make_pair((int)ch[c].keys.size(), nodes.begin())); }
+      }
+  };
+  bool finish = false;
+  while (!finish) {
+    const int prevSize = (int)nodes.size();
+    int nToExpand = 0;
+    expand.clear();
+    for (auto it = nodes.begin(); it != nodes.end();) {
+      if (it->noMore) { ++it; continue; }
+      OctNode ch[4];
+      divide_node(*it, K, ch);
+      add_children(ch, &nToExpand);
+      it = nodes.erase(it);
+    }
+    if ((int)nodes.size() >= N || (int)nodes.size() == prevSize) finish = true;
+    else if ((int)nodes.size() + nToExpand * 3 > N) {
+      while (!finish) {
+        const int prev2 = (int)nodes.size();
+        std::vector<std::pair<int, It>> prev = expand;
+        expand.clear();
+        std::sort(prev.begin(), prev.end(), [](const std::pair<int, It>& a, const std::pair<int, It>& b) {
+          return a.first != b.first ? a.first < b.first : a.second->seq < b.second->seq;
+        });
+        for (int j = (int)prev.size() - 1; j >= 0; --j) {
+          OctNode ch[4];
+          divide_node(*prev[j].second, K, ch);
+          add_children(ch, nullptr);
+          nodes.erase(prev[j].second);
+          if ((int)nodes.size() >= N) break;
+        }
+        if ((int)nodes.size() >= N || (int)nodes.size() == prev2) finish = true;
+      }
+    }
+  }
+  result.reserve(nodes.size());
+  for (const OctNode& n : nodes) {
+    int best = n.keys[0];
+    float mr = K[best].response;
+    for (size_t k = 1; k < n.keys.size(); ++k)
+      if (K[n.keys[k]].response > mr) { best = n.keys[k]; mr = K[best].response; }
+    result.push_back(K[best]);
+  }
+  return result;
+}
+
+int compute_keypoints_octree(Extractor& e) {
+  std::vector<Corner> corners;
+  const float Wc = 30;
+  for (int level = 0; level < e.nlevels; ++level) {
+    Level& L = e.lv[level];
+    const int minBX = EDGE_THRESHOLD - 3, minBY = minBX;
+    const int maxBX = L.w - EDGE_THRESHOLD + 3, maxBY = L.h - EDGE_THRESHOLD + 3;
+    std::vector<KeyPoint> toDistribute;
+    const float width = (float)(maxBX - minBX), height = (float)(maxBY - minBY);
+    const int nCols = (int)(width / Wc), nRows = (int)(height / Wc);
+    if (nCols < 1 || nRows < 1) return -2;      // the reference divides by zero
+    const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+    for (int i = 0; i < nRows; ++i) {
+      const float iniY = (float)(minBY + i * hCell);
+      float maxY = iniY + hCell + 6;
+      if (iniY >= maxBY - 3) continue;
+      if (maxY > maxBY) maxY = (float)maxBY;
+      for (int j = 0; j < nCols; ++j) {
+        const float iniX = (float)(minBX + j * wCell);
+        float maxX = iniX + wCell + 6;
+        if (iniX >= maxBX - 6) continue;
+        if (maxX > maxBX) maxX = (float)maxBX;
+        const int x0 = (int)iniX, y0 = (int)iniY, ww = (int)maxX - x0, wh = (int)maxY - y0;
+        const uint8_t* win = &L.img[(size_t)y0 * L.w + x0];
+        fast9_nms(win, ww, wh, L.w, e.iniThFAST, true, corners, e.fs); e.n_fast_calls++;
+        if (corners.empty()) { fast9_nms(win, ww, wh, L.w, e.minThFAST, true, corners, e.fs); e.n_fast_calls++; }
+        for (const Corner& c : corners)
+          toDistribute.push_back(KeyPoint{(float)c.x + j * wCell, (float)c.y + i * hCell, 7.f, -1.f, (float)c.score, 0, -1});
+        e.n_raw += (long)corners.size();
+      }
+    }
+    std::vector<KeyPoint>& keypoints = e.levelKeys[level];
+    keypoints = distribute_octree(toDistribute, minBX, maxBX, minBY, maxBY, e.nPerLevel[level]);
+    const int scaledPatchSize = (int)(PATCH_SIZE * e.scale[level]);
+    for (KeyPoint& kp : keypoints) { kp.x += minBX; kp.y += minBY; kp.octave = level; kp.size = (float)scaledPatchSize; }
+  }
+  for (int level = 0; level < e.nlevels; ++level)
+    for (KeyPoint& kp : e.levelKeys[level]) kp.angle = ic_angle(e.lv[level], kp.x, kp.y, e.umax);
+  return 0;
+}
+
 // ORBextractor::operator() (src/ORBextractor.cc:1224-1296)
 int extract(Extractor& e, const uint8_t* img, int w, int h, size_t stride, const uint8_t* cost,
             size_t cost_stride, KeyPoint* kps, uint8_t* desc, int cap, int* n_out) {
@@ -575,7 +731,7 @@ int extract(Extractor& e, const uint8_t* img, int w, int h, size_t stride, const
   compute_pyramid(e, img, w, h, stride, false);
   const auto t1 = now();
   const double fast_before = e.t_stage[1], ang_before = e.t_stage[3];
-  int rc = compute_keypoints_old(e);
+  int rc = e.kp_mode == 1 ? compute_keypoints_octree(e) : compute_keypoints_old(e);
   if (rc) return rc;
   const auto t2 = now();
   e.t_stage[0] += secs(t0, t1);
@@ -756,6 +912,7 @@ void* orc_extractor_create(int nfeatures, float scaleFactor, int nlevels, int in
 }
 void orc_extractor_destroy(void* h) { delete (Extractor*)h; }
 void orc_set_trig_mode(void* h, int mode) { ((Extractor*)h)->trig_mode = mode; }
+void orc_set_keypoint_mode(void* h, int mode) { ((Extractor*)h)->kp_mode = mode; }
 int orc_features_per_level(void* h, int* out) { Extractor* e = (Extractor*)h; for (int l = 0; l < e->nlevels; ++l) out[l] = e->nPerLevel[l]; return e->nlevels; }
 int orc_scale_factors(void* h, float* out) { Extractor* e = (Extractor*)h; for (int l = 0; l < e->nlevels; ++l) out[l] = e->scale[l]; return e->nlevels; }
 int orc_umax(void* h, int* out) { Extractor* e = (Extractor*)h; for (int v = 0; v <= 15; ++v) out[v] = e->umax[v]; return 16; }

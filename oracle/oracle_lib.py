@@ -75,6 +75,8 @@ def lib():
     L.orc_extractor_destroy.restype = None
     L.orc_set_trig_mode.argtypes = [vp, C.c_int]
     L.orc_set_trig_mode.restype = None
+    L.orc_set_keypoint_mode.argtypes = [vp, C.c_int]
+    L.orc_set_keypoint_mode.restype = None
     for name in ("orc_features_per_level", "orc_scale_factors", "orc_umax"):
         getattr(L, name).argtypes = [vp, vp]
         getattr(L, name).restype = C.c_int
@@ -174,6 +176,11 @@ class OracleExtractor:
 
     def set_trig_mode(self, mode):
         lib().orc_set_trig_mode(self.h, mode)
+
+    def set_keypoint_mode(self, mode):
+        """0: ComputeKeyPointsOld (the reference's live path), 1: ComputeKeyPointsOctTree (dead there, optional here)."""
+        lib().orc_set_keypoint_mode(self.h, mode)
+        self.cap = self.nfeatures + 64 if mode == 0 else self.nfeatures + 64 + 4 * self.nlevels
 
     def features_per_level(self):
         out = np.zeros(self.nlevels, np.int32)

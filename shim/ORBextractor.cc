@@ -34,6 +34,8 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 
 ORBextractor::~ORBextractor() { ivg_extractor_destroy(mHandle); }
 
+void ORBextractor::SetKeypointMode(int mode) { check(ivg_extractor_set_mode(mHandle, mode), "ivg_extractor_set_mode"); }
+
 void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
                               cv::OutputArray _descriptors) {
   if (_image.empty()) return;                                   // src/ORBextractor.cc:1227-1228

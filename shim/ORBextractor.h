@@ -11,7 +11,8 @@
  *  - mvImagePyramid / mvQualityImagePyramid are filled lazily by SyncPyramidsToHost() (the device keeps the master
  *    copy; the GPU stereo matcher never needs them on the host).  Code that reads the pyramids directly, like the
  *    reference's Frame::ComputeStereoMatches, must call it first — the shim's ComputeStereoMatches does not need to;
- *  - the dead ComputeKeyPointsOctTree / DistributeOctTree / ExtractorNode members are not provided.
+ *  - ComputeKeyPointsOctTree / DistributeOctTree (dead code in the reference) are available as an optional mode,
+ *    SetKeypointMode(1); the protected member functions themselves and ExtractorNode are not exposed.
  */
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
@@ -48,6 +49,9 @@ class ORBextractor {
   std::vector<cv::Mat> mvImagePyramid;
   std::vector<cv::Mat> mvQualityImagePyramid;
 
+  // 0 (default): ComputeKeyPointsOld, the path the reference runs; 1: ComputeKeyPointsOctTree + DistributeOctTree, which
+  // the reference compiles but never calls (src/ORBextractor.cc:1247-1248).  See ivg_extractor_set_mode.
+  void SetKeypointMode(int mode);
   // Copies the device pyramids of the last operator() call into mvImagePyramid / mvQualityImagePyramid.
   void SyncPyramidsToHost();
   // The underlying C-ABI handle (used by the GPU Frame::ComputeStereoMatches replacement).

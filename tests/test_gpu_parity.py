@@ -273,3 +273,19 @@ def test_warp_nth_element_matches_libstdcxx(gpu_api, oracle):
         got = gpu_api.debug_nth_element(keys, nth)
         want = oracle.retain_best(resp, nth + 1)      # first nth+1 survivors of nth_element(begin, begin+nth, end)
         assert np.array_equal(got[:nth + 1], want), (vals.size, nth)
+
+
+@pytest.mark.parametrize("w,h,nf,ini", [(1241, 376, 2000, 20), (960, 600, 2000, 12), (640, 480, 1000, 20), (3840, 2160, 8000, 20), (752, 480, 1200, 50)])
+def test_octree_mode(gpu_api, oracle, w, h, nf, ini):
+    """Optional mode 1 = ComputeKeyPointsOctTree + DistributeOctTree (dead code in the reference, named by the north star),
+    with the reference's pointer tie-break replaced by creation order in both the oracle and the CUDA path."""
+    left, right = S.make_stereo_pair(w, h, w + ini)
+    gL, gR, oL, oR = _pair(gpu_api, oracle, nf, ini, 7, False)
+    for e in (gL, gR, oL, oR):
+        e.set_keypoint_mode(1)
+    info = _check_frame(gpu_api, oracle, gL, gR, oL, oR, left, right, None, 100.0, 400.0, "octree %dx%d" % (w, h))
+    assert nf - 50 <= info["n"] <= nf + 3 * 8
+    # and back to the live path on the same handles
+    for e in (gL, gR, oL, oR):
+        e.set_keypoint_mode(0)
+    _check_frame(gpu_api, oracle, gL, gR, oL, oR, left, right, None, 100.0, 400.0, "live after octree")

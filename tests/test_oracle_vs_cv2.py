@@ -90,6 +90,28 @@ def test_pipeline_matches_cv2_composition(oracle, w, h, nf, ini, intro):
     assert np.array_equal(do, dc)
 
 
+@pytest.mark.parametrize("w,h,nf", [(640, 480, 1000), (1241, 376, 2000)])
+def test_octree_mode_matches_independent_restatement(oracle, w, h, nf):
+    """Mode 1 (ComputeKeyPointsOctTree + DistributeOctTree, dead code in the reference): the C++ oracle (std::list, like the
+    reference) against the independent Python restatement built on cv2's FAST.  Both break the reference's pointer
+    tie-break by creation order."""
+    img = S.make_image(w, h, 33)
+    eo = oracle.OracleExtractor(nf, 1.2, 8, 20, 7)
+    eo.set_keypoint_mode(1)
+    ec = Cv2Extractor(nf, 1.2, 8, 20, 7)
+    ec.kp_mode = 1
+    ko, do = eo(img)
+    kc, dc = ec(img)
+    assert ko.size == kc.size and nf - 50 <= ko.size <= nf + 24
+    for f in ko.dtype.names:
+        assert np.array_equal(ko[f], kc[f]), f
+    assert np.array_equal(do, dc)
+    # one keypoint per quadtree node => no duplicates inside a level
+    for l in range(8):
+        k = eo.level_keypoints(l)
+        assert len(set(zip(k["x"].tolist(), k["y"].tolist()))) == k.size
+
+
 @pytest.mark.parametrize("name", ["small_plain", "small_cost", "kitti_c1", "jackal_c2"])
 def test_oracle_reproduces_golden(oracle, name):
     """tests/golden/*.npz were produced by make_golden.py from cv2 4.13; the C++ oracle must reproduce them bit-for-bit."""
