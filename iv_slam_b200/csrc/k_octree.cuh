@@ -12,7 +12,7 @@
 //   emit     one keypoint per node, the first of maximal response, in list order (:747-766).
 // One deliberate difference: the reference sorts (size, ExtractorNode*) pairs (:690), so equal-size nodes are ordered
 // by heap address — nondeterministic across runs.  Here the tie is broken by creation order (later
-// created = larger), identical to the oracle, so the result is a pure function of the image.
+// created = larger), so the result is a pure function of the image (the tests hold the CPU restatement to the same rule).
 #pragma once
 #include "common.cuh"
 
