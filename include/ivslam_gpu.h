@@ -105,6 +105,12 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
                       ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
 int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
                      size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes);
+/* Same as ivg_upload_batch for frames that already live in DEVICE memory on the handle's device (the
+ * introspection CNN's cost-map is produced on the GPU; this avoids the GPU->CPU->GPU round trip of the reference,
+ * Examples/Stereo/stereo_kitti.cc:494-521).  Contiguous, 4-byte aligned frames are read in place by the ingest kernel.
+ * The caller guarantees the producer has finished writing (or was enqueued on a stream this handle is ordered after). */
+int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, int width, int height, size_t stride,
+                            size_t frame_bytes, const uint8_t* d_costs, size_t cost_stride, size_t cost_frame_bytes);
 int ivg_run_batch(ivg_extractor* h);
 int ivg_download_batch(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
 int ivg_sync(ivg_extractor* h);

@@ -63,6 +63,7 @@ def lib():
         "ivg_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, C.c_int, i32p]),
         "ivg_extract_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz, vp, vp, C.c_int, vp]),
         "ivg_upload_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
+        "ivg_upload_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_run_batch": (C.c_int, [vp]),
         "ivg_download_batch": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "ivg_sync": (C.c_int, [vp]),
@@ -236,6 +237,12 @@ class ORBextractor:
         n, H, W = images.shape
         _ck(lib().ivg_upload_batch(self._h, n, _p(images), W, H, images.strides[1], images.strides[0], _p(masks),
                                    masks.strides[1] if masks is not None else 0, masks.strides[0] if masks is not None else 0), "ivg_upload_batch")
+        self._batch = n
+
+    def upload_device(self, n, width, height, d_images, d_masks=None):
+        """Frames already in device memory (integer device pointers to n contiguous HxW u8 frames)."""
+        _ck(lib().ivg_upload_batch_device(self._h, n, C.c_void_p(d_images), width, height, width, width * height,
+                                          C.c_void_p(d_masks) if d_masks else None, width, width * height), "ivg_upload_batch_device")
         self._batch = n
 
     def run(self):

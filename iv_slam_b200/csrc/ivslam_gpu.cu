@@ -664,9 +664,25 @@ int ivg_device_input(ivg_extractor* h, int index, int which, void** dev_ptr, siz
   return IVG_OK;
 }
 
-static int copy_frames_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& stage, int n, const uint8_t* src, size_t stride, size_t frame_bytes) {
+static int copy_frames_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& stage, int n, const uint8_t* src, size_t stride, size_t frame_bytes,
+                          bool src_on_device = false) {
   const FrameSet& fs = h->fs;
   const size_t dpitch = fs.lv[0].pitch;
+  if (src_on_device) {
+    // frames already in device memory (e.g. the introspection CNN's cost-map): no staging copy at all when they are
+    // contiguous and word aligned — the ingest kernel reads them in place; otherwise a device-to-device pitched copy
+    if (stride == (size_t)h->W && frame_bytes == (size_t)h->W * h->H && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+      dim3 grid(((h->W + 3) / 4 + 255) / 256, h->H, n);
+      k_ingest<<<grid, 256, 0, h->stream>>>(src, plane, fs.planeBytes, h->W, h->H, (int)dpitch);
+      h->launches++;
+      CK(cudaGetLastError());
+    } else {
+      for (int f = 0; f < n; ++f)
+        CK(cudaMemcpy2DAsync(plane + (size_t)f * fs.planeBytes, dpitch, src + (size_t)f * frame_bytes, stride, h->W, h->H,
+                             cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return IVG_OK;
+  }
   if (stride == (size_t)h->W && frame_bytes == (size_t)h->W * h->H) {
     // contiguous frames: one linear DMA + on-device re-pitch
     const size_t bytes = (size_t)n * frame_bytes;
@@ -709,6 +725,20 @@ int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, 
     if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, costs, cost_stride, cost_frame_bytes))) return rc;
   }
   CK(cudaEventRecord(h->evIngest, h->stream));
+  return IVG_OK;
+}
+
+int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, int width, int height, size_t stride,
+                            size_t frame_bytes, const uint8_t* d_costs, size_t cost_stride, size_t cost_frame_bytes) {
+  if (!h || !d_images || n < 1 || stride < (size_t)width) return IVG_ERR_INVALID;
+  int rc = ivg_set_batch(h, n, width, height, d_costs != nullptr);
+  if (rc) return rc;
+  if ((rc = honour_wait(h))) return rc;
+  if ((rc = copy_frames_in(h, h->pyr.p, h->stageImg, n, d_images, stride, frame_bytes, true))) return rc;
+  if (h->curWeighted) {
+    if (cost_stride < (size_t)width) return IVG_ERR_INVALID;
+    if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, d_costs, cost_stride, cost_frame_bytes, true))) return rc;
+  }
   return IVG_OK;
 }
 

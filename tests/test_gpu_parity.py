@@ -289,3 +289,30 @@ def test_octree_mode(gpu_api, oracle, w, h, nf, ini):
     for e in (gL, gR, oL, oR):
         e.set_keypoint_mode(0)
     _check_frame(gpu_api, oracle, gL, gR, oL, oR, left, right, None, 100.0, 400.0, "live after octree")
+
+
+def test_device_resident_inputs_and_weighted_batch(gpu_api, oracle):
+    """N3 hand-off: image and cost-map already on the GPU (torch tensors stand in for the introspection CNN's output) go in
+    through ivg_upload_batch_device; a weighted batch must equal the per-frame oracle."""
+    import torch
+    n, w, h = 3, 960, 600
+    L = np.stack([S.make_image(w, h, 70 + i) for i in range(n)])
+    cost = np.stack([S.make_cost_map(w, h, 80 + i) for i in range(n)])
+    dL, dC = torch.from_numpy(L).cuda(), torch.from_numpy(cost).cuda()
+    torch.cuda.synchronize()
+    g = gpu_api.ORBextractor(2000, 1.2, 8, 12, 7, True)
+    o = oracle.OracleExtractor(2000, 1.2, 8, 12, 7, True)
+    g.upload_device(n, w, h, dL.data_ptr(), dC.data_ptr())
+    g.run()
+    kps = np.zeros((n, g.cap), gpu_api.KP_DTYPE)
+    desc = np.zeros((n, g.cap, 32), np.uint8)
+    cnt = np.zeros(n, np.int32)
+    g.download(kps, desc, cnt)
+    g.sync()
+    for f in range(n):
+        ko, do = o(L[f], cost[f])
+        assert_keypoints_equal(kps[f, :cnt[f]], ko, "device input frame %d" % f)
+        assert np.array_equal(desc[f, :cnt[f]], do)
+    # host path, weighted batch: same answer
+    k2, d2, c2 = g.extract_batch(L, cost)
+    assert np.array_equal(c2, cnt) and k2.tobytes() == kps.tobytes() and d2.tobytes() == desc.tobytes()
