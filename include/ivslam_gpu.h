@@ -153,6 +153,17 @@ int ivg_stereo_match_keypoints(ivg_extractor* left, ivg_extractor* right,
 /* Pyramid only (no detection) for frame 0: stages mvImagePyramid for ivg_stereo_match_keypoints. Synchronous. */
 int ivg_compute_pyramid(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride);
 
+/* ---- N1 (next row): the keypoint loops of the stereo Frame constructor after extraction ----
+ * mvKeyQualScore (src/Frame.cc:128-143), UndistortKeyPoints for rectified input (identity, :696-700), AssignFeaturesToGrid
+ * + PosInGrid (:415-430, :670-680) for every frame of the last batch, on the keypoints still on the device.
+ * (minX, maxX, minY, maxY) = mnMinX.. of ComputeImageBounds (:728-756; 0, cols, 0, rows without distortion).
+ * keyQualScore: frames*cap floats (1.0 when the batch had no cost-map; the cost-map is used whenever one was uploaded,
+ * with or without introspection, like the reference).  Grid as CSR per frame: gridStart has 64*48+1 entries, cell =
+ * col*48 + row (mGrid[col][row]); gridIndices lists keypoint indices, ascending inside a cell.  Distorted input
+ * (k1 != 0) is not supported.  Async unless sync != 0. */
+int ivg_frame_postprocess_batch(ivg_extractor* h, float minX, float maxX, float minY, float maxY,
+                                float* keyQualScore, int* gridStart, int* gridIndices, int cap, int sync);
+
 /* ---- measurement helpers (bench.py) ---- */
 /* CUDA-event timer on the handle's stream: start records an event, stop records another, elapsed waits for it. */
 int ivg_timer_start(ivg_extractor* h);

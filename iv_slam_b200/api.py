@@ -77,6 +77,7 @@ def lib():
         "ivg_stereo_match_batch": (C.c_int, [vp, vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int]),
         "ivg_stereo_match_keypoints": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp]),
         "ivg_compute_pyramid": (C.c_int, [vp, vp, C.c_int, C.c_int, sz]),
+        "ivg_frame_postprocess_batch": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, C.c_int, C.c_int]),
         "ivg_timer_start": (C.c_int, [vp]),
         "ivg_timer_stop": (C.c_int, [vp]),
         "ivg_timer_elapsed_ms": (C.c_int, [vp, f32p]),
@@ -282,6 +283,15 @@ class ORBextractor:
         n = C.c_int(0)
         _ck(lib().ivg_get_level_keypoints(self._h, index, level, _p(x), _p(y), _p(r), cap, C.byref(n)), "ivg_get_level_keypoints")
         return x[:n.value].copy(), y[:n.value].copy(), r[:n.value].copy()
+
+    def frame_postprocess(self, minX, maxX, minY, maxY):
+        """mvKeyQualScore + AssignFeaturesToGrid for every frame of the last batch -> (qual[n,cap], gridStart[n,3073], gridIdx[n,cap])."""
+        n = self._batch
+        qual = np.zeros((n, self.cap), np.float32)
+        gs = np.zeros((n, 64 * 48 + 1), np.int32)
+        gi = np.zeros((n, self.cap), np.int32)
+        _ck(lib().ivg_frame_postprocess_batch(self._h, minX, maxX, minY, maxY, _p(qual), _p(gs), _p(gi), self.cap, 1), "ivg_frame_postprocess_batch")
+        return qual, gs, gi
 
     # -- measurement
     def timer_start(self):

@@ -20,6 +20,7 @@
 #include "k_blur.cuh"
 #include "k_describe.cuh"
 #include "k_fast.cuh"
+#include "k_frame.cuh"
 #include "k_pyramid.cuh"
 #include "k_select.cuh"
 #include "k_octree.cuh"
@@ -98,6 +99,7 @@ struct ivg_extractor {
   FrameSet fs{};                        // template (pointers filled, nImages/weighted set per run)
   int curBatch = 0;
   bool curWeighted = false;
+  bool haveCost = false;                // a cost-map was supplied with the current batch (used by ivg_frame_postprocess even without introspection)
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
@@ -113,7 +115,8 @@ struct ivg_extractor {
   DevBuf<uint2> workCell, workLevel, levelKp;
   DevBuf<int> levelCount, outN, sad, nExt, rowStart;
   DevBuf<uint4> sortedR;
-  DevBuf<float> uRight, depth;
+  DevBuf<float> uRight, depth, kpQual;
+  DevBuf<int> gridStart, gridIdx;
   // stereo on caller-supplied keypoints
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
   bool graphMode = false;
@@ -598,6 +601,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release();
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
+  h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
   h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->sortedR.release(); h->rowStart.release();
   for (cudaEvent_t e : h->profEv) cudaEventDestroy(e);
@@ -652,6 +656,11 @@ int ivg_set_batch(ivg_extractor* h, int n, int width, int height, int with_cost)
   if (rc) return rc;
   h->curBatch = n;
   h->curWeighted = with_cost && h->enableIntrospection;   // src/ORBextractor.cc:1231
+  h->haveCost = with_cost != 0;
+  if (with_cost && !h->qual.p) {                           // cost-map planes are also needed by ivg_frame_postprocess
+    if ((rc = h->qual.alloc((size_t)h->maxBatch * h->fs.planeBytes))) return rc;
+    h->fs.qual = h->qual.p;
+  }
   return IVG_OK;
 }
 
@@ -720,7 +729,7 @@ int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, 
   if (rc) return rc;
   if ((rc = honour_wait(h))) return rc;
   if ((rc = copy_frames_in(h, h->pyr.p, h->stageImg, n, images, stride, frame_bytes))) return rc;
-  if (h->curWeighted) {
+  if (h->haveCost) {
     if (cost_stride < (size_t)width) return IVG_ERR_INVALID;
     if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, costs, cost_stride, cost_frame_bytes))) return rc;
   }
@@ -735,7 +744,7 @@ int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, in
   if (rc) return rc;
   if ((rc = honour_wait(h))) return rc;
   if ((rc = copy_frames_in(h, h->pyr.p, h->stageImg, n, d_images, stride, frame_bytes, true))) return rc;
-  if (h->curWeighted) {
+  if (h->haveCost) {
     if (cost_stride < (size_t)width) return IVG_ERR_INVALID;
     if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, d_costs, cost_stride, cost_frame_bytes, true))) return rc;
   }
@@ -948,6 +957,41 @@ int ivg_stereo_match_keypoints(ivg_extractor* left, ivg_extractor* right, const 
   u.release(); d.release(); s.release();
   if (e != cudaSuccess) { g_cuda_err = cudaGetErrorString(e); return IVG_ERR_CUDA; }
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------- N1: rest of the Frame ctor
+int ivg_frame_postprocess_batch(ivg_extractor* h, float minX, float maxX, float minY, float maxY,
+                                float* keyQualScore, int* gridStart, int* gridIndices, int cap, int sync) {
+  if (!h || !h->haveResults) return IVG_ERR_STATE;
+  if (!(maxX > minX) || !(maxY > minY)) return IVG_ERR_INVALID;
+  if (cap < h->fs.kpCap) return IVG_ERR_CAPACITY;
+  CK(cudaSetDevice(h->device));
+  const int n = h->curBatch;
+  const int NC = GRID_COLS * GRID_ROWS;
+  int rc;
+  if ((rc = h->kpQual.alloc((size_t)h->maxBatch * h->fs.kpCap)) || (rc = h->gridIdx.alloc((size_t)h->maxBatch * h->fs.kpCap)) ||
+      (rc = h->gridStart.alloc((size_t)h->maxBatch * (NC + 1))))
+    return rc;
+  FramePostArgs A{};
+  A.kp = h->outKp.p; A.n = h->outN.p;
+  A.cost = h->haveCost ? h->qual.p : nullptr;             // level 0 of the cost-map plane = the map itself
+  A.planeBytes = h->fs.planeBytes; A.costPitch = h->fs.lv[0].pitch; A.cap = h->fs.kpCap;
+  A.minX = minX; A.minY = minY;
+  A.invW = (float)GRID_COLS / (maxX - minX);               // mfGridElementWidthInv  (src/Frame.cc:213)
+  A.invH = (float)GRID_ROWS / (maxY - minY);               // mfGridElementHeightInv (src/Frame.cc:216)
+  A.qual = h->kpQual.p; A.gridStart = h->gridStart.p; A.gridIdx = h->gridIdx.p;
+  CK(cudaStreamWaitEvent(h->stream, h->evD2H, 0));
+  k_frame_post<<<n, 256, 0, h->stream>>>(A); h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->evKernels, h->stream));
+  CK(cudaStreamWaitEvent(h->copyOut, h->evKernels, 0));
+  const size_t k = h->fs.kpCap;
+  if (keyQualScore) CK(cudaMemcpy2DAsync(keyQualScore, (size_t)cap * 4, h->kpQual.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, h->copyOut));
+  if (gridIndices) CK(cudaMemcpy2DAsync(gridIndices, (size_t)cap * 4, h->gridIdx.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, h->copyOut));
+  if (gridStart) CK(cudaMemcpyAsync(gridStart, h->gridStart.p, (size_t)n * (NC + 1) * 4, cudaMemcpyDeviceToHost, h->copyOut));
+  CK(cudaEventRecord(h->evD2H, h->copyOut));
+  if (sync) return ivg_sync(h);
+  return IVG_OK;
 }
 
 // ---------------------------------------------------------------------------------------- measurement helpers

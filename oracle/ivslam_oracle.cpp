@@ -953,6 +953,33 @@ int orc_stereo_match(void* left, void* right, const void* kL, int N, const uint8
                       mbf, maxD, uRight, depth, bestDist, sad);
 }
 
+// N1: mvKeyQualScore (src/Frame.cc:128-143), UndistortKeyPoints for k1 == 0 (:696-700), AssignFeaturesToGrid + PosInGrid
+// (:415-430, :670-680).  cost may be null (=> scores 1.0).  Grid as CSR: cell = col*48 + row, indices ascending.
+void orc_frame_post(const void* kps_, int N, const uint8_t* cost, size_t cost_stride, float minX, float maxX, float minY, float maxY,
+                    float* qual, int* gridStart, int* gridIdx) {
+  const KeyPoint* k = (const KeyPoint*)kps_;
+  const int COLS = 64, ROWS = 48;
+  for (int i = 0; i < N; ++i) {
+    if (cost) {
+      int px = static_cast<int>(std::round(k[i].x)), py = static_cast<int>(std::round(k[i].y));
+      float c = static_cast<float>(cost[(size_t)py * cost_stride + px]);
+      float qual_score = 1.0 / (1.0 + c / 256);
+      float qual_score_norm = 2 * qual_score - 1;
+      qual[i] = qual_score_norm;
+    } else qual[i] = 1.0f;
+  }
+  const float invW = static_cast<float>(COLS) / (maxX - minX), invH = static_cast<float>(ROWS) / (maxY - minY);
+  std::vector<std::vector<int>> grid(COLS * ROWS);
+  for (int i = 0; i < N; ++i) {
+    int posX = (int)std::round((k[i].x - minX) * invW), posY = (int)std::round((k[i].y - minY) * invH);
+    if (posX < 0 || posX >= COLS || posY < 0 || posY >= ROWS) continue;
+    grid[posX * ROWS + posY].push_back(i);
+  }
+  int run = 0;
+  for (int c = 0; c < COLS * ROWS; ++c) { gridStart[c] = run; for (int i : grid[c]) gridIdx[run++] = i; }
+  gridStart[COLS * ROWS] = run;
+}
+
 // One stereo frame with the reference's threading: two extraction threads, then matching on
 // the caller (src/Frame.cc:115-125, :193).  cost applies to the left eye only (the right
 // extractor is built without introspection, src/Tracking.cc:182-183).

@@ -96,6 +96,8 @@ def lib():
     L.orc_stats.restype = None
     L.orc_stage_seconds.argtypes = [vp, vp]
     L.orc_stage_seconds.restype = None
+    L.orc_frame_post.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    L.orc_frame_post.restype = None
     L.orc_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]
     L.orc_stereo_match.restype = C.c_int
     L.orc_stereo_frame.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_float,
@@ -297,3 +299,15 @@ def stereo_batch(params, imgsL, imgsR, mbf, maxD, workers):
     if rc:
         raise RuntimeError("oracle batch failed rc=%d" % rc)
     return nL, nM
+
+
+def frame_post(kps, cost, minX, maxX, minY, maxY):
+    """mvKeyQualScore + AssignFeaturesToGrid (N1) -> (qual[N], gridStart[3073], gridIdx[N])."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    if cost is not None:
+        cost = _u8(cost)
+    qual = np.zeros(kps.size, np.float32)
+    gs = np.zeros(64 * 48 + 1, np.int32)
+    gi = np.zeros(max(kps.size, 1), np.int32)
+    lib().orc_frame_post(_p(kps), kps.size, _p(cost), cost.strides[0] if cost is not None else 0, minX, maxX, minY, maxY, _p(qual), _p(gs), _p(gi))
+    return qual, gs, gi[:kps.size]

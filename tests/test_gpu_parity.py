@@ -316,3 +316,23 @@ def test_device_resident_inputs_and_weighted_batch(gpu_api, oracle):
     # host path, weighted batch: same answer
     k2, d2, c2 = g.extract_batch(L, cost)
     assert np.array_equal(c2, cnt) and k2.tobytes() == kps.tobytes() and d2.tobytes() == desc.tobytes()
+
+
+@pytest.mark.parametrize("intro", [False, True])
+def test_n1_frame_postprocess(gpu_api, oracle, intro):
+    """N1: mvKeyQualScore (cost/256 at the rounded level-0 position) and AssignFeaturesToGrid (64x48, ascending indices)."""
+    n, w, h = 2, 960, 600
+    L = np.stack([S.make_image(w, h, 90 + i) for i in range(n)])
+    cost = np.stack([S.make_cost_map(w, h, 95 + i) for i in range(n)])
+    g = gpu_api.ORBextractor(2000, 1.2, 8, 12, 7, intro)
+    kps, desc, cnt = g.extract_batch(L, cost)
+    qual, gs, gi = g.frame_postprocess(0.0, float(w), 0.0, float(h))
+    for f in range(n):
+        m = int(cnt[f])
+        q, s, i = oracle.frame_post(kps[f, :m], cost[f], 0.0, float(w), 0.0, float(h))
+        assert np.array_equal(qual[f, :m], q) and np.array_equal(gs[f], s) and np.array_equal(gi[f, :s[-1]], i[:s[-1]])
+        assert s[-1] == m and 0.0 <= q.min() and q.max() <= 1.0
+    # without a cost-map every score is 1.0
+    g.extract_batch(L)
+    qual, gs, gi = g.frame_postprocess(0.0, float(w), 0.0, float(h))
+    assert (qual[0, :int(cnt[0])] == 1.0).all()
