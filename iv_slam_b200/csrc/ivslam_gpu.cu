@@ -287,8 +287,8 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
       bh = std::min(std::max(bh, 4), 200);
       L.fBH = std::min(bh, L.cellH);
       const size_t ssBytes = align_up((size_t)L.fSS * (L.fBH + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (L.fBH + 2), 16);
-      L.fSeg = ((((L.fBH + 3) / 2) * ((L.fBW + 3) / 4) + 7) / 8) * 128;   // per-warp pair list: items of up to 4 chunks x 32 lanes
-      const size_t listBytes = (size_t)2 * 8 * L.fSeg;
+      L.fSeg = ((((L.fBH + 3) / 2) * ((L.fBW + 3) / 4) + FC_WARPS - 1) / FC_WARPS) * 128;   // per-warp pair list: items of up to 4 chunks x 32 lanes
+      const size_t listBytes = (size_t)2 * FC_WARPS * L.fSeg;
       fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + ssBytes + bitBytes + listBytes);
     }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
@@ -464,7 +464,7 @@ int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
 int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   int rc = launch_pyramid(h, fs);
   if (rc) return rc;
-  { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), 256, h->fastSmem, h->stream>>>(fs); }
+  { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS, h->fastSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
   if (h->kpMode == 1) { ProfScope ps(h, IVG_K_SELECT); k_octree_select<<<dim3(fs.nlevels, fs.nImages), 256, sizeof(OctShared), h->stream>>>(fs); }
   else { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }

@@ -58,10 +58,13 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
   return __vmaxu2(best, 0x02000200u - worst);
 }
 
-__global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
+constexpr int FC_THREADS = 160; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
+constexpr int FC_WARPS = FC_THREADS / 32;
+
+__global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char fsm[];
-  __shared__ int wcnt[2][8];
-  __shared__ int sred[3][8];
+  __shared__ int wcnt[2][FC_WARPS];
+  __shared__ int sred[3][FC_WARPS];
 
   const CellDev c = fs.cells[blockIdx.x];
   const LevelDev& L = fs.lv[c.level];
@@ -97,9 +100,9 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
       // thread = (column group g, row segment): rows are walked top to bottom with the previous row carried in a
       // register, so every global word is loaded once
       const int nG4 = SP >> 2;
-      const int nSeg = max(256 / nG4, 1);
+      const int nSeg = max(FC_THREADS / nG4, 1);
       const int segRows = (nWR + nSeg - 1) / nSeg;
-      for (int t = tid; t < nG4 * nSeg; t += 256) {
+      for (int t = tid; t < nG4 * nSeg; t += FC_THREADS) {
         const int seg = t / nG4, g = t - seg * nG4;
         const int q0 = seg * segRows, q1 = min(q0 + segRows, nWR);
         if (q0 < q1) {
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
     }
     {
       uint4* z = reinterpret_cast<uint4*>(ss);                // scores + bitmap are contiguous
-      for (int i = tid; i < ((ssBytes + bitBytes) >> 4); i += 256) z[i] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < ((ssBytes + bitBytes) >> 4); i += FC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
 
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
       // work item = (row pair p, segment of up to 4 chunks of 32 columns); the inner loop only bumps pointers
       const int nSegs = (nChunks + 3) >> 2;
       const unsigned ltmask = (1u << lane) - 1u;
-      for (int it = warp; it < nPairs * nSegs; it += 8) {
+      for (int it = warp; it < nPairs * nSegs; it += FC_WARPS) {
         const int p = it / nSegs, sg = it - p * nSegs;
         int x = sg * 128 + lane;
         const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
 
     // ---- E: emit in row-major order
     const int nWords = (r1 - r0) * BW;
-    for (int base = 0; base < nWords; base += 256) {
+    for (int base = 0; base < nWords; base += FC_THREADS) {
       const int i = base + tid;
       unsigned bits = i < nWords ? sbit[i] : 0u;
       const int cnt = __popc(bits);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
       __syncthreads();
       int off = running + incl - cnt, tot = 0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
+      for (int w = 0; w < FC_WARPS; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
       running += tot;
       par ^= 1;
       if (bits) {
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
   unsigned csum = 0;
   if (fs.weighted) {
     const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
-    for (int y = warp; y < c.wh; y += 8) {
+    for (int y = warp; y < c.wh; y += FC_WARPS) {
       const uint8_t* qr = q + (size_t)(c.wy + y) * L.pitch + c.wx;
       for (int x = lane; x < c.ww; x += 32) csum += __ldg(qr + x);
     }
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_cells(FrameSet fs) {
   if (tid == 0) {
     int a = 0, b = 0; unsigned s = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { a += sred[0][w]; b += sred[1][w]; s += (unsigned)sred[2][w]; }
+    for (int w = 0; w < FC_WARPS; ++w) { a += sred[0][w]; b += sred[1][w]; s += (unsigned)sred[2][w]; }
     fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = make_int2(b, a);   // x: corners at minTh, y: corners at iniTh
     fs.cellCost[img * fs.cellCostStride + blockIdx.x] = s;
   }
