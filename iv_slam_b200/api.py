@@ -8,8 +8,10 @@ Frame::ComputeStereoMatches (src/Frame.cc:758-932) on what the two extractors ho
 There is NO CPU fallback: importing works anywhere (so the build check can import the package), but creating an
 extractor without the compiled library or without an sm_100 GPU raises.
 """
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -120,6 +122,25 @@ def device_info(device=0):
     return rc, name.value.decode(), sm.value, cnt.value
 
 
+_live = weakref.WeakSet()      # extractors and pinned buffers still open: closed in a safe order before the CUDA runtime unloads
+
+
+def _close_all():
+    objs = list(_live)
+    for o in objs:          # handles that borrow a stream first, then stream owners, then pinned memory
+        if isinstance(o, ORBextractor) and getattr(o, "_stream_owner", None) is not None:
+            o.close()
+    for o in objs:
+        if isinstance(o, ORBextractor):
+            o.close()
+    for o in objs:
+        if isinstance(o, PinnedArray):
+            o.free()
+
+
+atexit.register(_close_all)
+
+
 class PinnedArray:
     """numpy view over cudaHostAlloc'ed memory (for real async H2D/D2H in the batch path)."""
 
@@ -130,6 +151,7 @@ class PinnedArray:
         _ck(lib().ivg_host_alloc(C.byref(self.ptr), max(self.nbytes, 1)), "ivg_host_alloc")
         buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+        _live.add(self)
 
     def free(self):
         if self.ptr:
@@ -154,6 +176,8 @@ class ORBextractor:
         self.nfeatures, self.nlevels, self.device = nfeatures, nlevels, device
         self.cap = lib().ivg_max_keypoints(self._h)
         self._batch = 0
+        self._stream_owner = None
+        _live.add(self)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -595,7 +595,9 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
 void ivg_extractor_destroy(ivg_extractor* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  // a shared kernel stream belongs to another handle (which may already be gone): the cudaFree calls below synchronise
+  // the device anyway, so only streams this handle owns are touched
+  if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
   h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release();

@@ -97,15 +97,13 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     // ---- A: stage. word row q holds pixel rows (q, q+1) counted from global row gy0
     const int gy0 = c.y0 + s0 - 3;
     {
-      // thread = (column group g, row segment): rows are walked top to bottom with the previous row carried in a
-      // register, so every global word is loaded once
+      // warp = row segment, lane = column group: rows are walked top to bottom with the previous row carried in a
+      // register, so every global word is loaded once (plus one seed row per segment); no integer division anywhere
       const int nG4 = SP >> 2;
-      const int nSeg = max(FC_THREADS / nG4, 1);
-      const int segRows = (nWR + nSeg - 1) / nSeg;
-      for (int t = tid; t < nG4 * nSeg; t += FC_THREADS) {
-        const int seg = t / nG4, g = t - seg * nG4;
-        const int q0 = seg * segRows, q1 = min(q0 + segRows, nWR);
-        if (q0 < q1) {
+      const int segRows = (nWR + FC_WARPS - 1) / FC_WARPS;
+      const int q0 = warp * segRows, q1 = min(q0 + segRows, nWR);
+      if (q0 < q1) {
+        for (int g = lane; g < nG4; g += 32) {
           const bool in = xa + 4 * g < pitch;
           const uint8_t* prow = pix + (size_t)(gy0 + q0) * pitch + xa + 4 * g;
           uint32_t a = in ? __ldg(reinterpret_cast<const uint32_t*>(prow)) : 0u;
@@ -138,8 +136,11 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       // work item = (row pair p, segment of up to 4 chunks of 32 columns); the inner loop only bumps pointers
       const int nSegs = (nChunks + 3) >> 2;
       const unsigned ltmask = (1u << lane) - 1u;
-      for (int it = warp; it < nPairs * nSegs; it += FC_WARPS) {
-        const int p = it / nSegs, sg = it - p * nSegs;
+      int p = 0, sg = warp;                          // item index it = p * nSegs + sg, advanced by FC_WARPS without dividing
+      while (sg >= nSegs) { sg -= nSegs; ++p; }
+      for (; p < nPairs; sg += FC_WARPS) {
+        while (sg >= nSegs) { sg -= nSegs; ++p; }
+        if (p >= nPairs) break;
         int x = sg * 128 + lane;
         const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
         const uint32_t* cp3 = ctr + 3 * SP;  const uint32_t* cm3 = ctr - 3 * SP;     // ring rows +-3, +-2 (row 0 via ctr)
