@@ -683,7 +683,7 @@ static int copy_frames_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& sta
     // frames already in device memory (e.g. the introspection CNN's cost-map): no staging copy at all when they are
     // contiguous and word aligned — the ingest kernel reads them in place; otherwise a device-to-device pitched copy
     if (stride == (size_t)h->W && frame_bytes == (size_t)h->W * h->H && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-      dim3 grid(((h->W + 3) / 4 + 255) / 256, h->H, n);
+      dim3 grid(((h->W + 15) / 16 + 255) / 256, h->H, n);
       k_ingest<<<grid, 256, 0, h->stream>>>(src, plane, fs.planeBytes, h->W, h->H, (int)dpitch);
       h->launches++;
       CK(cudaGetLastError());
@@ -703,7 +703,7 @@ static int copy_frames_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& sta
     CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, h->copyIn));
     CK(cudaEventRecord(h->evH2D, h->copyIn));
     CK(cudaStreamWaitEvent(h->stream, h->evH2D, 0));
-    dim3 grid(((h->W + 3) / 4 + 255) / 256, h->H, n);
+    dim3 grid(((h->W + 15) / 16 + 255) / 256, h->H, n);
     k_ingest<<<grid, 256, 0, h->stream>>>(stage.p, plane, fs.planeBytes, h->W, h->H, (int)dpitch);
     h->launches++;
     CK(cudaGetLastError());

@@ -24,16 +24,21 @@ constexpr int RZ_W = 128, RZ_H = 32;
 // source bytes come from two aligned words and a funnel shift (rows of an unpitched frame are not word aligned).
 __global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ stage, uint8_t* __restrict__ plane, size_t planeBytes,
                                                 int w, int h, int pitch) {
-  const int xw = blockIdx.x * 256 + threadIdx.x;     // destination word of the row
+  const int x16 = (blockIdx.x * 256 + threadIdx.x) * 16;     // 16 destination bytes per thread (one 128-bit store)
   const int y = blockIdx.y;
   const size_t f = blockIdx.z;
-  if (4 * xw >= w) return;
-  const size_t a = f * (size_t)w * h + (size_t)y * w + 4 * xw;
+  if (x16 >= w) return;
+  const size_t a = f * (size_t)w * h + (size_t)y * w + x16;
   const uint32_t* s = reinterpret_cast<const uint32_t*>(stage) + (a >> 2);
-  const int sh = (int)(a & 3);
-  const uint32_t lo = __ldg(s), hi = sh ? __ldg(s + 1) : 0u;     // the second word is only touched when the row is misaligned
-  const uint32_t v = __funnelshift_r(lo, hi, 8 * sh);
-  *reinterpret_cast<uint32_t*>(plane + f * planeBytes + (size_t)y * pitch + 4 * xw) = v;
+  const int sh = 8 * (int)(a & 3);
+  const size_t last = (f * (size_t)w * h + (size_t)h * w - 1) >> 2;     // word holding this frame's last byte: nothing past it is read
+  uint32_t v[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) v[i] = ((a >> 2) + i <= last && (i < 4 || sh)) ? __ldg(s + i) : 0u;
+  uint4 o;
+  o.x = __funnelshift_r(v[0], v[1], sh); o.y = __funnelshift_r(v[1], v[2], sh);
+  o.z = __funnelshift_r(v[2], v[3], sh); o.w = __funnelshift_r(v[3], v[4], sh);
+  *reinterpret_cast<uint4*>(plane + f * planeBytes + (size_t)y * pitch + x16) = o;      // bytes past w land in the row padding
 }
 
 __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, int which /*0 image, 1 cost-map*/,
