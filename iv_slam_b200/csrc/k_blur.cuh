@@ -3,21 +3,22 @@
 // (introspective_ORB_SLAM/src/ORBextractor.cc:1276-1277).  Arithmetic = OpenCV's 8-bit fixed-point path
 // (SURVEY Appendix A.2): Q8 kernel {18,34,48,56,48,34,18}, 16-bit horizontal sums, (v + 2^15) >> 16.
 //
-// Separable, one CTA per 128x32 tile (tile table spans all levels and frames: one launch per batch).
-//   stage       tile + halo (160 x 38 bytes) lands in shared memory through ONE TMA box load (cp.async.bulk.tensor.3d over
+// Separable, one CTA per 128x64 tile (tile table spans all levels and frames: one launch per batch).
+//   stage       tile + halo (160 x 70 bytes) lands in shared memory through ONE TMA box load (cp.async.bulk.tensor.3d over
 //               x, y, frame; out-of-image bytes arrive as zeros) signalled on an mbarrier; only tiles that touch an image
 //               edge then patch their halo by reflection from the bytes already in shared memory;
 //   horizontal  4 pixels per thread in packed 16-bit lanes: the row sums are < 2^16, so one IMAD on a register holding
 //               two pixels (x, x+2) is two exact multiply-adds — 8 masked funnel-shifted windows feed both the even
 //               and the odd pixel pair (28 instructions per 4 pixels);
-//   vertical    4 pixels x 4 rows per thread from the packed 16-bit plane, one aligned 32-bit store per row.
+//   vertical    4 pixels x 8 rows per thread from the packed 16-bit plane, one aligned 32-bit store per row.
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"
 
 namespace ivg {
 
-constexpr int BL_W = 128, BL_H = 32;
+constexpr int BL_W = 128, BL_H = 64;
+constexpr int BL_RPS = BL_H / 8;          // output rows per 32-thread row segment in the vertical pass
 constexpr int BL_BOXW = 160;              // TMA box width in bytes: x0-16 .. x0+143 (the box must start 16-byte aligned)
 constexpr int BL_X0 = 16;                 // staged byte index of tile column 0
 constexpr int BL_PW = BL_BOXW / 4;        // staged words per row
@@ -102,12 +103,12 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs, const __grid_consta
     const int g = tid & 31, seg = tid >> 5;                 // 32 column groups x 8 row segments of 4 rows
     const int gx = x0 + 4 * g;
     if (gx < L.pitch) {
-      uint32_t e[10], o[10];
+      uint32_t e[BL_RPS + 6], o[BL_RPS + 6];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) { const uint2 v = shs[(seg * 4 + j) * (BL_W / 4) + g]; e[j] = v.x; o[j] = v.y; }
+      for (int j = 0; j < BL_RPS + 6; ++j) { const uint2 v = shs[(seg * BL_RPS + j) * (BL_W / 4) + g]; e[j] = v.x; o[j] = v.y; }
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int gy = y0 + seg * 4 + rr;
+      for (int rr = 0; rr < BL_RPS; ++rr) {
+        const int gy = y0 + seg * BL_RPS + rr;
         if (gy >= L.h) break;
         uint32_t res[4];
 #pragma unroll

@@ -46,7 +46,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int DK_SLOTS = 32;             // keypoint slots per CTA
+constexpr int DK_SLOTS = 64;             // keypoint slots per CTA
 constexpr int DK_PR = 18;                // |rotated pattern offset| <= 18 (pattern radius 13*sqrt(2) rounds to 18)
 constexpr int DK_BOXW = 64, DK_BOXH = 2 * DK_PR + 1;   // TMA box: 64 x 37 bytes
 

@@ -3,7 +3,7 @@
 // (introspective_ORB_SLAM/src/ORBextractor.cc:1298-1357, resize calls at :1311 and :1341).
 // Arithmetic = OpenCV's 8-bit fixed-point bilinear path: taps and Q11 coefficients are
 // precomputed on the host exactly as OpenCV derives them; the kernel does the integer part, separably:
-//   stage       the source rectangle of a 128x32 output tile lands in shared memory through ONE TMA box load
+//   stage       the source rectangle of a 128x64 output tile lands in shared memory through ONE TMA box load
 //               (cp.async.bulk.tensor.3d over x, y, frame of the source level, signalled on an mbarrier; every source
 //               byte is read from L2/HBM once per tile).  Scale factors whose source box would exceed the 256-element
 //               TMA box limit use a plain 32-bit load loop instead;
@@ -17,7 +17,8 @@
 
 namespace ivg {
 
-constexpr int RZ_W = 128, RZ_H = 32;
+constexpr int RZ_W = 128, RZ_H = 64;
+constexpr int RZ_RPS = RZ_H / 8;           // output rows per 32-thread row segment
 
 // Level-0 ingest: frames arrive from the host as ONE contiguous copy (row-pitched DMA of 1241-byte rows runs at a third
 // of the PCIe rate); this kernel lays them out in the row-pitched level-0 plane.  One aligned 32-bit store per thread,
@@ -92,12 +93,12 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, in
   }
   __syncthreads();
   {
-    const int g = tid & 31, seg = tid >> 5;                  // 32 groups of 4 columns x 8 row segments of 4 rows
+    const int g = tid & 31, seg = tid >> 5;                  // 32 groups of 4 columns x 8 row segments of RZ_RPS rows
     const int gx = x0 + 4 * g;
     if (gx < D.pitch && gx <= x1) {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int y = y0 + seg * 4 + rr;
+      for (int rr = 0; rr < RZ_RPS; ++rr) {
+        const int y = y0 + seg * RZ_RPS + rr;
         if (y > y1) break;
         const ResizeTap t = ty[y];
         const uint2 A = *reinterpret_cast<const uint2*>(sT + (t.s0 - sya) * RZ_W + 4 * g);
