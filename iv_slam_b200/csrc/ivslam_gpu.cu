@@ -30,7 +30,7 @@ using namespace ivg;
 
 namespace {
 
-constexpr size_t FAST_SMEM_BUDGET = 44 * 1024;   // k_fast_cells stages at most this much per CTA (taller cells are banded)
+constexpr size_t FAST_SMEM_BUDGET = 31 * 1024;   // k_fast_cells stages at most this much per CTA (taller cells are banded)
 
 thread_local std::string g_cuda_err;
 
@@ -276,20 +276,22 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.cellBase = (int)h->cellsPlain.size();
     L.btX = (L.w + BL_W - 1) / BL_W; L.btY = (L.h + BL_H - 1) / BL_H;
     L.btBase = btBase; btBase += L.btX * L.btY;
-    // k_fast_cells shared-memory geometry: 4 B per staged pixel (two rows packed) + 1 B per score
-    L.fSP = (int)align_up(L.cellW + 9, 4);
-    L.fSS = (int)align_up(L.cellW, 4) + 8;
+    // k_fast_cells shared-memory geometry: one 32-bit word per horizontal pixel pair (2 B per pixel) + 1 B per score
+    L.fSP = (int)align_up(L.cellW + 9, 4) / 2;
+    L.fSS = (int)align_up(L.cellW + 6, 4);
     L.fBW = (L.cellW + 31) / 32;
-    if (L.cellW > 512) return IVG_ERR_CAPACITY;               // pair list packs x in 9 bits
+    if (L.cellW > 512) return IVG_ERR_CAPACITY;               // pair list packs the pair index in 9 bits
     {
-      const int perRow = 4 * L.fSP + L.fSS + 4 * L.fBW + 128 * ((L.fBW + 3) / 4) + 64;   // pixels + scores + bitmap + pair list (2 B per pair)
-      int bh = (int)(FAST_SMEM_BUDGET / perRow) - 8;
-      bh = std::min(std::max(bh, 4), 200);
-      L.fBH = std::min(bh, L.cellH);
-      const size_t ssBytes = align_up((size_t)L.fSS * (L.fBH + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (L.fBH + 2), 16);
-      L.fSeg = ((((L.fBH + 3) / 2) * ((L.fBW + 3) / 4) + FC_WARPS - 1) / FC_WARPS) * 128;   // per-warp pair list: items of up to 4 chunks x 32 lanes
-      const size_t listBytes = (size_t)2 * FC_WARPS * L.fSeg;
-      fastSmem = std::max(fastSmem, (size_t)4 * L.fSP * (L.fBH + 8) + ssBytes + bitBytes + listBytes);
+      const int chunks = ((L.cellW + 2) / 2 + 31) / 32;                                   // 32-pair chunks per row
+      auto bytes = [&](int bh, int* seg) {
+        const size_t ssBytes = align_up((size_t)L.fSS * (bh + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (bh + 2), 16);
+        *seg = ((bh + 2 + FC_WARPS - 1) / FC_WARPS) * 32 * chunks;                        // per-warp pair list: its rows, every pair
+        return align_up((size_t)4 * L.fSP * (bh + 8), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * FC_WARPS * *seg;
+      };
+      int bh = std::min(L.cellH, 120);                                                    // list entries hold the row in 7 bits
+      while (bh > 4 && bytes(bh, &L.fSeg) > FAST_SMEM_BUDGET) --bh;                       // taller cells are processed in bands
+      L.fBH = bh;
+      fastSmem = std::max(fastSmem, bytes(bh, &L.fSeg));
     }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
     const int chW = std::max(hYlast - 6, 0);                    // weighted: every row searches this many rows

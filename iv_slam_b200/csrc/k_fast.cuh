@@ -14,12 +14,13 @@
 //
 // Work shape: integer stencil on u8 pixels, no tensor-core shape anywhere.  Phases of one CTA (per band of cell rows):
 //   A stage    the cell's pixels (+3 px ring margin) are loaded with aligned 32-bit words and stored in shared memory
-//              as one 32-bit word per pixel holding TWO vertically adjacent pixels in 16-bit lanes
-//              (pix(x,y) | pix(x,y+1)<<16): every ring sample of a vertical pixel pair is then ONE conflict-free LDS.32
-//              that is already in the packed 16x2 layout of the DPX min/max instructions (VIMNMX[3].U16x2);
+//              as one 32-bit word per HORIZONTAL pixel pair, one pixel per 16-bit lane (pix(2w,y) | pix(2w+1,y)<<16):
+//              2 B of shared memory per pixel, and a word is already in the packed 16x2 layout of the DPX min/max
+//              instructions (VIMNMX[3].U16x2).  Ring samples at even dx are one conflict-free LDS.32, samples at odd
+//              dx are two LDS.32 and one PRMT;
 //   B reject   every pixel pair takes the opposing-pair test on 4 of the 8 ring diameters (any 9-arc contains one end
-//              of every diameter): 8 packed differences, 14 packed min/max.  ~4 % of pixels survive; their pair
-//              positions are appended to a list (order irrelevant);
+//              of every diameter): 11 LDS, 2 PRMT, 14 packed min/max.  ~7 % of the pairs survive; their positions are
+//              appended to the warp's list (order irrelevant);
 //   C score    dense loop over the list: 16 packed differences and the exact score network — min over each 9-arc as a
 //              min3 of three 3-minima, max over arcs, both polarities: 88 packed min/max for two pixels;
 //   D nms      dense loop over the list: strict 3x3 maximum inside the cell's score map; survivors set a bit;
@@ -60,6 +61,7 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
 
 constexpr int FC_THREADS = 160; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
 constexpr int FC_WARPS = FC_THREADS / 32;
+constexpr int FC_SLACK = 512;   // bytes after the staged pixels that B's masked lanes may read
 
 __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char fsm[];
@@ -74,52 +76,43 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cw = c.cw, ch = c.ch;
   const int SP = L.fSP, SS = L.fSS, BH = L.fBH, BW = L.fBW, pitch = L.pitch, segCap = L.fSeg;
-  // shared layout: packed pixel pairs | score bytes | survivor bitmap | pair list
+  // shared layout: packed pixel pairs (+ slack for the masked overreads of B) | score bytes | survivor bitmap | pair list
   uint32_t* sp = reinterpret_cast<uint32_t*>(fsm);
   const int ssBytes = (SS * (BH + 4) + 15) & ~15, bitBytes = (4 * BW * (BH + 2) + 15) & ~15;
-  uint8_t* ss = fsm + (size_t)4 * SP * (BH + 8);
+  uint8_t* ss = fsm + (((size_t)4 * SP * (BH + 8) + 15) & ~(size_t)15) + FC_SLACK;
   uint32_t* sbit = reinterpret_cast<uint32_t*>(ss + ssBytes);
   uint16_t* slist = reinterpret_cast<uint16_t*>(ss + ssBytes + bitBytes);
   const int xa = (c.x0 - 3) & ~3;          // global x of staged column 0 (word aligned)
-  const int cOff = c.x0 - xa;              // staged column of detect column 0
+  const int cOff = c.x0 - xa;              // staged column of detect column 0 (3..6)
+  const int lead = cOff & 1;               // 1: pair 0 starts one column left of the detect range
+  const int w0 = cOff >> 1;                // staged word of pair 0
+  const int nPr = (lead + cw + 1) >> 1;    // pixel pairs per row
+  const int nChunks = (nPr + 31) >> 5;
   const int scoreTh = fs.scoreTh;
   const unsigned kK2 = ((unsigned)scoreTh + 1u) * 0x00010001u;      // th + 1 in both 16-bit lanes
-  const int nChunks = (cw + 31) >> 5;
+  const unsigned kB = 0x80008000u - kK2;
 
   int running = 0, nIni = 0, nMin = 0, par = 0;
 
   for (int r0 = 0; r0 < ch; r0 += BH) {
     const int r1 = min(r0 + BH, ch);
     const int s0 = max(r0 - 1, 0), s1 = min(r1 + 1, ch);
-    const int nPairs = (s1 - s0 + 1) >> 1;
-    const int nWR = 2 * nPairs + 5;
+    const int nSR = s1 - s0;               // score rows of this band (1 overlap row per side for the NMS)
+    const int nR = nSR + 6;
 
-    // ---- A: stage. word row q holds pixel rows (q, q+1) counted from global row gy0
+    // ---- A: stage pixel rows gy0 .. gy0+nR-1; warp = row, lane = group of 4 pixels
     const int gy0 = c.y0 + s0 - 3;
     {
-      // warp = row segment, lane = column group: rows are walked top to bottom with the previous row carried in a
-      // register, so every global word is loaded once (plus one seed row per segment); no integer division anywhere
-      const int nG4 = SP >> 2;
-      const int segRows = (nWR + FC_WARPS - 1) / FC_WARPS;
-      const int q0 = warp * segRows, q1 = min(q0 + segRows, nWR);
-      if (q0 < q1) {
+      const int nG4 = SP >> 1;
+      for (int q = warp; q < nR; q += FC_WARPS) {
+        const uint8_t* prow = pix + (size_t)(gy0 + q) * pitch + xa;
+        uint32_t* dst = sp + q * SP;
         for (int g = lane; g < nG4; g += 32) {
-          const bool in = xa + 4 * g < pitch;
-          const uint8_t* prow = pix + (size_t)(gy0 + q0) * pitch + xa + 4 * g;
-          uint32_t a = in ? __ldg(reinterpret_cast<const uint32_t*>(prow)) : 0u;
-          uint32_t* dst = sp + q0 * SP + 4 * g;
-          for (int q = q0; q < q1; ++q) {
-            prow += pitch;
-            const uint32_t b = in ? __ldg(reinterpret_cast<const uint32_t*>(prow)) : 0u;
-            uint4 o;
-            o.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu;
-            o.y = __byte_perm(a, b, 0x0501) & 0x00FF00FFu;
-            o.z = __byte_perm(a, b, 0x0602) & 0x00FF00FFu;
-            o.w = __byte_perm(a, b, 0x0703) & 0x00FF00FFu;
-            *reinterpret_cast<uint4*>(dst) = o;
-            dst += SP;
-            a = b;
-          }
+          const uint32_t a = xa + 4 * g < pitch ? __ldg(reinterpret_cast<const uint32_t*>(prow + 4 * g)) : 0u;
+          uint2 o;
+          o.x = __byte_perm(a, 0u, 0x4140);
+          o.y = __byte_perm(a, 0u, 0x4342);
+          *reinterpret_cast<uint2*>(dst + 2 * g) = o;
         }
       }
     }
@@ -133,39 +126,36 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     uint16_t* wlist = slist + warp * segCap;        // this warp's private segment: no atomics, no ordering needed
     int wn = 0;
     {
-      // work item = (row pair p, segment of up to 4 chunks of 32 columns); the inner loop only bumps pointers
-      const int nSegs = (nChunks + 3) >> 2;
       const unsigned ltmask = (1u << lane) - 1u;
-      int p = 0, sg = warp;                          // item index it = p * nSegs + sg, advanced by FC_WARPS without dividing
-      while (sg >= nSegs) { sg -= nSegs; ++p; }
-      for (; p < nPairs; sg += FC_WARPS) {
-        while (sg >= nSegs) { sg -= nSegs; ++p; }
-        if (p >= nPairs) break;
-        int x = sg * 128 + lane;
-        const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
-        const uint32_t* cp3 = ctr + 3 * SP;  const uint32_t* cm3 = ctr - 3 * SP;     // ring rows +-3, +-2 (row 0 via ctr)
+      for (int y = warp; y < nSR; y += FC_WARPS) {
+        const uint32_t* ctr = sp + (y + 3) * SP + w0 + lane;
+        const uint32_t* cp3 = ctr + 3 * SP;  const uint32_t* cm3 = ctr - 3 * SP;
         const uint32_t* cp2 = ctr + 2 * SP;  const uint32_t* cm2 = ctr - 2 * SP;
-        const int xend = min(cw, sg * 128 + 128);
-        const int ebase = p * 512;
-#pragma unroll 1
-        for (; x - lane < xend; x += 32, ctr += 32, cp3 += 32, cm3 += 32, cp2 += 32, cm2 += 32) {
-          bool pass = false;
-          if (x < xend) {
-            // directly on the packed pixels (no differences needed for a reject test):
-            //   bright possible  <=>  min over diameters of max(ring_k, ring_k+8) >= centre + th + 1
-            //   dark possible    <=>  max over diameters of min(ring_k, ring_k+8) <= centre - th - 1
-            const unsigned C = ctr[0];
-            const unsigned r0 = cp3[0], r8 = cm3[0], r2 = cp2[2], r10 = cm2[-2], r4 = ctr[3], r12 = ctr[-3], r6 = cm2[2], r14 = cp2[-2];
-            const unsigned a = __vminu2(vmin3(__vmaxu2(r0, r8), __vmaxu2(r2, r10), __vmaxu2(r4, r12)), __vmaxu2(r6, r14));
-            const unsigned b = __vmaxu2(vmax3(__vminu2(r0, r8), __vminu2(r2, r10), __vminu2(r4, r12)), __vminu2(r6, r14));
-            // bit 15 of each 16-bit lane: (a >= C + K) and (C >= b + K), K = th + 1; no borrow can cross lanes
-            const unsigned X = a + (0x80008000u - kK2) - C;
-            const unsigned Y = C + (0x80008000u - kK2) - b;
-            pass = ((X | Y) & 0x80008000u) != 0u;
+        const int ebase = y * 512 + lane;
+        for (int cb = 0; cb < nChunks; cb += 4, ctr += 128, cp3 += 128, cm3 += 128, cp2 += 128, cm2 += 128) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (cb + k < nChunks) {
+              const int o = 32 * k;
+              // directly on the packed pixels (no differences needed for a reject test):
+              //   bright possible  <=>  min over diameters of max(ring_k, ring_k+8) >= centre + th + 1
+              //   dark possible    <=>  max over diameters of min(ring_k, ring_k+8) <= centre - th - 1
+              // lanes past the end of the row read staged neighbours / slack and are masked below
+              const unsigned C = ctr[o];
+              const unsigned r0_ = cp3[o], r8 = cm3[o], r2 = cp2[o + 1], r10 = cm2[o - 1], r6 = cm2[o + 1], r14 = cp2[o - 1];
+              const unsigned r4 = __byte_perm(ctr[o + 1], ctr[o + 2], 0x5432), r12 = __byte_perm(ctr[o - 2], ctr[o - 1], 0x5432);
+              const unsigned a = __vminu2(vmin3(__vmaxu2(r0_, r8), __vmaxu2(r2, r10), __vmaxu2(r4, r12)), __vmaxu2(r6, r14));
+              const unsigned b = __vmaxu2(vmax3(__vminu2(r0_, r8), __vminu2(r2, r10), __vminu2(r4, r12)), __vminu2(r6, r14));
+              // bit 15 of each 16-bit lane: (a >= C + K) and (C >= b + K), K = th + 1; no borrow can cross lanes
+              const unsigned X = a + kB - C;
+              const unsigned Y = C + kB - b;
+              const int pi = (cb + k) * 32 + lane;
+              const bool pass = (((X | Y) & 0x80008000u) != 0u) & (pi < nPr);
+              const unsigned m = __ballot_sync(0xffffffffu, pass);
+              if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + (cb + k) * 32);   // nPr <= 512, rows < 128: host
+              wn += __popc(m);
+            }
           }
-          const unsigned m = __ballot_sync(0xffffffffu, pass);
-          if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + x);   // cw <= 512 enforced by the host
-          wn += __popc(m);
         }
       }
     }
@@ -173,35 +163,51 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
 
     // ---- C: exact score of the surviving pairs
     for (int j = lane; j < wn; j += 32) {
-      const int e = wlist[j], p = e >> 9, x = e & 511;
-      const uint32_t* ctr = sp + (2 * p + 3) * SP + cOff + x;
+      const int e = wlist[j], y = e >> 9, pi = e & 511;
+      const uint32_t* ctr = sp + (y + 3) * SP + w0 + pi;
       const unsigned C = ctr[0] + 0x01000100u;
       unsigned D[16];
-      D[0] = C - ctr[3 * SP];          D[1] = C - ctr[3 * SP + 1];      D[2] = C - ctr[2 * SP + 2];      D[3] = C - ctr[SP + 3];
-      D[4] = C - ctr[3];               D[5] = C - ctr[-SP + 3];         D[6] = C - ctr[-2 * SP + 2];     D[7] = C - ctr[-3 * SP + 1];
-      D[8] = C - ctr[-3 * SP];         D[9] = C - ctr[-3 * SP - 1];     D[10] = C - ctr[-2 * SP - 2];    D[11] = C - ctr[-SP - 3];
-      D[12] = C - ctr[-3];             D[13] = C - ctr[SP - 3];         D[14] = C - ctr[2 * SP - 2];     D[15] = C - ctr[3 * SP - 1];
+      {
+        const uint32_t* r = ctr + 3 * SP;
+        const unsigned a = r[-1], b = r[0], d = r[1];
+        D[15] = C - __byte_perm(a, b, 0x5432);  D[0] = C - b;  D[1] = C - __byte_perm(b, d, 0x5432);
+      }
+      {
+        const uint32_t* r = ctr - 3 * SP;
+        const unsigned a = r[-1], b = r[0], d = r[1];
+        D[9] = C - __byte_perm(a, b, 0x5432);   D[8] = C - b;  D[7] = C - __byte_perm(b, d, 0x5432);
+      }
+      D[14] = C - ctr[2 * SP - 1];   D[2] = C - ctr[2 * SP + 1];
+      D[10] = C - ctr[-2 * SP - 1];  D[6] = C - ctr[-2 * SP + 1];
+      {
+        const uint32_t* r = ctr + SP;
+        D[13] = C - __byte_perm(r[-2], r[-1], 0x5432);  D[3] = C - __byte_perm(r[1], r[2], 0x5432);
+      }
+      D[12] = C - __byte_perm(ctr[-2], ctr[-1], 0x5432);  D[4] = C - __byte_perm(ctr[1], ctr[2], 0x5432);
+      {
+        const uint32_t* r = ctr - SP;
+        D[11] = C - __byte_perm(r[-2], r[-1], 0x5432);  D[5] = C - __byte_perm(r[1], r[2], 0x5432);
+      }
       const unsigned T = fast_score_pair(D);
+      const int x = 2 * pi - lead;                            // detect column of the low lane
       int sA = (int)(T & 0xFFFFu) - 257, sB = (int)(T >> 16) - 257;
-      sA = sA >= scoreTh ? sA : 0;
-      sB = sB >= scoreTh ? sB : 0;
-      uint8_t* o = ss + (2 * p + 1) * SS + 4 + x;
-      o[0] = (uint8_t)sA;
-      if (s0 + 2 * p + 1 < s1) o[SS] = (uint8_t)sB;
+      sA = (sA >= scoreTh && x >= 0) ? sA : 0;
+      sB = (sB >= scoreTh && x + 1 < cw) ? sB : 0;
+      *reinterpret_cast<uint16_t*>(ss + (y + 1) * SS + 2 + 2 * pi) = (uint16_t)(sA | (sB << 8));
     }
     __syncthreads();
 
     // ---- D: 3x3 strict maximum inside the cell (zero border = "no score outside the cell")
     for (int j = lane; j < 2 * wn; j += 32) {
-      const int e = wlist[j >> 1], p = e >> 9, x = e & 511, half = j & 1;
-      const int srow = 2 * p + half;                       // score row relative to s0
-      const int row = s0 + srow;                           // detect row of the cell
+      const int e = wlist[j >> 1], y = e >> 9, pi = e & 511, half = j & 1;
+      const int row = s0 + y;                              // detect row of the cell
       if (row < r0 || row >= r1) continue;                 // overlap rows belong to the neighbouring band
-      const uint8_t* s = ss + (srow + 1) * SS + 4 + x;
+      const uint8_t* s = ss + (y + 1) * SS + 2 + 2 * pi + half;
       const int v = s[0];
       if (v == 0) continue;
       const int m = max(max(max((int)s[-1], (int)s[1]), max((int)s[-SS - 1], (int)s[-SS])),
                         max(max((int)s[-SS + 1], (int)s[SS - 1]), max((int)s[SS], (int)s[SS + 1])));
+      const int x = 2 * pi - lead + half;
       if (v > m) atomicOr(&sbit[(row - r0) * BW + (x >> 5)], 1u << (x & 31));
     }
     __syncthreads();
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       par ^= 1;
       if (bits) {
         const int row = i / BW, xb = (i - row * BW) * 32;
-        const uint8_t* srow = ss + (r0 + row - s0 + 1) * SS + 4 + xb;
+        const uint8_t* srow = ss + (r0 + row - s0 + 1) * SS + 2 + lead + xb;
         while (bits) {
           const int k = __ffs(bits) - 1;
           bits &= bits - 1;
