@@ -20,7 +20,8 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 assert KP_DTYPE.itemsize == 28
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libivslam_gpu.so")
+# IVSLAM_GPU_LIB: developer override to A/B a differently-built libivslam_gpu.so (same C ABI); never a fallback
+LIB_PATH = os.environ.get("IVSLAM_GPU_LIB") or os.path.join(_HERE, "lib", "libivslam_gpu.so")
 
 IVG_OK = 0
 KERNEL_NAMES = ("k_resize_level", "k_fast_cells", "k_gauss7", "k_level_select", "k_orient_describe", "k_stereo_match",

@@ -30,7 +30,10 @@ using namespace ivg;
 
 namespace {
 
-constexpr size_t FAST_SMEM_BUDGET = 31 * 1024;   // k_fast_cells stages at most this much per CTA (taller cells are banded)
+#ifndef IVG_FAST_SMEM_KB
+#define IVG_FAST_SMEM_KB 31
+#endif
+constexpr size_t FAST_SMEM_BUDGET = IVG_FAST_SMEM_KB * 1024;   // k_fast_cells stages at most this much per CTA (taller cells are banded)
 
 thread_local std::string g_cuda_err;
 

@@ -59,7 +59,10 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
   return __vmaxu2(best, 0x02000200u - worst);
 }
 
-constexpr int FC_THREADS = 160; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
+#ifndef IVG_FC_THREADS
+#define IVG_FC_THREADS 160
+#endif
+constexpr int FC_THREADS = IVG_FC_THREADS; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
 constexpr int FC_WARPS = FC_THREADS / 32;
 constexpr int FC_SLACK = 512;   // bytes after the staged pixels that B's masked lanes may read
 
@@ -103,16 +106,21 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     // ---- A: stage pixel rows gy0 .. gy0+nR-1; warp = row, lane = group of 4 pixels
     const int gy0 = c.y0 + s0 - 3;
     {
+      // per-thread source/destination pointers are set up once and bumped per row; two column groups per pass
       const int nG4 = SP >> 1;
-      for (int q = warp; q < nR; q += FC_WARPS) {
-        const uint8_t* prow = pix + (size_t)(gy0 + q) * pitch + xa;
-        uint32_t* dst = sp + q * SP;
-        for (int g = lane; g < nG4; g += 32) {
-          const uint32_t a = xa + 4 * g < pitch ? __ldg(reinterpret_cast<const uint32_t*>(prow + 4 * g)) : 0u;
-          uint2 o;
-          o.x = __byte_perm(a, 0u, 0x4140);
-          o.y = __byte_perm(a, 0u, 0x4342);
-          *reinterpret_cast<uint2*>(dst + 2 * g) = o;
+      const int rstep = FC_WARPS * pitch, dstep = FC_WARPS * SP;
+      for (int gb = 0; gb < nG4; gb += 64) {
+        const int g0 = gb + lane, g1 = g0 + 32;
+        const bool st0 = g0 < nG4, st1 = g1 < nG4;
+        const bool ld0 = st0 && xa + 4 * g0 < pitch, ld1 = st1 && xa + 4 * g1 < pitch;
+        const uint8_t* src = pix + (size_t)(gy0 + warp) * pitch + xa + 4 * g0;
+        uint32_t* dst = sp + warp * SP + 2 * g0;
+#pragma unroll 2
+        for (int q = warp; q < nR; q += FC_WARPS, src += rstep, dst += dstep) {
+          const uint32_t a0 = ld0 ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
+          const uint32_t a1 = ld1 ? __ldg(reinterpret_cast<const uint32_t*>(src + 128)) : 0u;
+          if (st0) *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(a0, 0u, 0x4140), __byte_perm(a0, 0u, 0x4342));
+          if (st1) *reinterpret_cast<uint2*>(dst + 64) = make_uint2(__byte_perm(a1, 0u, 0x4140), __byte_perm(a1, 0u, 0x4342));
         }
       }
     }
@@ -212,12 +220,13 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     }
     __syncthreads();
 
-    // ---- E: emit in row-major order
-    const int nWords = (r1 - r0) * BW;
-    for (int base = 0; base < nWords; base += FC_THREADS) {
-      const int i = base + tid;
-      unsigned bits = i < nWords ? sbit[i] : 0u;
-      const int cnt = __popc(bits);
+    // ---- E: emit in row-major order; thread t owns the bitmap words [t*per, (t+1)*per): one scan per band
+    {
+      const int nWords = (r1 - r0) * BW;
+      const int per = (nWords + FC_THREADS - 1) / FC_THREADS;
+      const int wbeg = tid * per, wend = min(wbeg + per, nWords);
+      int cnt = 0;
+      for (int i = wbeg; i < wend; ++i) cnt += __popc(sbit[i]);
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -231,16 +240,21 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       for (int w = 0; w < FC_WARPS; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
       running += tot;
       par ^= 1;
-      if (bits) {
-        const int row = i / BW, xb = (i - row * BW) * 32;
-        const uint8_t* srow = ss + (r0 + row - s0 + 1) * SS + 2 + lead + xb;
-        while (bits) {
-          const int k = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const int s = srow[k];
-          list[off++] = pack_xys(c.x0 + xb + k, c.y0 + r0 + row, s);
-          nIni += s >= fs.iniTh;
-          nMin += s >= fs.minTh;
+      if (cnt) {
+        int row = wbeg / BW, xw = wbeg - row * BW;
+        for (int i = wbeg; i < wend; ++i) {
+          unsigned bits = sbit[i];
+          const int xb = xw * 32;
+          const uint8_t* srow = ss + (r0 + row - s0 + 1) * SS + 2 + lead + xb;
+          while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int s = srow[k];
+            list[off++] = pack_xys(c.x0 + xb + k, c.y0 + r0 + row, s);
+            nIni += s >= fs.iniTh;
+            nMin += s >= fs.minTh;
+          }
+          if (++xw == BW) { xw = 0; ++row; }
         }
       }
     }
