@@ -880,7 +880,7 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
   A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
   A.bandMargin = (int)std::ceil(2.0f * left->scale[left->nlevels - 1]) + 2;
   { ProfScope ps(left, IVG_K_STEREO); k_stereo_index<<<nPairs, 256, (A.nRows + 1) * sizeof(int), left->stream>>>(A); }
-  { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + 7) / 8, nPairs), 256, 0, left->stream>>>(fs, A); }
+  { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A); }
   { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());
   return IVG_OK;

@@ -3,7 +3,8 @@
 //   k_stereo_index   one CTA per stereo pair: counting sort of the right keypoints by image row (int)y into a CSR
 //       table (the reference's vRowIndices build, :768-785, stores every keypoint in all rows of its band; here each
 //       keypoint is stored once and the band test is applied by the searcher).
-//   k_stereo_match   one warp per left keypoint.
+//   k_stereo_match   one warp per 8 left keypoints: the candidate search runs one keypoint at a time on all 32 lanes,
+//     the SAD refinement of the 8 keypoints runs together, 4 lanes per keypoint.
 //     * candidate search (:787-841): the reference scans the list of row (int)vL, i.e. the right keypoints whose
 //       band [floor(y-r), ceil(y+r)], r = 2*scale[octave], covers that row.  Candidate membership is a pure predicate
 //       of (left kp, right kp), and the winner is the minimum of (Hamming distance, iR) because the list is in
@@ -77,114 +78,208 @@ __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_stereo_match(FrameSet fs, StereoArgs A) {
+constexpr int SM_KP = 8;                   // left keypoints per warp
+constexpr int SM_ROWB = 48;                // staged bytes per patch row: right strip at [0,21), left patch at [32,43)
+constexpr int SM_SLOT = 11 * SM_ROWB;      // one keypoint's 11 rows
+constexpr int SM_WARPS = 8;
+
+// [b,0,b,0] with b = byte k of w: one 8-bit value in both 16-bit lanes
+__device__ __forceinline__ unsigned dup16(unsigned w, int k) { return __byte_perm(w, 0u, 0x4040u | (unsigned)k | ((unsigned)k << 8)); }
+
+__global__ void __launch_bounds__(32 * SM_WARPS) k_stereo_match(FrameSet fs, StereoArgs A) {
+  __shared__ __align__(16) uint8_t patch[SM_WARPS][SM_KP][SM_SLOT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t pair = blockIdx.y;
-  const int iL = blockIdx.x * 8 + warp;
+  const int iL0 = (blockIdx.x * SM_WARPS + warp) * SM_KP;
   const int N = A.nL[pair], Nr = A.nR[pair];
-  if (iL >= A.cap) return;
-  const size_t o = pair * A.cap + iL;
-  if (iL >= N) {   // slots past the keypoint count read as "no match"
-    if (lane == 0) { A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
-    return;
-  }
-  const float* kl = reinterpret_cast<const float*>(A.kpL + o * 28);
-  const float uL = kl[0], vL = kl[1];
-  const int levelL = reinterpret_cast<const int*>(kl)[5];
-  const int row = (int)vL;
-  const float minU = __fsub_rn(uL, A.maxD), maxU = uL;   // minD = 0
-  unsigned best = ((unsigned)TH_HIGH << 16) | 0xFFFFu;
-  uint32_t dl[8];
+  if (iL0 >= A.cap) return;
   {
-    const uint32_t* d = reinterpret_cast<const uint32_t*>(A.descL + o * 32);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) dl[k] = __ldg(d + k);
+    uint4* z = reinterpret_cast<uint4*>(&patch[warp][0][0]);   // pad bytes must read as zero
+    for (int i = lane; i < SM_KP * SM_SLOT / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
   }
-  if (row >= 0 && row < A.nRows && !(maxU < 0) && Nr > 0) {
-    const uint8_t* dr0 = A.descR + pair * A.cap * 32;
-    const int* rs = A.rowStart + pair * (size_t)(A.nRows + 1);
-    const uint4* srt = A.sorted + pair * A.cap;
-    const int jb = __ldg(rs + max(row - A.bandMargin, 0)), je = __ldg(rs + min(row + A.bandMargin + 1, A.nRows));
-    for (int j = jb + lane; j < je; j += 32) {
-      const uint4 e = __ldg(srt + j);
-      const int octR = (int)e.z;
-      if (octR < levelL - 1 || octR > levelL + 1) continue;
-      const float uR = __uint_as_float(e.x), kpY = __uint_as_float(e.y);
-      if (!(uR >= minU && uR <= maxU)) continue;
-      const float r = __fmul_rn(2.0f, fs.lv[octR].scale);
-      const int maxr = (int)ceilf(__fadd_rn(kpY, r)), minr = (int)floorf(__fsub_rn(kpY, r));
-      if (row < minr || row > maxr) continue;
-      const uint4* d = reinterpret_cast<const uint4*>(dr0 + (size_t)e.w * 32);
-      const uint4 da = __ldg(d), db = __ldg(d + 1);
-      const int dist = __popc(dl[0] ^ da.x) + __popc(dl[1] ^ da.y) + __popc(dl[2] ^ da.z) + __popc(dl[3] ^ da.w) +
-                       __popc(dl[4] ^ db.x) + __popc(dl[5] ^ db.y) + __popc(dl[6] ^ db.z) + __popc(dl[7] ^ db.w);
-      if (dist < TH_HIGH) best = min(best, ((unsigned)dist << 16) | e.w);
+  __syncwarp();
+
+  // ---- phase 1: one left keypoint at a time, the whole warp searches its candidates and stages the SAD patches.
+  // Lanes 4k..4k+3 remember keypoint k's parameters for phase 2.
+  bool gDo = false;
+  float gUL = 0.f, gUR0 = 0.f, gScale = 1.f;
+  const uint8_t* dr0 = A.descR + pair * A.cap * 32;
+  const int* rs = A.rowStart + pair * (size_t)(A.nRows + 1);
+  const uint4* srt = A.sorted + pair * A.cap;
+  const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+
+  for (int k = 0; k < SM_KP; ++k) {
+    const int iL = iL0 + k;
+    if (iL >= A.cap) break;
+    const size_t o = pair * A.cap + iL;
+    if (iL >= N) {   // slots past the keypoint count read as "no match"
+      if (lane == 0) { A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
+      continue;
+    }
+    const float* kl = reinterpret_cast<const float*>(A.kpL + o * 28);
+    const float uL = kl[0], vL = kl[1];
+    const int levelL = reinterpret_cast<const int*>(kl)[5];
+    const int row = (int)vL;
+    const float minU = __fsub_rn(uL, A.maxD), maxU = uL;   // minD = 0
+    unsigned best = ((unsigned)TH_HIGH << 16) | 0xFFFFu;
+    if (row >= 0 && row < A.nRows && !(maxU < 0) && Nr > 0) {
+      uint32_t dl[8];
+      {
+        const uint4* d = reinterpret_cast<const uint4*>(A.descL + o * 32);
+        const uint4 a = __ldg(d), b = __ldg(d + 1);
+        dl[0] = a.x; dl[1] = a.y; dl[2] = a.z; dl[3] = a.w; dl[4] = b.x; dl[5] = b.y; dl[6] = b.z; dl[7] = b.w;
+      }
+      const int jb = __ldg(rs + max(row - A.bandMargin, 0)), je = __ldg(rs + min(row + A.bandMargin + 1, A.nRows));
+      for (int j = jb + lane; j < je; j += 32) {
+        const uint4 e = __ldg(srt + j);
+        const int octR = (int)e.z;
+        if (octR < levelL - 1 || octR > levelL + 1) continue;
+        const float uR = __uint_as_float(e.x), kpY = __uint_as_float(e.y);
+        if (!(uR >= minU && uR <= maxU)) continue;
+        const float r = __fmul_rn(2.0f, fs.lv[octR].scale);
+        const int maxr = (int)ceilf(__fadd_rn(kpY, r)), minr = (int)floorf(__fsub_rn(kpY, r));
+        if (row < minr || row > maxr) continue;
+        const uint4* d = reinterpret_cast<const uint4*>(dr0 + (size_t)e.w * 32);
+        const uint4 da = __ldg(d), db = __ldg(d + 1);
+        const int dist = __popc(dl[0] ^ da.x) + __popc(dl[1] ^ da.y) + __popc(dl[2] ^ da.z) + __popc(dl[3] ^ da.w) +
+                         __popc(dl[4] ^ db.x) + __popc(dl[5] ^ db.y) + __popc(dl[6] ^ db.z) + __popc(dl[7] ^ db.w);
+        if (dist < TH_HIGH) best = min(best, ((unsigned)dist << 16) | e.w);
+      }
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, s));
+    const int bestDist = best >> 16;
+    const int bestIdxR = best & 0xFFFF;
+    if (A.bestDist && lane == 0) A.bestDist[o] = bestDist;
+    bool doSad = false;
+    float scaleduR0 = 0.f, lscale = 1.f;
+    if (bestDist < thOrbDist) {
+      const float uR0 = reinterpret_cast<const float*>(A.kpR + (pair * A.cap + bestIdxR) * 28)[0];
+      const LevelDev& L = fs.lv[levelL];
+      const float sf = L.invScale;
+      lscale = L.scale;
+      const float scaleduL = roundf(__fmul_rn(uL, sf)), scaledvL = roundf(__fmul_rn(vL, sf));
+      scaleduR0 = roundf(__fmul_rn(uR0, sf));
+      const int w = 5, Ls = 5;
+      const int cy = (int)scaledvL, cxL = (int)scaleduL, cxR = (int)scaleduR0;
+      const float iniu = scaleduR0 + (float)(Ls - w), endu = scaleduR0 + (float)(Ls + w + 1);
+      bool ok = !(iniu < 0 || endu >= (float)L.w);
+      ok = ok && !(cy - w < 0 || cy + w + 1 > L.h || cxL - w < 0 || cxL + w + 1 > L.w || cxR - Ls - w < 0);
+      if (ok) {
+        // lanes 0..20: right strip columns cxR-10..cxR+10; lanes 21..31: left patch columns cxL-5..cxL+5
+        const uint8_t* src = lane < 21 ? A.pyrR + pair * A.planeBytes + L.planeOff + (size_t)(cy - w) * L.pitch + (cxR - Ls - w + lane)
+                                       : A.pyrL + pair * A.planeBytes + L.planeOff + (size_t)(cy - w) * L.pitch + (cxL - w + lane - 21);
+        uint8_t* dst = &patch[warp][k][lane < 21 ? lane : lane + 11];
+        uint8_t v[11];
+#pragma unroll
+        for (int dy = 0; dy < 11; ++dy) v[dy] = __ldg(src + (size_t)dy * L.pitch);
+#pragma unroll
+        for (int dy = 0; dy < 11; ++dy) dst[dy * SM_ROWB] = v[dy];
+        doSad = true;
+      }
+    }
+    if (!doSad && lane == 0) { A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
+    if ((lane >> 2) == k) { gDo = doSad; gUL = uL; gUR0 = scaleduR0; gScale = lscale; }
+  }
+  if (!__any_sync(0xffffffffu, gDo)) return;
+  __syncwarp();
+
+  // ---- phase 2: SAD refinement, 4 lanes per keypoint (lane j takes patch rows j, j+4, j+8), two pixels per
+  // instruction in packed 16-bit lanes.  With e = L - cL, d' = (R - cR_s) - e for shift s:
+  //   |d'| = 2*max(d',0) - d',  max(d',0) = max(R + (cL - L), cR_s) - cR_s   (one VIADDMNMX.S16x2 per pixel pair)
+  // and the sum of d' over the window comes from window sums of R and the sum of L.  All integers: exact.
+  // The 11th pixel of a row is paired with a dummy whose max() is exactly cR_s.
+  const int j = lane & 3, kk = lane >> 2;
+  const uint8_t* S = &patch[warp][kk][0];
+  unsigned cR2[11];
+  int cL;
+  {
+    const uint4 r5 = *reinterpret_cast<const uint4*>(S + 5 * SM_ROWB);           // right bytes 0..15 of the centre row
+    cR2[0] = dup16(r5.y, 1); cR2[1] = dup16(r5.y, 2); cR2[2] = dup16(r5.y, 3);     // cR_s = right byte 5 + s
+    cR2[3] = dup16(r5.z, 0); cR2[4] = dup16(r5.z, 1); cR2[5] = dup16(r5.z, 2); cR2[6] = dup16(r5.z, 3);
+    cR2[7] = dup16(r5.w, 0); cR2[8] = dup16(r5.w, 1); cR2[9] = dup16(r5.w, 2); cR2[10] = dup16(r5.w, 3);
+    cL = S[5 * SM_ROWB + 32 + 5];
+  }
+  const unsigned cL2p1 = (unsigned)(cL + 1) * 0x00010001u;
+  unsigned acc[11], accW[11], sumL2 = 0;
+#pragma unroll
+  for (int s = 0; s < 11; ++s) { acc[s] = 0; accW[s] = 0; }
+#pragma unroll 1
+  for (int dy = j; dy < 11; dy += 4) {
+    const uint8_t* rp = S + dy * SM_ROWB;
+    const uint4 ra = *reinterpret_cast<const uint4*>(rp);
+    const uint2 rb = *reinterpret_cast<const uint2*>(rp + 16);
+    const uint4 la = *reinterpret_cast<const uint4*>(rp + 32);
+    const unsigned w[6] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y};
+    unsigned R2[21];                       // R2[c] = right bytes (c, c+1) in 16-bit lanes
+#pragma unroll
+    for (int c = 0; c < 21; ++c) {
+      const int i = c >> 2, m = c & 3;
+      R2[c] = m == 0 ? __byte_perm(w[i], 0u, 0x4140) : m == 1 ? __byte_perm(w[i], 0u, 0x4241) : m == 2 ? __byte_perm(w[i], 0u, 0x4342)
+                     : __byte_perm(__funnelshift_r(w[i], w[i + 1 < 6 ? i + 1 : 5], 24), 0u, 0x4140);
+    }
+    unsigned L2[6] = {__byte_perm(la.x, 0u, 0x4140), __byte_perm(la.x, 0u, 0x4342), __byte_perm(la.y, 0u, 0x4140),
+                      __byte_perm(la.y, 0u, 0x4342), __byte_perm(la.z, 0u, 0x4140), __byte_perm(la.z, 0u, 0x4342)};   // byte 11 is a zero pad
+    sumL2 += L2[0] + L2[1] + L2[2] + L2[3] + L2[4] + L2[5];
+    unsigned ne2[6];                       // (cL - L) per 16-bit lane
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ne2[i] = __vadd2(cL2p1, ~L2[i]);
+    ne2[5] = (ne2[5] & 0xFFFFu) | 0xC0000000u;                    // dummy partner: -16384 => its max() is cR_s
+    // window sums of the right strip: V = 5 full pairs (sliding, stride 2), plus the single 11th pixel
+    unsigned V0 = R2[0] + R2[2] + R2[4] + R2[6] + R2[8], V1 = R2[1] + R2[3] + R2[5] + R2[7] + R2[9];
+#pragma unroll
+    for (int s = 0; s < 11; ++s) {
+      unsigned& V = (s & 1) ? V1 : V0;
+      accW[s] += V + (R2[s + 10] & 0xFFFFu);
+      if (s + 2 < 11) V = V - R2[s] + R2[s + 10];
+      const unsigned m0 = __viaddmax_s16x2(R2[s], ne2[0], cR2[s]), m1 = __viaddmax_s16x2(R2[s + 2], ne2[1], cR2[s]);
+      const unsigned m2 = __viaddmax_s16x2(R2[s + 4], ne2[2], cR2[s]), m3 = __viaddmax_s16x2(R2[s + 6], ne2[3], cR2[s]);
+      const unsigned m4 = __viaddmax_s16x2(R2[s + 8], ne2[4], cR2[s]), m5 = __viaddmax_s16x2(R2[s + 10], ne2[5], cR2[s]);
+      acc[s] += m0 + m1 + m2 + m3 + m4 + m5;                       // every lane value is in [0, 510]: no carry between lanes
     }
   }
+  int T[11];
 #pragma unroll
-  for (int s = 16; s; s >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, s));
-  const int bestDist = best >> 16;
-  const int bestIdxR = best & 0xFFFF;
-  float outU = -1.f, outD = -1.f;
-  int outSad = -1;
-  if (A.bestDist && lane == 0) A.bestDist[o] = bestDist;
-  const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
-  if (bestDist < thOrbDist) {
-    const float uR0 = reinterpret_cast<const float*>(A.kpR + (pair * A.cap + bestIdxR) * 28)[0];
-    const LevelDev& L = fs.lv[levelL];
-    const float sf = L.invScale;
-    const float scaleduL = roundf(__fmul_rn(uL, sf)), scaledvL = roundf(__fmul_rn(vL, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
-    const int w = 5, Ls = 5;
-    const int cy = (int)scaledvL, cxL = (int)scaleduL, cxR = (int)scaleduR0;
-    const float iniu = scaleduR0 + (float)(Ls - w), endu = scaleduR0 + (float)(Ls + w + 1);
-    bool ok = !(iniu < 0 || endu >= (float)L.w);
-    ok = ok && !(cy - w < 0 || cy + w + 1 > L.h || cxL - w < 0 || cxL + w + 1 > L.w || cxR - Ls - w < 0);
-    if (ok) {
-      const uint8_t* PL = A.pyrL + pair * A.planeBytes + L.planeOff;
-      const uint8_t* PR = A.pyrR + pair * A.planeBytes + L.planeOff;
-      const int cL = __ldg(PL + (size_t)cy * L.pitch + cxL);
-      int cR[11];
+  for (int s = 0; s < 11; ++s) T[s] = 2 * (int)((acc[s] & 0xFFFFu) + (acc[s] >> 16)) - (int)((accW[s] & 0xFFFFu) + (accW[s] >> 16));
+  int SL = (int)((sumL2 & 0xFFFFu) + (sumL2 >> 16));
 #pragma unroll
-      for (int s = 0; s < 11; ++s) cR[s] = __ldg(PR + (size_t)cy * L.pitch + cxR + s - Ls);
-      int acc[11];
+  for (int q = 1; q <= 2; q <<= 1) {
 #pragma unroll
-      for (int s = 0; s < 11; ++s) acc[s] = 0;
-      for (int p = lane; p < 121; p += 32) {
-        const int dy = p / 11 - w, dx = p % 11 - w;
-        const int lv = (int)__ldg(PL + (size_t)(cy + dy) * L.pitch + cxL + dx) - cL;
-        const uint8_t* rr = PR + (size_t)(cy + dy) * L.pitch + cxR + dx - Ls;
+    for (int s = 0; s < 11; ++s) T[s] += __shfl_xor_sync(0xffffffffu, T[s], q);
+    SL += __shfl_xor_sync(0xffffffffu, SL, q);
+  }
+  if (!gDo || j != 0) return;
+  {
+    const int Ls = 5;
+    const size_t o = pair * A.cap + iL0 + kk;
+    float outU = -1.f, outD = -1.f;
+    int outSad = -1;
+    int sadv[11];
 #pragma unroll
-        for (int s = 0; s < 11; ++s) acc[s] += abs(lv - ((int)__ldg(rr + s) - cR[s]));
-      }
+    for (int s = 0; s < 11; ++s) sadv[s] = T[s] - 143 * (int)(cR2[s] & 0xFFFFu) - 121 * cL + SL;
+    int bestSad = 0x7fffffff, bestinc = 0;
 #pragma unroll
-      for (int s = 0; s < 11; ++s) {
+    for (int s = 0; s < 11; ++s)
+      if (sadv[s] < bestSad) { bestSad = sadv[s]; bestinc = s - Ls; }
+    if (!(bestinc == -Ls || bestinc == Ls)) {
+      float d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-        for (int q = 16; q; q >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], q);
-      }
-      int bestSad = 0x7fffffff, bestinc = 0;
-#pragma unroll
-      for (int s = 0; s < 11; ++s)
-        if (acc[s] < bestSad) { bestSad = acc[s]; bestinc = s - Ls; }
-      if (!(bestinc == -Ls || bestinc == Ls)) {
-        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-        for (int s = 1; s < 10; ++s)
-          if (s - Ls == bestinc) { d1 = (float)acc[s - 1]; d2 = (float)acc[s]; d3 = (float)acc[s + 1]; }
-        const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
-        if (!(deltaR < -1.f || deltaR > 1.f)) {
-          float bestuR = __fmul_rn(L.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
-          float disparity = __fsub_rn(uL, bestuR);
-          if (disparity >= 0.f && disparity < A.maxD) {
-            if (disparity <= 0.f) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
-            outD = __fdiv_rn(A.mbf, disparity);
-            outU = bestuR;
-            outSad = bestSad;
-          }
+      for (int s = 1; s < 10; ++s)
+        if (s - Ls == bestinc) { d1 = (float)sadv[s - 1]; d2 = (float)sadv[s]; d3 = (float)sadv[s + 1]; }
+      const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+      if (!(deltaR < -1.f || deltaR > 1.f)) {
+        float bestuR = __fmul_rn(gScale, __fadd_rn(__fadd_rn(gUR0, (float)bestinc), deltaR));
+        float disparity = __fsub_rn(gUL, bestuR);
+        if (disparity >= 0.f && disparity < A.maxD) {
+          if (disparity <= 0.f) { disparity = 0.01f; bestuR = (float)((double)gUL - 0.01); }
+          outD = __fdiv_rn(A.mbf, disparity);
+          outU = bestuR;
+          outSad = bestSad;
         }
       }
     }
+    A.uRight[o] = outU; A.depth[o] = outD; A.sad[o] = outSad;
   }
-  if (lane == 0) { A.uRight[o] = outU; A.depth[o] = outD; A.sad[o] = outSad; }
 }
 
 __global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {

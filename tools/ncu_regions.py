@@ -21,8 +21,9 @@ for w in want:
         print('%-90s %s %s' % (w, data[i], units[i]))
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kern, '--launch-skip', skip, '--launch-count', '1'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+hdr = rows[1]
 ia, isrc, isamp = hdr.index('Instructions Executed'), hdr.index('Source'), hdr.index('# Samples')
+data = [r for r in rows[2:] if len(r) > max(ia, isrc, isamp) and r[ia].isdigit()]
 tot = sum(int(r[ia]) for r in data); tots = sum(int(r[isamp]) for r in data)
 print('total warp instr', tot, 'samples', tots)
 i = 0
