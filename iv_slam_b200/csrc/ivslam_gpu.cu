@@ -522,6 +522,7 @@ int init_device_constants(int device) {
   CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_octree_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OctShared)));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_stereo_index, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return IVG_OK;
 }
 
@@ -876,10 +877,12 @@ int ivg_get_level_keypoints(ivg_extractor* h, int index, int level, float* x, fl
 static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& A, int nPairs) {
   const FrameSet fs = active_fs(left);
   int rc;
-  if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (A.nRows + 1)))) return rc;
+  A.nLevels = left->nlevels;
+  const size_t nBins = (size_t)A.nRows * A.nLevels;
+  if ((nBins + 1) * sizeof(int) > 200 * 1024) return IVG_ERR_CAPACITY;
+  if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (nBins + 1)))) return rc;
   A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
-  A.bandMargin = (int)std::ceil(2.0f * left->scale[left->nlevels - 1]) + 2;
-  { ProfScope ps(left, IVG_K_STEREO); k_stereo_index<<<nPairs, 256, (A.nRows + 1) * sizeof(int), left->stream>>>(A); }
+  { ProfScope ps(left, IVG_K_STEREO); k_stereo_index<<<nPairs, 256, (nBins + 1) * sizeof(int), left->stream>>>(A); }
   { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A); }
   { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());

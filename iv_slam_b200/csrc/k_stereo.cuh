@@ -1,8 +1,9 @@
 // k_stereo.cuh — K7-K10: Frame::ComputeStereoMatches (introspective_ORB_SLAM/src/Frame.cc:758-932).
 //
-//   k_stereo_index   one CTA per stereo pair: counting sort of the right keypoints by image row (int)y into a CSR
-//       table (the reference's vRowIndices build, :768-785, stores every keypoint in all rows of its band; here each
-//       keypoint is stored once and the band test is applied by the searcher).
+//   k_stereo_index   one CTA per stereo pair: counting sort of the right keypoints by (octave, image row (int)y) into a
+//       CSR table (the reference's vRowIndices build, :768-785, stores every keypoint in all rows of its band; here
+//       each keypoint is stored once and the band test is applied by the searcher, which only visits the three octaves
+//       levelL-1..levelL+1 the reference accepts (:815) and, per octave, the rows its band radius can reach).
 //   k_stereo_match   one warp per 8 left keypoints: the candidate search runs one keypoint at a time on all 32 lanes,
 //     the SAD refinement of the 8 keypoints runs together, 4 lanes per keypoint.
 //     * candidate search (:787-841): the reference scans the list of row (int)vL, i.e. the right keypoints whose
@@ -35,27 +36,33 @@ struct StereoArgs {
   float* uRight; float* depth; int* sad;                     // [nPairs][cap]
   int* bestDist;                                             // optional debug [nPairs][cap] or null
   uint4* sorted;                                             // [nPairs][cap] right keypoints bucketed by row: (x bits, y bits, octave, iR)
-  int* rowStart;                                             // [nPairs][nRows + 1]
-  int bandMargin;                                            // rows to scan either side of (int)vL: ceil(2*scale[last]) + 2
+  int* rowStart;                                             // [nPairs][nLevels * nRows + 1], bin = octave * nRows + row
+  int nLevels;
 };
 
 constexpr int TH_HIGH = 100, TH_LOW = 50;
 
+__device__ __forceinline__ int stereo_bin(float y, int oct, int nRows, int nLevels) {
+  if (oct < 0 || oct >= nLevels) return -1;      // the reference would index mvScaleFactors out of range; such keypoints never match here
+  return oct * nRows + min(max((int)y, 0), nRows - 1);
+}
+
 __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
-  extern __shared__ int ssh[];               // nRows + 1 counters, then the scatter cursors in place
+  extern __shared__ int ssh[];               // nBins + 1 counters, then the scatter cursors in place
   __shared__ int wsum[8];
   const size_t pair = blockIdx.x;
-  const int Nr = A.nR[pair], nRows = A.nRows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Nr = A.nR[pair], nRows = A.nRows, nBins = A.nRows * A.nLevels, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t* kr0 = A.kpR + pair * A.cap * 28;
-  for (int i = tid; i <= nRows; i += 256) ssh[i] = 0;
+  for (int i = tid; i <= nBins; i += 256) ssh[i] = 0;
   __syncthreads();
   for (int iR = tid; iR < Nr; iR += 256) {
-    const float y = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28)[1];
-    atomicAdd(&ssh[min(max((int)y, 0), nRows - 1)], 1);
+    const float* kr = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28);
+    const int bin = stereo_bin(kr[1], reinterpret_cast<const int*>(kr)[5], nRows, A.nLevels);
+    if (bin >= 0) atomicAdd(&ssh[bin], 1);
   }
   __syncthreads();
-  // exclusive scan over nRows+1 entries: each thread owns a contiguous chunk
-  const int per = (nRows + 1 + 255) / 256, b0 = tid * per, b1 = min(b0 + per, nRows + 1);
+  // exclusive scan over nBins+1 entries: each thread owns a contiguous chunk
+  const int per = (nBins + 1 + 255) / 256, b0 = min(tid * per, nBins + 1), b1 = min(b0 + per, nBins + 1);
   int local = 0;
   for (int i = b0; i < b1; ++i) local += ssh[i];
   int incl = local;
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
   __syncthreads();
   int base = incl - local;
   for (int w = 0; w < warp; ++w) base += wsum[w];
-  int* rs = A.rowStart + pair * (size_t)(nRows + 1);
+  int* rs = A.rowStart + pair * (size_t)(nBins + 1);
   for (int i = b0; i < b1; ++i) { const int c = ssh[i]; ssh[i] = base; rs[i] = base; base += c; }
   __syncthreads();
   uint4* out = A.sorted + pair * A.cap;
@@ -73,7 +80,9 @@ __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
     const float* kr = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28);
     const float x = kr[0], y = kr[1];
     const int oct = reinterpret_cast<const int*>(kr)[5];
-    const int pos = atomicAdd(&ssh[min(max((int)y, 0), nRows - 1)], 1);   // order inside a row is irrelevant (arg-min is order-free)
+    const int bin = stereo_bin(y, oct, nRows, A.nLevels);
+    if (bin < 0) continue;
+    const int pos = atomicAdd(&ssh[bin], 1);   // order inside a bin is irrelevant (arg-min is order-free)
     out[pos] = make_uint4(__float_as_uint(x), __float_as_uint(y), (unsigned)oct, (unsigned)iR);
   }
 }
@@ -86,7 +95,10 @@ constexpr int SM_WARPS = 8;
 // [b,0,b,0] with b = byte k of w: one 8-bit value in both 16-bit lanes
 __device__ __forceinline__ unsigned dup16(unsigned w, int k) { return __byte_perm(w, 0u, 0x4040u | (unsigned)k | ((unsigned)k << 8)); }
 
-__global__ void __launch_bounds__(32 * SM_WARPS) k_stereo_match(FrameSet fs, StereoArgs A) {
+#ifndef IVG_SM_MINB
+#define IVG_SM_MINB 5
+#endif
+__global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(FrameSet fs, StereoArgs A) {
   __shared__ __align__(16) uint8_t patch[SM_WARPS][SM_KP][SM_SLOT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t pair = blockIdx.y;
@@ -100,13 +112,35 @@ __global__ void __launch_bounds__(32 * SM_WARPS) k_stereo_match(FrameSet fs, Ste
   __syncwarp();
 
   // ---- phase 1: one left keypoint at a time, the whole warp searches its candidates and stages the SAD patches.
+  // Up front lane k (< 8) loads keypoint k's record and lanes 3k..3k+2 look up its three CSR segments (octaves
+  // levelL-1, levelL, levelL+1), so the per-keypoint dependent chain is: candidates -> descriptors -> patch rows.
   // Lanes 4k..4k+3 remember keypoint k's parameters for phase 2.
   bool gDo = false;
   float gUL = 0.f, gUR0 = 0.f, gScale = 1.f;
   const uint8_t* dr0 = A.descR + pair * A.cap * 32;
-  const int* rs = A.rowStart + pair * (size_t)(A.nRows + 1);
+  const int nBins = A.nRows * A.nLevels;
+  const int* rs = A.rowStart + pair * (size_t)(nBins + 1);
   const uint4* srt = A.sorted + pair * A.cap;
   const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+  float myU = 0.f, myV = 0.f;
+  int myLev = -1;
+  if (lane < SM_KP && iL0 + lane < N) {
+    const float* kl = reinterpret_cast<const float*>(A.kpL + (pair * A.cap + iL0 + lane) * 28);
+    myU = kl[0]; myV = kl[1]; myLev = reinterpret_cast<const int*>(kl)[5];
+  }
+  int segB = 0, segN = 0;
+  {
+    const int k3 = lane / 3, t = lane - 3 * k3, src = min(k3, SM_KP - 1);
+    const float u = __shfl_sync(0xffffffffu, myU, src), v = __shfl_sync(0xffffffffu, myV, src);
+    const int lev = __shfl_sync(0xffffffffu, myLev, src);
+    const int oct = lev - 1 + t, row = (int)v;
+    if (k3 < SM_KP && lev >= 0 && lev < A.nLevels && oct >= 0 && oct < A.nLevels && row >= 0 && row < A.nRows && !(u < 0) && Nr > 0) {
+      // rows whose bucket can hold a keypoint with row in [floor(y - r), ceil(y + r)], r = 2*scale[oct]
+      const int m = (int)ceilf(__fmul_rn(2.0f, fs.lv[oct].scale)) + 1;
+      segB = __ldg(rs + oct * A.nRows + max(row - m, 0));
+      segN = __ldg(rs + oct * A.nRows + min(row + m + 1, A.nRows)) - segB;
+    }
+  }
 
   for (int k = 0; k < SM_KP; ++k) {
     const int iL = iL0 + k;
@@ -116,45 +150,48 @@ __global__ void __launch_bounds__(32 * SM_WARPS) k_stereo_match(FrameSet fs, Ste
       if (lane == 0) { A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
       continue;
     }
-    const float* kl = reinterpret_cast<const float*>(A.kpL + o * 28);
-    const float uL = kl[0], vL = kl[1];
-    const int levelL = reinterpret_cast<const int*>(kl)[5];
+    const float uL = __shfl_sync(0xffffffffu, myU, k), vL = __shfl_sync(0xffffffffu, myV, k);
+    const int levelL = __shfl_sync(0xffffffffu, myLev, k);
+    const int b0 = __shfl_sync(0xffffffffu, segB, 3 * k), b1 = __shfl_sync(0xffffffffu, segB, 3 * k + 1), b2 = __shfl_sync(0xffffffffu, segB, 3 * k + 2);
+    const int n0 = __shfl_sync(0xffffffffu, segN, 3 * k), n1 = __shfl_sync(0xffffffffu, segN, 3 * k + 1), n2 = __shfl_sync(0xffffffffu, segN, 3 * k + 2);
     const int row = (int)vL;
     const float minU = __fsub_rn(uL, A.maxD), maxU = uL;   // minD = 0
     unsigned best = ((unsigned)TH_HIGH << 16) | 0xFFFFu;
-    if (row >= 0 && row < A.nRows && !(maxU < 0) && Nr > 0) {
+    float bestU = 0.f;
+    const int total = n0 + n1 + n2;
+    if (total > 0) {
       uint32_t dl[8];
       {
         const uint4* d = reinterpret_cast<const uint4*>(A.descL + o * 32);
         const uint4 a = __ldg(d), b = __ldg(d + 1);
         dl[0] = a.x; dl[1] = a.y; dl[2] = a.z; dl[3] = a.w; dl[4] = b.x; dl[5] = b.y; dl[6] = b.z; dl[7] = b.w;
       }
-      const int jb = __ldg(rs + max(row - A.bandMargin, 0)), je = __ldg(rs + min(row + A.bandMargin + 1, A.nRows));
-      for (int j = jb + lane; j < je; j += 32) {
-        const uint4 e = __ldg(srt + j);
-        const int octR = (int)e.z;
-        if (octR < levelL - 1 || octR > levelL + 1) continue;
+      for (int j = lane; j < total; j += 32) {
+        const int idx = j < n0 ? b0 + j : (j < n0 + n1 ? b1 + (j - n0) : b2 + (j - n0 - n1));
+        const uint4 e = __ldg(srt + idx);
         const float uR = __uint_as_float(e.x), kpY = __uint_as_float(e.y);
         if (!(uR >= minU && uR <= maxU)) continue;
-        const float r = __fmul_rn(2.0f, fs.lv[octR].scale);
+        const float r = __fmul_rn(2.0f, fs.lv[(int)e.z].scale);
         const int maxr = (int)ceilf(__fadd_rn(kpY, r)), minr = (int)floorf(__fsub_rn(kpY, r));
         if (row < minr || row > maxr) continue;
         const uint4* d = reinterpret_cast<const uint4*>(dr0 + (size_t)e.w * 32);
         const uint4 da = __ldg(d), db = __ldg(d + 1);
         const int dist = __popc(dl[0] ^ da.x) + __popc(dl[1] ^ da.y) + __popc(dl[2] ^ da.z) + __popc(dl[3] ^ da.w) +
                          __popc(dl[4] ^ db.x) + __popc(dl[5] ^ db.y) + __popc(dl[6] ^ db.z) + __popc(dl[7] ^ db.w);
-        if (dist < TH_HIGH) best = min(best, ((unsigned)dist << 16) | e.w);
+        const unsigned cand = ((unsigned)dist << 16) | e.w;
+        if (dist < TH_HIGH && cand < best) { best = cand; bestU = uR; }
       }
     }
+    const unsigned mine = best;
 #pragma unroll
     for (int s = 16; s; s >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, s));
     const int bestDist = best >> 16;
-    const int bestIdxR = best & 0xFFFF;
     if (A.bestDist && lane == 0) A.bestDist[o] = bestDist;
     bool doSad = false;
     float scaleduR0 = 0.f, lscale = 1.f;
     if (bestDist < thOrbDist) {
-      const float uR0 = reinterpret_cast<const float*>(A.kpR + (pair * A.cap + bestIdxR) * 28)[0];
+      // x of the winning right keypoint: held by the lane that found it (iR is unique, so is the winner)
+      const float uR0 = __shfl_sync(0xffffffffu, bestU, __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1);
       const LevelDev& L = fs.lv[levelL];
       const float sf = L.invScale;
       lscale = L.scale;
