@@ -283,7 +283,6 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.fSP = (int)align_up(L.cellW + 9, 4) / 2;
     L.fSS = (int)align_up(L.cellW + 6, 4);
     L.fBW = (L.cellW + 31) / 32;
-    if (L.cellW > 512) return IVG_ERR_CAPACITY;               // pair list packs the pair index in 9 bits
     {
       const int chunks = ((L.cellW + 2) / 2 + 31) / 32;                                   // 32-pair chunks per row
       auto bytes = [&](int bh, int* seg) {
@@ -291,7 +290,10 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
         *seg = ((bh + 2 + FC_WARPS - 1) / FC_WARPS) * 32 * chunks;                        // per-warp pair list: its rows, every pair
         return align_up((size_t)4 * L.fSP * (bh + 8), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * FC_WARPS * *seg;
       };
-      int bh = std::min(L.cellH, 120);                                                    // list entries hold the row in 7 bits
+      L.fShift = 1;
+      while ((1 << L.fShift) < 32 * chunks) ++L.fShift;                                   // list entry = (score row << fShift) | pair index, 16 bits
+      if ((65536 >> L.fShift) < 8) return IVG_ERR_CAPACITY;                               // cells wider than ~16k px
+      int bh = std::min(L.cellH, (65536 >> L.fShift) - 2);
       while (bh > 4 && bytes(bh, &L.fSeg) > FAST_SMEM_BUDGET) --bh;                       // taller cells are processed in bands
       L.fBH = bh;
       fastSmem = std::max(fastSmem, bytes(bh, &L.fSeg));

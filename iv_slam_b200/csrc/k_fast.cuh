@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cw = c.cw, ch = c.ch;
   const int SP = L.fSP, SS = L.fSS, BH = L.fBH, BW = L.fBW, pitch = L.pitch, segCap = L.fSeg;
+  const int sh = L.fShift;                 // list entry = (score row << sh) | pair index
+  const int piMask = (1 << sh) - 1;
   // shared layout: packed pixel pairs (+ slack for the masked overreads of B) | score bytes | survivor bitmap | pair list
   uint32_t* sp = reinterpret_cast<uint32_t*>(fsm);
   const int ssBytes = (SS * (BH + 4) + 15) & ~15, bitBytes = (4 * BW * (BH + 2) + 15) & ~15;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
         const uint32_t* ctr = sp + (y + 3) * SP + w0 + lane;
         const uint32_t* cp3 = ctr + 3 * SP;  const uint32_t* cm3 = ctr - 3 * SP;
         const uint32_t* cp2 = ctr + 2 * SP;  const uint32_t* cm2 = ctr - 2 * SP;
-        const int ebase = y * 512 + lane;
+        const int ebase = (y << sh) + lane;
         for (int cb = 0; cb < nChunks; cb += 4, ctr += 128, cp3 += 128, cm3 += 128, cp2 += 128, cm2 += 128) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
               const int pi = (cb + k) * 32 + lane;
               const bool pass = (((X | Y) & 0x80008000u) != 0u) & (pi < nPr);
               const unsigned m = __ballot_sync(0xffffffffu, pass);
-              if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + (cb + k) * 32);   // nPr <= 512, rows < 128: host
+              if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + (cb + k) * 32);   // fits 16 bits: the host bounds the band height
               wn += __popc(m);
             }
           }
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
 
     // ---- C: exact score of the surviving pairs
     for (int j = lane; j < wn; j += 32) {
-      const int e = wlist[j], y = e >> 9, pi = e & 511;
+      const int e = wlist[j], y = e >> sh, pi = e & piMask;
       const uint32_t* ctr = sp + (y + 3) * SP + w0 + pi;
       const unsigned C = ctr[0] + 0x01000100u;
       unsigned D[16];
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
 
     // ---- D: 3x3 strict maximum inside the cell (zero border = "no score outside the cell")
     for (int j = lane; j < 2 * wn; j += 32) {
-      const int e = wlist[j >> 1], y = e >> 9, pi = e & 511, half = j & 1;
+      const int e = wlist[j >> 1], y = e >> sh, pi = e & piMask, half = j & 1;
       const int row = s0 + y;                              // detect row of the cell
       if (row < r0 || row >= r1) continue;                 // overlap rows belong to the neighbouring band
       const uint8_t* s = ss + (y + 1) * SS + 2 + 2 * pi + half;

@@ -144,6 +144,39 @@ def test_scale_factor_and_levels_variants(gpu_api, oracle):
         assert np.array_equal(g[0].features_per_level(), g[2].features_per_level())
 
 
+@pytest.mark.parametrize("seed", range(20))
+def test_random_geometries(gpu_api, oracle, seed):
+    """Seeded fuzz over image sizes / feature counts / thresholds / pyramid shapes: exercises every alignment of the
+    FAST cells (odd widths, both parities of the first staged column, banded tall cells), partially filled blur/resize
+    tiles and sparse stereo row tables.  Images the reference's grid cannot handle must be rejected by both sides."""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(160, 1400)), int(rng.integers(120, 900))
+    nf = int(rng.integers(150, 4000))
+    sf = float(rng.choice([1.2, 1.2, 1.1, 1.3, 1.5]))
+    nl = int(rng.integers(3, 9))
+    ini = int(rng.choice([12, 20, 20, 35]))
+    intro = bool(rng.integers(0, 2))
+    noise = seed % 4 == 3                      # a few pure-noise images: almost every pixel passes the FAST reject test
+    if noise:
+        left = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        right = np.roll(left, -7, axis=1)
+    else:
+        left, right = S.make_stereo_pair(w, h, 2000 + seed)
+    cost = S.make_cost_map(w, h, 3000 + seed) if intro else None
+    what = "fuzz%d %dx%d nf%d sf%.1f nl%d ini%d intro%d" % (seed, w, h, nf, sf, nl, ini, intro)
+    g = _pair(gpu_api, oracle, nf, ini, 7, intro, sf, nl)
+    try:
+        oracle_ok = True
+        g[2](left, cost)
+    except Exception:
+        oracle_ok = False
+    if not oracle_ok:
+        with pytest.raises(gpu_api.IvgError):
+            g[0](left, cost)
+        return
+    _check_frame(gpu_api, oracle, *g, left, right, cost, 120.0, 300.0, what)
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_cost_map_extremes(gpu_api, oracle):
     """cost 255 everywhere => every weight 0 => NaN budgets => one feature per cell; cost 0 => weights 1."""
