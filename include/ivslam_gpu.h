@@ -111,6 +111,18 @@ int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, 
  * The caller guarantees the producer has finished writing (or was enqueued on a stream this handle is ordered after). */
 int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, int width, int height, size_t stride,
                             size_t frame_bytes, const uint8_t* d_costs, size_t cost_stride, size_t cost_frame_bytes);
+/* SURVEY §8(f) N4 — the input prologue, fused into the upload.
+ * ivg_set_rectify_maps: the CV_32FC1 maps of cv::initUndistortRectifyMap (Examples/Stereo/stereo_kitti.cc:284-343,
+ *   stereo_euroc.cc:247-254), uploaded once; width x height is the rectified (output) size.  NULL maps clear them.
+ * ivg_upload_batch_raw: frames as they come from the camera / image file — 1, 3 or 4 interleaved 8-bit channels,
+ *   rgb_order != 0 when R comes first (Tracking::mbRGB).  On the device each frame goes through
+ *   cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) when maps are set (stereo_kitti.cc:463-464) and then through
+ *   cvtColor(.., CV_{BGR,RGB,BGRA,RGBA}2GRAY) (src/Tracking.cc:278-294) into pyramid level 0; the optional cost-maps
+ *   (1 channel, source size) are remapped with the same maps (stereo_kitti.cc:519-521).  Results are bit-identical to
+ *   OpenCV 4.13's fixed-point remap / cvtColor.  Then ivg_run_batch / ivg_download_batch as usual. */
+int ivg_set_rectify_maps(ivg_extractor* h, const float* mapx, const float* mapy, int width, int height, size_t stride_floats);
+int ivg_upload_batch_raw(ivg_extractor* h, int n, const uint8_t* frames, int src_width, int src_height, size_t stride, size_t frame_bytes,
+                         int channels, int rgb_order, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes);
 int ivg_run_batch(ivg_extractor* h);
 int ivg_download_batch(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
 int ivg_sync(ivg_extractor* h);

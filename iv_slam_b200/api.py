@@ -67,6 +67,8 @@ def lib():
         "ivg_extract_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz, vp, vp, C.c_int, vp]),
         "ivg_upload_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_upload_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
+        "ivg_set_rectify_maps": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, sz]),
+        "ivg_upload_batch_raw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, C.c_int, C.c_int, vp, sz, sz]),
         "ivg_run_batch": (C.c_int, [vp]),
         "ivg_download_batch": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "ivg_sync": (C.c_int, [vp]),
@@ -264,6 +266,38 @@ class ORBextractor:
         _ck(lib().ivg_upload_batch(self._h, n, _p(images), W, H, images.strides[1], images.strides[0], _p(masks),
                                    masks.strides[1] if masks is not None else 0, masks.strides[0] if masks is not None else 0), "ivg_upload_batch")
         self._batch = n
+
+    def set_rectify_maps(self, mapx, mapy):
+        """N4: the CV_32FC1 maps of cv::initUndistortRectifyMap (stereo_kitti.cc:284-343); None, None clears them."""
+        if mapx is None or mapy is None:
+            _ck(lib().ivg_set_rectify_maps(self._h, None, None, 0, 0, 0), "ivg_set_rectify_maps")
+            return
+        mapx, mapy = np.ascontiguousarray(mapx, np.float32), np.ascontiguousarray(mapy, np.float32)
+        assert mapx.ndim == 2 and mapx.shape == mapy.shape
+        _ck(lib().ivg_set_rectify_maps(self._h, _p(mapx), _p(mapy), mapx.shape[1], mapx.shape[0], mapx.shape[1]), "ivg_set_rectify_maps")
+
+    def upload_raw(self, frames, rgb=False, masks=None):
+        """N4: raw camera frames [n, H, W] or [n, H, W, 3|4] (u8): remap (if maps are set) + cvtColor on the device."""
+        assert frames.dtype == np.uint8 and frames.ndim in (3, 4)
+        n, H, W = frames.shape[:3]
+        cn = 1 if frames.ndim == 3 else frames.shape[3]
+        assert frames.strides[2] == cn and (cn == 1 or frames.strides[3] == 1)
+        if masks is not None:
+            assert masks.dtype == np.uint8 and masks.shape == (n, H, W) and masks.strides[2] == 1
+        _ck(lib().ivg_upload_batch_raw(self._h, n, _p(frames), W, H, frames.strides[1], frames.strides[0], cn, int(bool(rgb)), _p(masks),
+                                       masks.strides[1] if masks is not None else 0, masks.strides[0] if masks is not None else 0), "ivg_upload_batch_raw")
+        self._batch = n
+
+    def extract_raw(self, frame, rgb=False, mask=None):
+        """remap + cvtColor + operator() for one raw frame: (keypoints, descriptors)."""
+        self.upload_raw(frame[None], rgb, None if mask is None else mask[None])
+        self.run()
+        kps = np.zeros((1, self.cap), KP_DTYPE)
+        desc = np.zeros((1, self.cap, 32), np.uint8)
+        cnt = np.zeros(1, np.int32)
+        self.download(kps, desc, cnt)
+        self.sync()
+        return kps[0, :cnt[0]].copy(), desc[0, :cnt[0]].copy()
 
     def upload_device(self, n, width, height, d_images, d_masks=None):
         """Frames already in device memory (integer device pointers to n contiguous HxW u8 frames)."""

@@ -24,6 +24,7 @@
 #include "k_pyramid.cuh"
 #include "k_select.cuh"
 #include "k_octree.cuh"
+#include "k_prologue.cuh"
 #include "k_stereo.cuh"
 
 using namespace ivg;
@@ -106,6 +107,8 @@ struct ivg_extractor {
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
+  DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
+  int mapW = 0, mapH = 0;
   size_t fastSmem = 0, resizeSmem = 0, selSmem = 0;
   TmaMaps blurMaps{};                   // per level: 160 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
   TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
@@ -608,7 +611,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
-  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release();
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release();
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
@@ -758,6 +761,65 @@ int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, in
     if (cost_stride < (size_t)width) return IVG_ERR_INVALID;
     if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, d_costs, cost_stride, cost_frame_bytes, true))) return rc;
   }
+  return IVG_OK;
+}
+
+// ---------------------------------------------------------------------------------------- N4: input prologue
+int ivg_set_rectify_maps(ivg_extractor* h, const float* mapx, const float* mapy, int width, int height, size_t stride_floats) {
+  if (!h) return IVG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (!mapx || !mapy) { h->mapW = h->mapH = 0; return IVG_OK; }
+  if (width < 1 || height < 1 || stride_floats < (size_t)width) return IVG_ERR_INVALID;
+  int rc;
+  const size_t n = (size_t)width * height;
+  if ((rc = h->mapX.alloc(n)) || (rc = h->mapY.alloc(n))) return rc;
+  CK(cudaMemcpy2D(h->mapX.p, (size_t)width * 4, mapx, stride_floats * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2D(h->mapY.p, (size_t)width * 4, mapy, stride_floats * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+  h->mapW = width; h->mapH = height;
+  return IVG_OK;
+}
+
+static int prologue_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& stage, int n, const uint8_t* src, int sw, int sh, size_t stride,
+                       size_t frame_bytes, int cn, int rgb) {
+  const size_t rowB = (size_t)sw * cn, fb = rowB * sh;
+  int rc = stage.alloc((size_t)n * fb + 16);
+  if (rc) return rc;
+  CK(cudaStreamWaitEvent(h->copyIn, h->evIngest, 0));            // the previous prologue has consumed the staging buffer
+  if (stride == rowB && frame_bytes == fb) {
+    CK(cudaMemcpyAsync(stage.p, src, (size_t)n * fb, cudaMemcpyHostToDevice, h->copyIn));
+  } else {
+    for (int f = 0; f < n; ++f)
+      CK(cudaMemcpy2DAsync(stage.p + (size_t)f * fb, rowB, src + (size_t)f * frame_bytes, stride, rowB, sh, cudaMemcpyHostToDevice, h->copyIn));
+  }
+  CK(cudaEventRecord(h->evH2D, h->copyIn));
+  CK(cudaStreamWaitEvent(h->stream, h->evH2D, 0));
+  PrologueArgs P{};
+  P.src = stage.p; P.srcFrameBytes = fb; P.sw = sw; P.sh = sh; P.cn = cn; P.rgb = rgb;
+  P.mapx = h->mapW ? h->mapX.p : nullptr; P.mapy = h->mapW ? h->mapY.p : nullptr;
+  P.plane = plane; P.planeBytes = h->fs.planeBytes; P.W = h->W; P.H = h->H; P.pitch = h->fs.lv[0].pitch;
+  dim3 grid(((h->W + 3) / 4 + 255) / 256, h->H, n);
+  k_prologue<<<grid, 256, 0, h->stream>>>(P);
+  h->launches++;
+  CK(cudaGetLastError());
+  return IVG_OK;
+}
+
+int ivg_upload_batch_raw(ivg_extractor* h, int n, const uint8_t* frames, int src_width, int src_height, size_t stride, size_t frame_bytes,
+                         int channels, int rgb_order, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes) {
+  if (!h || !frames || n < 1 || src_width < 1 || src_height < 1) return IVG_ERR_INVALID;
+  if (channels != 1 && channels != 3 && channels != 4) return IVG_ERR_INVALID;
+  if (stride < (size_t)src_width * channels) return IVG_ERR_INVALID;
+  const int W = h->mapW ? h->mapW : src_width, H = h->mapW ? h->mapH : src_height;
+  int rc = ivg_set_batch(h, n, W, H, costs != nullptr);
+  if (rc) return rc;
+  if ((rc = honour_wait(h))) return rc;
+  if ((rc = prologue_in(h, h->pyr.p, h->stageImg, n, frames, src_width, src_height, stride, frame_bytes, channels, rgb_order != 0))) return rc;
+  if (h->haveCost) {   // the cost-map goes through the left camera's maps too (stereo_kitti.cc:519-521)
+    if (cost_stride < (size_t)src_width) return IVG_ERR_INVALID;
+    if ((rc = prologue_in(h, h->qual.p, h->stageCost, n, costs, src_width, src_height, cost_stride, cost_frame_bytes, 1, 0))) return rc;
+  }
+  CK(cudaEventRecord(h->evIngest, h->stream));
   return IVG_OK;
 }
 

@@ -879,6 +879,54 @@ int stereo_match(const Extractor& eL, const Extractor& eR, const KeyPoint* kL, i
 // =====================================================================================
 // C interface for ctypes (tests / bench only).
 // =====================================================================================
+// ------------------------------------------------------------------------------------------------------------------
+// N4 input prologue: cv::remap(INTER_LINEAR, CV_32FC1 maps, BORDER_CONSTANT 0) and cvtColor(*2GRAY).
+// Call sites in the reference: Examples/Stereo/stereo_kitti.cc:463-464,520, stereo_euroc.cc:369-370,397 (remap);
+// src/Tracking.cc:278-294 (cvtColor).  The arithmetic is OpenCV's (un-vendored; pinned to the 4.13.0 wheel of this image):
+//   imgproc/src/imgwarp.cpp  RemapInvoker (sx = cvRound(mapx*INTER_TAB_SIZE), INTER_BITS = 5), initInterTab2D
+//     (INTER_REMAP_COEF_BITS = 15; the (0,0) entry is saturate_cast<short>(32768) = 32767 and its correction lands on an
+//     element that is recomputed afterwards), remapBilinear<FixedPtCast<int, uchar, 15>> (taps outside the source = 0);
+//   imgproc/src/color_rgb.simd.hpp  RGB2Gray<uchar>: (B*3735 + G*19235 + R*9798 + 2^14) >> 15.
+// Checked bit-for-bit against cv2.remap / cv2.cvtColor in tests/test_oracle_vs_cv2.py.
+static inline int cv_round_x32(float m) {
+  const float v = m * 32.0f;
+  if (!(v > -2147483648.0f && v < 2147483648.0f)) return (int)0x80000000;   // cvtss2si "integer indefinite"
+  return (int)lrintf(v);                                                     // round half to even (default rounding mode)
+}
+
+static void prologue_frame(const uint8_t* src, int sw, int sh, size_t sstride, int cn, int rgb, const float* mapx, const float* mapy,
+                           size_t mstride, uint8_t* dst, int W, int H, size_t dstride) {
+  const int nc = cn == 1 ? 1 : 3;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      int v[3] = {0, 0, 0};
+      if (!mapx) {
+        for (int c = 0; c < nc; ++c) v[c] = src[(size_t)y * sstride + (size_t)x * cn + c];
+      } else {
+        const int sx = cv_round_x32(mapx[(size_t)y * mstride + x]), sy = cv_round_x32(mapy[(size_t)y * mstride + x]);
+        const int fx = sx & 31, fy = sy & 31;
+        const int ix = std::min(std::max(sx >> 5, -32768), 32767), iy = std::min(std::max(sy >> 5, -32768), 32767);
+        int w[4] = {(32 - fy) * (32 - fx) * 32, (32 - fy) * fx * 32, fy * (32 - fx) * 32, fy * fx * 32};
+        if (fx == 0 && fy == 0) w[0] = 32767;
+        for (int c = 0; c < nc; ++c) {
+          int acc = 0;
+          for (int t = 0; t < 4; ++t) {
+            const int tx = ix + (t & 1), ty = iy + (t >> 1);
+            const int pix = (tx >= 0 && tx < sw && ty >= 0 && ty < sh) ? src[(size_t)ty * sstride + (size_t)tx * cn + c] : 0;
+            acc += pix * w[t];
+          }
+          v[c] = (acc + (1 << 14)) >> 15;
+        }
+      }
+      int g = v[0];
+      if (cn != 1) {
+        const int b = rgb ? v[2] : v[0], r = rgb ? v[0] : v[2];
+        g = (b * 3735 + v[1] * 19235 + r * 9798 + (1 << 14)) >> 15;
+      }
+      dst[(size_t)y * dstride + x] = (uint8_t)g;
+    }
+}
+
 extern "C" {
 
 void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstride, uint8_t* dst, int dw, int dh, size_t dstride) {
@@ -1028,6 +1076,11 @@ int orc_stereo_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, i
   for (int t = 0; t < workers; ++t) th.emplace_back(work);
   for (auto& t : th) t.join();
   return err.load();
+}
+
+void orc_prologue(const uint8_t* src, int sw, int sh, size_t sstride, int cn, int rgb, const float* mapx, const float* mapy,
+                  size_t mstride, uint8_t* dst, int W, int H, size_t dstride) {
+  prologue_frame(src, sw, sh, sstride, cn, rgb, mapx, mapy, mstride, dst, W, H, dstride);
 }
 
 }  // extern "C"

@@ -98,6 +98,8 @@ def lib():
     L.orc_stage_seconds.restype = None
     L.orc_frame_post.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.orc_frame_post.restype = None
+    L.orc_prologue.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]
+    L.orc_prologue.restype = None
     L.orc_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]
     L.orc_stereo_match.restype = C.c_int
     L.orc_stereo_frame.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_float,
@@ -126,6 +128,22 @@ def resize_linear(src, dw, dh):
     dst = np.empty((dh, dw), np.uint8)
     lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
     return dst
+
+
+def prologue(frame, rgb=False, mapx=None, mapy=None):
+    """N4: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) with CV_32FC1 maps (optional) then cvtColor(*2GRAY) (if 3/4 channels)."""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    sh, sw = frame.shape[:2]
+    cn = 1 if frame.ndim == 2 else frame.shape[2]
+    if mapx is not None:
+        mapx, mapy = np.ascontiguousarray(mapx, np.float32), np.ascontiguousarray(mapy, np.float32)
+        H, W = mapx.shape
+    else:
+        H, W = sh, sw
+    out = np.zeros((H, W), np.uint8)
+    lib().orc_prologue(_p(frame), sw, sh, sw * cn, cn, int(bool(rgb)), _p(mapx) if mapx is not None else None,
+                       _p(mapy) if mapy is not None else None, W, _p(out), W, H, W)
+    return out
 
 
 def gauss7(src):

@@ -31,7 +31,38 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def euroc_like_maps(w, h, sw, sh):
+    """Undistort/rectify maps from cv2.initUndistortRectifyMap with an EuRoC-like calibration scaled to (sw, sh) -> (w, h)."""
+    import cv2
+    fx, fy = 0.61 * sw, 0.95 * sh
+    K = np.array([[fx, 0, 0.49 * sw], [0, fy, 0.52 * sh], [0, 0, 1]])
+    D = np.array([-0.2834, 0.0740, 0.00019, 1.76e-05])
+    a = 0.01
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    P = np.array([[0.45 * w, 0, 0.5 * w], [0, 0.7 * h, 0.5 * h], [0, 0, 1]])
+    return cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32F)
+
+
+def prologue_fixture():
+    """N4: raw BGR frame + cost-map -> cv2.remap(INTER_LINEAR) -> cv2.cvtColor(BGR2GRAY): inputs, maps and cv2's outputs."""
+    import cv2
+    rng = np.random.default_rng(21)
+    sw, sh, w, h = 200, 150, 176, 128
+    gray = S.make_image(sw, sh, 21)
+    frame = np.stack([gray, np.roll(gray, 3, 1), 255 - gray], -1) ^ rng.integers(0, 8, (sh, sw, 3), dtype=np.uint8)
+    cost = S.make_cost_map(sw, sh, 22)
+    m1, m2 = euroc_like_maps(w, h, sw, sh)
+    out = dict(frame=frame, cost=cost, mapx=m1, mapy=m2,
+               gray_bgr=cv2.cvtColor(cv2.remap(frame, m1, m2, cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY),
+               gray_rgb=cv2.cvtColor(cv2.remap(frame, m1, m2, cv2.INTER_LINEAR), cv2.COLOR_RGB2GRAY),
+               gray_noremap=cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY),
+               cost_remapped=cv2.remap(cost, m1, m2, cv2.INTER_LINEAR))
+    np.savez_compressed(os.path.join(HERE, "prologue_small.npz"), **out)
+    print("prologue_small", out["gray_bgr"].shape, "border zeros", int((out["gray_bgr"] == 0).sum()))
+
+
 def main():
+    prologue_fixture()
     for name, (w, h, seed, nf, ini, mn, intro, mbf, maxD) in CASES.items():
         left, right = S.make_stereo_pair(w, h, seed)
         cost = S.make_cost_map(w, h, seed + 1000) if intro else None

@@ -369,3 +369,53 @@ def test_n1_frame_postprocess(gpu_api, oracle, intro):
     g.extract_batch(L)
     qual, gs, gi = g.frame_postprocess(0.0, float(w), 0.0, float(h))
     assert (qual[0, :int(cnt[0])] == 1.0).all()
+
+
+# ----------------------------------------------------------------------------- N4: input prologue (remap + cvtColor fused into the upload)
+@pytest.mark.parametrize("cn,rgb,remap", [(1, False, True), (3, False, True), (3, True, True), (4, True, True), (3, False, False), (4, False, False)])
+def test_n4_prologue_matches_oracle(gpu_api, oracle, cn, rgb, remap):
+    rng = np.random.default_rng(60 + cn)
+    sw, sh, w, h = 700, 420, 640, 400
+    gray = S.make_image(sw, sh, 61)
+    frame = gray if cn == 1 else np.stack([gray, np.roll(gray, 2, 1), np.roll(gray, 3, 0), 255 - gray][:cn], -1).copy()
+    cost = S.make_cost_map(sw, sh, 62)
+    mx = my = None
+    if remap:
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        mx = (xx * 1.12 - 20 + 6 * np.sin(yy / 37)).astype(np.float32)        # leaves the source on the left and right
+        my = (yy * 1.1 - 15 + 5 * np.cos(xx / 53)).astype(np.float32)
+        mx[5, 7] = np.nan
+        my[9, 11] = 3e11
+    g = gpu_api.ORBextractor(900, 1.2, 8, 20, 7, True)
+    o = oracle.OracleExtractor(900, 1.2, 8, 20, 7, True)
+    g.set_rectify_maps(mx, my)
+    k, d = g.extract_raw(frame, rgb, cost)
+    want_img = oracle.prologue(frame, rgb, mx, my)
+    want_cost = oracle.prologue(cost, False, mx, my)
+    assert np.array_equal(g.level(0, 0), want_img), "prologue image"
+    assert np.array_equal(g.level(0, 2), want_cost), "prologue cost-map"
+    ko, do = o(want_img, want_cost)
+    assert_keypoints_equal(k, ko, "n4")
+    assert_descriptors_close(d, do, "n4")
+    # clearing the maps returns to plain ingest + cvtColor
+    g.set_rectify_maps(None, None)
+    g.extract_raw(frame, rgb, cost)
+    assert np.array_equal(g.level(0, 0), oracle.prologue(frame, rgb))
+
+
+def test_n4_prologue_golden_cv2(gpu_api):
+    z = load_golden("prologue_small")
+    g = gpu_api.ORBextractor(300, 1.2, 4, 20, 7, True)
+    g.set_rectify_maps(z["mapx"], z["mapy"])
+    frames = np.stack([z["frame"], z["frame"][::-1].copy()])          # a batch of two
+    g.upload_raw(frames, False, np.stack([z["cost"], z["cost"]]))
+    g.run(); g.sync()
+    assert np.array_equal(g.level(0, 0, 0), z["gray_bgr"])
+    assert np.array_equal(g.level(0, 2, 0), z["cost_remapped"])
+    g.upload_raw(frames[:1], True)
+    g.run(); g.sync()
+    assert np.array_equal(g.level(0, 0, 0), z["gray_rgb"])
+    g.set_rectify_maps(None, None)
+    g.upload_raw(frames[:1], False)
+    g.run(); g.sync()
+    assert np.array_equal(g.level(0, 0, 0), z["gray_noremap"])

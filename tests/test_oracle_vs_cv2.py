@@ -152,3 +152,40 @@ def test_oracle_edge_cases(oracle):
     k1, d1 = e(roi)
     k2, d2 = e(np.ascontiguousarray(roi))
     assert np.array_equal(d1, d2) and all(np.array_equal(k1[f], k2[f]) for f in k1.dtype.names)
+
+
+# ----------------------------------------------------------------------------- N4: input prologue (remap + cvtColor)
+@pytest.mark.parametrize("cn,rgb", [(1, False), (3, False), (3, True), (4, False), (4, True)])
+def test_prologue_matches_cv2(oracle, cn, rgb):
+    import cv2
+    rng = np.random.default_rng(40 + cn + int(rgb))
+    sh, sw, h, w = 131, 203, 97, 160
+    src = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+    if cn == 1:
+        src = src[..., 0]
+    code = {(3, False): cv2.COLOR_BGR2GRAY, (3, True): cv2.COLOR_RGB2GRAY, (4, False): cv2.COLOR_BGRA2GRAY, (4, True): cv2.COLOR_RGBA2GRAY}.get((cn, rgb))
+    gray = (lambda a: a) if code is None else (lambda a: cv2.cvtColor(a, code))
+    assert np.array_equal(oracle.prologue(src, rgb), gray(src)), "cvtColor only"
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    cases = {
+        "identity": (xx[:, :sw].copy(), yy[:sh].copy()),
+        "warp": ((xx * (sw / w) + rng.normal(0, 2.5, xx.shape)).astype(np.float32), (yy * (sh / h) + rng.normal(0, 2.5, xx.shape)).astype(np.float32)),
+        "border": ((xx * 1.6 - 30).astype(np.float32), (yy * 1.7 - 25).astype(np.float32)),          # large parts fall outside the source
+        "halves": ((xx * (sw / w) + 0.5).astype(np.float32), (yy * (sh / h) + 0.015625).astype(np.float32)),   # ties of cvRound(32*m)
+    }
+    bad = cases["warp"][0].copy()
+    bad[::7, ::5] = np.nan
+    bad[1::9, 2::6] = 1e12
+    bad[2::11, ::4] = -np.inf
+    cases["nonfinite"] = (bad, cases["warp"][1])
+    for name, (mx, my) in cases.items():
+        ref = gray(cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+        assert np.array_equal(oracle.prologue(src, rgb, mx, my), ref), name
+
+
+def test_prologue_golden_and_real_rectification_maps(oracle):
+    g = load_golden("prologue_small")
+    assert np.array_equal(oracle.prologue(g["frame"], False, g["mapx"], g["mapy"]), g["gray_bgr"])
+    assert np.array_equal(oracle.prologue(g["frame"], True, g["mapx"], g["mapy"]), g["gray_rgb"])
+    assert np.array_equal(oracle.prologue(g["frame"], False), g["gray_noremap"])
+    assert np.array_equal(oracle.prologue(g["cost"], False, g["mapx"], g["mapy"]), g["cost_remapped"])
