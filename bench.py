@@ -269,6 +269,7 @@ def main():
         peak, peak_kind = measured_peak()
         alg, P = algorithmic_bytes(W, H)
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        prof = {k: v for k, v in prof.items() if v[1]}      # kernels that did not launch in this workload (e.g. the N4 prologue)
         shares = {k: v[0] / tot_ms for k, v in prof.items()}
         dom = max(prof, key=lambda k: prof[k][0])
         units = B      # images (extractor kernels: one launch per eye) or pairs (stereo kernels) per launch

@@ -799,8 +799,7 @@ static int prologue_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& stage,
   P.mapx = h->mapW ? h->mapX.p : nullptr; P.mapy = h->mapW ? h->mapY.p : nullptr;
   P.plane = plane; P.planeBytes = h->fs.planeBytes; P.W = h->W; P.H = h->H; P.pitch = h->fs.lv[0].pitch;
   dim3 grid(((h->W + 3) / 4 + 255) / 256, h->H, n);
-  k_prologue<<<grid, 256, 0, h->stream>>>(P);
-  h->launches++;
+  { ProfScope ps(h, IVG_K_PROLOGUE); k_prologue<<<grid, 256, 0, h->stream>>>(P); }
   CK(cudaGetLastError());
   return IVG_OK;
 }

@@ -56,6 +56,33 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
   else desc.rowRange(0, n).copyTo(_descriptors);
 }
 
+void ORBextractor::SetRectifyMaps(const cv::Mat& M1, const cv::Mat& M2) {
+  if (M1.empty() || M2.empty()) { check(ivg_set_rectify_maps(mHandle, nullptr, nullptr, 0, 0, 0), "ivg_set_rectify_maps"); return; }
+  if (M1.type() != CV_32FC1 || M2.type() != CV_32FC1 || M1.rows != M2.rows || M1.cols != M2.cols || M1.step != M2.step)
+    throw std::runtime_error("SetRectifyMaps: CV_32FC1 maps of equal size expected (initUndistortRectifyMap(..., CV_32F, ...))");
+  check(ivg_set_rectify_maps(mHandle, reinterpret_cast<const float*>(M1.data), reinterpret_cast<const float*>(M2.data), M1.cols, M1.rows,
+                             M1.step / sizeof(float)), "ivg_set_rectify_maps");
+}
+
+void ORBextractor::ExtractRaw(const cv::Mat& raw, const cv::Mat& cost, bool rgb, std::vector<cv::KeyPoint>& _keypoints,
+                              cv::OutputArray _descriptors) {
+  if (raw.empty()) return;
+  bqualityScoresAvailable = !cost.empty() && benableIntrospection;
+  check(ivg_upload_batch_raw(mHandle, 1, raw.data, raw.cols, raw.rows, raw.step, raw.step * raw.rows, raw.channels(), rgb ? 1 : 0,
+                             bqualityScoresAvailable ? cost.data : nullptr, bqualityScoresAvailable ? (size_t)cost.step : 0,
+                             bqualityScoresAvailable ? (size_t)cost.step * cost.rows : 0), "ivg_upload_batch_raw");
+  check(ivg_run_batch(mHandle), "ivg_run_batch");
+  const int cap = ivg_max_keypoints(mHandle);
+  _keypoints.resize(cap);
+  cv::Mat desc(cap, 32, CV_8U);
+  int n = 0;
+  check(ivg_download_batch(mHandle, reinterpret_cast<ivg_keypoint*>(_keypoints.data()), desc.data, cap, &n), "ivg_download_batch");
+  check(ivg_sync(mHandle), "ivg_sync");
+  _keypoints.resize(n);
+  if (n == 0) _descriptors.release();
+  else desc.rowRange(0, n).copyTo(_descriptors);
+}
+
 void ORBextractor::SyncPyramidsToHost() {
   for (int l = 0; l < nlevels; ++l) {
     int w = 0, h = 0;

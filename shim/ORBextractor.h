@@ -54,6 +54,12 @@ class ORBextractor {
   void SetKeypointMode(int mode);
   // Copies the device pyramids of the last operator() call into mvImagePyramid / mvQualityImagePyramid.
   void SyncPyramidsToHost();
+  // N4 (optional): the steps the reference runs on the CPU before operator() — cv::remap with the CV_32FC1 maps of
+  // cv::initUndistortRectifyMap (Examples/Stereo/stereo_kitti.cc:463-464; the cost-map too, :519-521) and
+  // Tracking::GrabImageStereo's cvtColor (src/Tracking.cc:278-294) — fused into the upload.  ExtractRaw takes the frame as
+  // read from the camera (CV_8UC1 / CV_8UC3 / CV_8UC4; rgb = Tracking::mbRGB) and the un-rectified cost-map (or empty).
+  void SetRectifyMaps(const cv::Mat& M1, const cv::Mat& M2);    // empty Mats clear the maps
+  void ExtractRaw(const cv::Mat& raw, const cv::Mat& cost, bool rgb, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors);
   // The underlying C-ABI handle (used by the GPU Frame::ComputeStereoMatches replacement).
   ivg_extractor* handle() const { return mHandle; }
 

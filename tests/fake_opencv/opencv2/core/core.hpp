@@ -8,6 +8,9 @@
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_8UC4 24
+#define CV_32FC1 5
 
 namespace cv {
 
@@ -25,12 +28,15 @@ class Mat {
   size_t step = 0;
   unsigned char* data = nullptr;
   Mat() {}
-  Mat(int r, int c, int /*type*/) { create(r, c, 0); }
-  Mat(int r, int c, int /*type*/, void* ext, size_t stp) : rows(r), cols(c), step(stp), data((unsigned char*)ext) {}
-  void create(int r, int c, int /*type*/) {
-    if (r == rows && c == cols && store_) return;
-    rows = r; cols = c; step = (size_t)c;
-    store_ = std::shared_ptr<unsigned char>(new unsigned char[(size_t)r * c + 1], std::default_delete<unsigned char[]>());
+  Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(int r, int c, int type, void* ext, size_t stp) : rows(r), cols(c), step(stp), data((unsigned char*)ext), type_(type) {}
+  int type() const { return type_; }
+  int channels() const { return (type_ >> 3) + 1; }
+  size_t elemSize() const { return (size_t)channels() * ((type_ & 7) == 5 ? 4 : 1); }
+  void create(int r, int c, int type) {
+    if (r == rows && c == cols && type == type_ && store_) return;
+    rows = r; cols = c; type_ = type; step = (size_t)c * elemSize();
+    store_ = std::shared_ptr<unsigned char>(new unsigned char[(size_t)r * step + 1], std::default_delete<unsigned char[]>());
     data = store_.get();
   }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
@@ -38,11 +44,12 @@ class Mat {
   void release() { store_.reset(); data = nullptr; rows = cols = 0; }
   void copyTo(const _OutputArray& o) const;
   void copyTo(Mat& dst) const {
-    dst.create(rows, cols, 0);
-    for (int y = 0; y < rows; ++y) std::memcpy(dst.data + (size_t)y * dst.step, data + (size_t)y * step, cols);
+    dst.create(rows, cols, type_);
+    for (int y = 0; y < rows; ++y) std::memcpy(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols * elemSize());
   }
  private:
   std::shared_ptr<unsigned char> store_;
+  int type_ = 0;
 };
 
 // In OpenCV these are proxy classes; references to Mat are enough for the shim's use.

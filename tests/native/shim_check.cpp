@@ -69,3 +69,25 @@ extern "C" double shim_frame_latency_ms(const unsigned char* left, const unsigne
     return -1.0;
   }
 }
+
+// N4: SetRectifyMaps + ExtractRaw on a BGR frame; returns the keypoints/descriptors and the rectified gray level 0.
+extern "C" int shim_extract_raw(const unsigned char* bgr, int sw, int sh, const float* mapx, const float* mapy, int w, int h, int nfeatures,
+                                void* kps, unsigned char* desc, int* n, unsigned char* level0) {
+  try {
+    ORB_SLAM2::ORBextractor ex(nfeatures, 1.2f, 8, 20, 7);
+    cv::Mat raw(sh, sw, CV_8UC3, (void*)bgr, (size_t)sw * 3), none;
+    cv::Mat m1(h, w, CV_32FC1, (void*)mapx, (size_t)w * 4), m2(h, w, CV_32FC1, (void*)mapy, (size_t)w * 4);
+    ex.SetRectifyMaps(m1, m2);
+    std::vector<cv::KeyPoint> k;
+    cv::Mat d;
+    ex.ExtractRaw(raw, none, false, k, d);
+    *n = (int)k.size();
+    std::memcpy(kps, k.data(), k.size() * sizeof(cv::KeyPoint));
+    for (int i = 0; i < d.rows; ++i) std::memcpy(desc + 32 * i, d.data + (size_t)i * d.step, 32);
+    ex.SyncPyramidsToHost();
+    for (int y = 0; y < h; ++y) std::memcpy(level0 + (size_t)y * w, ex.mvImagePyramid[0].data + (size_t)y * ex.mvImagePyramid[0].step, w);
+    return 0;
+  } catch (const std::exception& e) {
+    return -1;
+  }
+}

@@ -58,3 +58,30 @@ def test_shim_matches_oracle(tmp_path, gpu_api, oracle):
     assert_stereo_close(u[:m], d[:m], r["uRight"], r["depth"], "shim")
     assert levels.value == 8 and np.float32(s1.value) == oL.scale_factors()[1]
     assert np.array_equal(pyr1[:pw.value * ph.value].reshape(ph.value, pw.value), oL.level(1))
+
+
+@pytest.mark.gpu
+def test_shim_extract_raw_matches_oracle(tmp_path, gpu_api, oracle):
+    """N4 through the C++ shim: SetRectifyMaps + ExtractRaw == oracle remap/cvtColor + oracle extraction."""
+    from iv_slam_b200 import synthetic as S
+    from helpers import assert_keypoints_equal
+    L = _build(tmp_path)
+    sw, sh, w, h, nf = 720, 440, 672, 400, 800
+    gray = S.make_image(sw, sh, 31)
+    bgr = np.ascontiguousarray(np.stack([gray, np.roll(gray, 1, 0), np.roll(gray, 2, 1)], -1))
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    mx = np.ascontiguousarray(xx * 1.05 + 4 * np.sin(yy / 41), np.float32)
+    my = np.ascontiguousarray(yy * 1.08 + 3 * np.cos(xx / 29), np.float32)
+    cap = nf + 64
+    kps = np.zeros(cap, gpu_api.KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    lvl0 = np.zeros((h, w), np.uint8)
+    n = C.c_int()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.shim_extract_raw(p(bgr), sw, sh, p(mx), p(my), w, h, nf, p(kps), p(desc), C.byref(n), p(lvl0))
+    assert rc == 0
+    want = oracle.prologue(bgr, False, mx, my)
+    assert np.array_equal(lvl0, want)
+    ko, do = oracle.OracleExtractor(nf, 1.2, 8, 20, 7)(want)
+    assert_keypoints_equal(kps[:n.value], ko, "shim raw")
+    assert np.array_equal(desc[:n.value], do)
