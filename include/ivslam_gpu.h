@@ -176,6 +176,31 @@ int ivg_compute_pyramid(ivg_extractor* h, const uint8_t* image, int width, int h
 int ivg_frame_postprocess_batch(ivg_extractor* h, float minX, float maxX, float minY, float maxY,
                                 float* keyQualScore, int* gridStart, int* gridIndices, int cap, int sync);
 
+/* ---- N2 (next row): the per-frame Hamming-search consumers in Track() ----
+ * Both work on frame `index` of the handle's last batch (keypoints, descriptors on the device; mvuRight if
+ * ivg_stereo_match_batch ran, else treated as -1) and need the 64x48 grid of ivg_frame_postprocess_batch (call it first,
+ * with the same image bounds).  MapPoint/Frame objects are flattened by the caller; flags[i] bit0 = the point takes part,
+ * bit1 = pMP->Observations() > 0 (it then blocks the keypoint it takes for all later points, like the sequential loops
+ * of the reference).  match[i2] = index of the point assigned to current keypoint i2 by this call, or -1; *nmatches is
+ * the function's return value.  cur_blocked[i2] != 0 marks keypoints whose mvpMapPoints entry has observations on
+ * entry (may be NULL).  Synchronous.
+ *
+ * ivg_search_by_projection_last = ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+ *   (src/ORBmatcher.cc:1372-1519).  flags bit0 = LastFrame.mvpMapPoints[i] && !mvbOutlier[i]; world_pos = GetWorldPos();
+ *   desc = GetDescriptor(); octave/angle = LastFrame.mvKeys[i].octave / mvKeysUn[i].angle; Rcw (row-major 3x3), tcw from
+ *   CurrentFrame.mTcw; mode 0 = neither forward nor backward (or bMono), 1 = bForward, 2 = bBackward (:1394-1395);
+ *   check_orientation = ORBmatcher::mbCheckOrientation.
+ * ivg_search_by_projection_map = ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th) (:45-133).
+ *   flags bit0 = mbTrackInView && !isBad(); proj = (mTrackProjX, mTrackProjY, mTrackProjXR); view_cos = mTrackViewCos;
+ *   level = mnTrackScaleLevel; nnratio = ORBmatcher::mfNNratio. */
+int ivg_search_by_projection_last(ivg_extractor* cur, int index, int n, const float* world_pos, const uint8_t* desc, const int* octave,
+                                  const float* angle, const uint8_t* flags, const float* Rcw, const float* tcw, float fx, float fy, float cx,
+                                  float cy, float mbf, float minX, float maxX, float minY, float maxY, int mode, float th,
+                                  int check_orientation, int* match, int cap, int* nmatches);
+int ivg_search_by_projection_map(ivg_extractor* cur, int index, int n, const float* proj, const float* view_cos, const int* level,
+                                 const uint8_t* desc, const uint8_t* flags, const uint8_t* cur_blocked, float minX, float maxX, float minY,
+                                 float maxY, float th, float nnratio, int* match, int cap, int* nmatches);
+
 /* ---- measurement helpers (bench.py) ---- */
 /* CUDA-event timer on the handle's stream: start records an event, stop records another, elapsed waits for it. */
 int ivg_timer_start(ivg_extractor* h);

@@ -68,6 +68,9 @@ def lib():
         "ivg_upload_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_upload_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_set_rectify_maps": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, sz]),
+        "ivg_search_by_projection_last": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp] + [C.c_float] * 9 +
+                                          [C.c_int, C.c_float, C.c_int, vp, C.c_int, i32p]),
+        "ivg_search_by_projection_map": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp] + [C.c_float] * 6 + [vp, C.c_int, i32p]),
         "ivg_upload_batch_raw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, C.c_int, C.c_int, vp, sz, sz]),
         "ivg_run_batch": (C.c_int, [vp]),
         "ivg_download_batch": (C.c_int, [vp, vp, vp, C.c_int, vp]),
@@ -298,6 +301,40 @@ class ORBextractor:
         self.download(kps, desc, cnt)
         self.sync()
         return kps[0, :cnt[0]].copy(), desc[0, :cnt[0]].copy()
+
+    def search_by_projection_last(self, world_pos, desc, octave, angle, flags, Rcw, tcw, cam, bounds, mode=0, th=7.0,
+                                  check_orientation=True, index=0):
+        """N2: ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on frame `index` (needs frame_postprocess).
+        cam = (fx, fy, cx, cy, mbf); bounds = (minX, maxX, minY, maxY).  Returns (match[cap] int32, nmatches)."""
+        f32, i32, u8 = np.float32, np.int32, np.uint8
+        world_pos, desc = np.ascontiguousarray(world_pos, f32), np.ascontiguousarray(desc, u8)
+        octave, angle, flags = np.ascontiguousarray(octave, i32), np.ascontiguousarray(angle, f32), np.ascontiguousarray(flags, u8)
+        Rcw, tcw = np.ascontiguousarray(Rcw, f32), np.ascontiguousarray(tcw, f32)
+        n = flags.size
+        assert world_pos.shape == (n, 3) and desc.shape == (n, 32) and octave.size == n and angle.size == n and Rcw.size == 9 and tcw.size == 3
+        match = np.zeros(self.cap, i32)
+        nm = C.c_int(0)
+        _ck(lib().ivg_search_by_projection_last(self._h, index, n, _p(world_pos), _p(desc), _p(octave), _p(angle), _p(flags), _p(Rcw), _p(tcw),
+                                                *[float(v) for v in cam], *[float(v) for v in bounds], int(mode), float(th),
+                                                int(bool(check_orientation)), _p(match), self.cap, C.byref(nm)), "ivg_search_by_projection_last")
+        return match, nm.value
+
+    def search_by_projection_map(self, proj, view_cos, level, desc, flags, bounds, cur_blocked=None, th=1.0, nnratio=0.8, index=0):
+        """N2: ORBmatcher::SearchByProjection(F, vpMapPoints, th).  proj[n,3] = (mTrackProjX, mTrackProjY, mTrackProjXR)."""
+        f32, i32, u8 = np.float32, np.int32, np.uint8
+        proj, view_cos, level = np.ascontiguousarray(proj, f32), np.ascontiguousarray(view_cos, f32), np.ascontiguousarray(level, i32)
+        desc, flags = np.ascontiguousarray(desc, u8), np.ascontiguousarray(flags, u8)
+        n = flags.size
+        assert proj.shape == (n, 3) and desc.shape == (n, 32) and view_cos.size == n and level.size == n
+        if cur_blocked is not None:
+            cur_blocked = np.ascontiguousarray(cur_blocked, u8)
+            assert cur_blocked.size >= self.cap
+        match = np.zeros(self.cap, i32)
+        nm = C.c_int(0)
+        _ck(lib().ivg_search_by_projection_map(self._h, index, n, _p(proj), _p(view_cos), _p(level), _p(desc), _p(flags), _p(cur_blocked),
+                                               *[float(v) for v in bounds], float(th), float(nnratio), _p(match), self.cap, C.byref(nm)),
+            "ivg_search_by_projection_map")
+        return match, nm.value
 
     def upload_device(self, n, width, height, d_images, d_masks=None):
         """Frames already in device memory (integer device pointers to n contiguous HxW u8 frames)."""

@@ -25,6 +25,7 @@
 #include "k_select.cuh"
 #include "k_octree.cuh"
 #include "k_prologue.cuh"
+#include "k_project.cuh"
 #include "k_stereo.cuh"
 
 using namespace ivg;
@@ -107,6 +108,8 @@ struct ivg_extractor {
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
+  DevBuf<uint8_t> projIn; DevBuf<uint32_t> projCand; DevBuf<int> projInt;   // N2 scratch
+  bool haveGrid = false, haveStereo = false;
   DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
   int mapW = 0, mapH = 0;
   size_t fastSmem = 0, resizeSmem = 0, selSmem = 0;
@@ -509,7 +512,7 @@ int launch_extract(ivg_extractor* h) {
     int rc = launch_extract_kernels(h, fs);
     if (rc) return rc;
   }
-  h->haveResults = true; h->havePyramid = true;
+  h->haveResults = true; h->havePyramid = true; h->haveGrid = false; h->haveStereo = false;
   return IVG_OK;
 }
 
@@ -611,7 +614,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
-  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release();
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release();
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
@@ -762,6 +765,94 @@ int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, in
     if ((rc = copy_frames_in(h, h->qual.p, h->stageCost, n, d_costs, cost_stride, cost_frame_bytes, true))) return rc;
   }
   return IVG_OK;
+}
+
+// ---------------------------------------------------------------------------------------- N2: SearchByProjection
+namespace {
+struct ProjUpload {   // packs the caller's host arrays into one device scratch buffer
+  ivg_extractor* h; size_t off = 0; std::vector<std::pair<size_t, std::pair<const void*, size_t>>> items;
+  size_t add(const void* src, size_t bytes) { const size_t o = off; items.push_back({o, {src, bytes}}); off = (off + bytes + 15) & ~(size_t)15; return o; }
+  int commit() {
+    int rc = h->projIn.alloc(off + 16);
+    if (rc) return rc;
+    for (auto& it : items)
+      if (it.second.first) CK(cudaMemcpyAsync(h->projIn.p + it.first, it.second.first, it.second.second, cudaMemcpyHostToDevice, h->stream));
+    return IVG_OK;
+  }
+};
+}  // namespace
+
+static int proj_common(ivg_extractor* h, int index, ProjArgs& A, int n, float minX, float maxX, float minY, float maxY, int* match, int cap, int* nmatches) {
+  if (!h->haveResults || !h->haveGrid) return IVG_ERR_STATE;              // needs ivg_frame_postprocess_batch (the 64x48 grid)
+  if (index < 0 || index >= h->curBatch || n < 0 || !match || !nmatches) return IVG_ERR_INVALID;
+  if (!(maxX > minX) || !(maxY > minY)) return IVG_ERR_INVALID;
+  if (cap < h->fs.kpCap) return IVG_ERR_CAPACITY;
+  const int K = h->fs.kpCap;
+  int rc;
+  if ((rc = h->projCand.alloc((size_t)std::max(n, 1) * K)) || (rc = h->projInt.alloc((size_t)std::max(n, 1) * 8 + K + 64))) return rc;
+  A.kp = h->outKp.p; A.desc = h->outDesc.p; A.uRight = h->haveStereo ? h->uRight.p : nullptr; A.nPtr = h->outN.p; A.index = index; A.cap = K;
+  A.gridStart = h->gridStart.p; A.gridIdx = h->gridIdx.p;
+  A.minX = minX; A.minY = minY; A.maxX = maxX; A.maxY = maxY;
+  A.invW = (float)GRID_COLS / (maxX - minX); A.invH = (float)GRID_ROWS / (maxY - minY);
+  for (int l = 0; l < h->nlevels; ++l) A.scale[l] = h->scale[l];
+  A.nLevels = h->nlevels;
+  A.n = n;
+  A.cand = h->projCand.p; A.candStride = K;
+  int* ip = h->projInt.p;                     // layout: candCount[n] | tent[4n] (16-B aligned) | accIdx[n] | accBin[n bytes] | match[K] | nmatches
+  A.candCount = ip;
+  const size_t tentOff = ((size_t)n + 3) & ~(size_t)3;
+  A.tent = reinterpret_cast<uint4*>(ip + tentOff);
+  A.accIdx = ip + tentOff + 4 * (size_t)n;
+  A.accBin = reinterpret_cast<int8_t*>(ip + tentOff + 5 * (size_t)n);
+  A.match = ip + tentOff + 5 * (size_t)n + ((size_t)n + 3) / 4;
+  A.nmatches = A.match + K;
+  if (n > 0) { k_proj_candidates<<<(n + 7) / 8, 256, 0, h->stream>>>(A); h->launches++; }
+  k_proj_resolve<<<1, 32, 0, h->stream>>>(A); h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(match, A.match, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = K; i < cap; ++i) match[i] = -1;
+  return IVG_OK;
+}
+
+int ivg_search_by_projection_last(ivg_extractor* cur, int index, int n, const float* world_pos, const uint8_t* desc, const int* octave,
+                                  const float* angle, const uint8_t* flags, const float* Rcw, const float* tcw, float fx, float fy, float cx,
+                                  float cy, float mbf, float minX, float maxX, float minY, float maxY, int mode, float th,
+                                  int check_orientation, int* match, int cap, int* nmatches) {
+  if (!cur || (n > 0 && (!world_pos || !desc || !octave || !angle || !flags)) || !Rcw || !tcw || mode < 0 || mode > 2) return IVG_ERR_INVALID;
+  CK(cudaSetDevice(cur->device));
+  ProjUpload up{cur};
+  const size_t oW = up.add(world_pos, (size_t)n * 12), oD = up.add(desc, (size_t)n * 32), oO = up.add(octave, (size_t)n * 4),
+               oA = up.add(angle, (size_t)n * 4), oF = up.add(flags, (size_t)n);
+  int rc = up.commit();
+  if (rc) return rc;
+  ProjArgs A{};
+  const uint8_t* b = cur->projIn.p;
+  A.world = reinterpret_cast<const float*>(b + oW); A.pdesc = b + oD; A.octave = reinterpret_cast<const int*>(b + oO);
+  A.angle = reinterpret_cast<const float*>(b + oA); A.flags = b + oF;
+  for (int i = 0; i < 9; ++i) A.Rcw[i] = Rcw[i];
+  for (int i = 0; i < 3; ++i) A.tcw[i] = tcw[i];
+  A.fx = fx; A.fy = fy; A.cx = cx; A.cy = cy; A.mbf = mbf; A.mode = mode; A.th = th; A.nnratio = 0.f; A.checkOri = check_orientation != 0;
+  return proj_common(cur, index, A, n, minX, maxX, minY, maxY, match, cap, nmatches);
+}
+
+int ivg_search_by_projection_map(ivg_extractor* cur, int index, int n, const float* proj, const float* view_cos, const int* level,
+                                 const uint8_t* desc, const uint8_t* flags, const uint8_t* cur_blocked, float minX, float maxX, float minY,
+                                 float maxY, float th, float nnratio, int* match, int cap, int* nmatches) {
+  if (!cur || (n > 0 && (!proj || !view_cos || !level || !desc || !flags))) return IVG_ERR_INVALID;
+  CK(cudaSetDevice(cur->device));
+  ProjUpload up{cur};
+  const size_t oP = up.add(proj, (size_t)n * 12), oV = up.add(view_cos, (size_t)n * 4), oL = up.add(level, (size_t)n * 4),
+               oD = up.add(desc, (size_t)n * 32), oF = up.add(flags, (size_t)n), oB = up.add(cur_blocked, cur_blocked ? (size_t)cur->fs.kpCap : 0);
+  int rc = up.commit();
+  if (rc) return rc;
+  ProjArgs A{};
+  const uint8_t* b = cur->projIn.p;
+  A.proj = reinterpret_cast<const float*>(b + oP); A.viewCos = reinterpret_cast<const float*>(b + oV); A.octave = reinterpret_cast<const int*>(b + oL);
+  A.pdesc = b + oD; A.flags = b + oF; A.curBlocked = cur_blocked ? b + oB : nullptr;
+  A.mode = 3; A.th = th; A.nnratio = nnratio; A.checkOri = 0;
+  return proj_common(cur, index, A, n, minX, maxX, minY, maxY, match, cap, nmatches);
 }
 
 // ---------------------------------------------------------------------------------------- N4: input prologue
@@ -972,6 +1063,7 @@ int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf,
   A.uRight = left->uRight.p; A.depth = left->depth.p; A.sad = left->sad.p; A.bestDist = nullptr;
   int rc = stereo_launch(left, right, A, n);
   if (rc) return rc;
+  left->haveStereo = true;
   const size_t k = A.cap;
   // the right handle must not overwrite its pyramids/keypoints before the matcher has read them
   CK(cudaEventRecord(left->evStereo, left->stream));
@@ -1055,6 +1147,7 @@ int ivg_frame_postprocess_batch(ivg_extractor* h, float minX, float maxX, float 
   A.qual = h->kpQual.p; A.gridStart = h->gridStart.p; A.gridIdx = h->gridIdx.p;
   CK(cudaStreamWaitEvent(h->stream, h->evD2H, 0));
   k_frame_post<<<n, 256, 0, h->stream>>>(A); h->launches++;
+  h->haveGrid = true;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->evKernels, h->stream));
   CK(cudaStreamWaitEvent(h->copyOut, h->evKernels, 0));

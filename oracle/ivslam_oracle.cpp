@@ -927,6 +927,169 @@ static void prologue_frame(const uint8_t* src, int sw, int sh, size_t sstride, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// N2: the per-frame Hamming-search consumers of the extractor's output in Track():
+//   ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)   src/ORBmatcher.cc:1372-1519
+//   ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)                   src/ORBmatcher.cc:45-133
+//   Frame::GetFeaturesInArea (src/Frame.cc:620-668), ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1650-1695),
+//   RadiusByViewingCos (:135-141), DescriptorDistance (:1700-1716).
+// MapPoint / Frame objects are flattened into arrays by the caller; flags bit0 = the point takes part (LastFrame:
+// mvpMapPoints[i] && !mvbOutlier[i]; local map: mbTrackInView && !isBad()), bit1 = pMP->Observations() > 0 (such a point
+// blocks the keypoint it is assigned to for all later points — the loops are sequential and order dependent).
+// Float pin: `Rcw*x3Dw+tcw` is cv::gemm's small-matrix path: float products summed left to right in float, then
+// (float)(sum*1.0 + t*1.0) in double (checked against cv2.gemm in tests); the remaining expressions are evaluated
+// without FMA contraction (-ffp-contract=off), like the rest of this file.
+struct ProjFrame {
+  const KeyPoint* kps; int N; const uint8_t* desc; const float* uRight;
+  const int* gridStart; const int* gridIdx;                      // 64 x 48 CSR of orc_frame_post (cell = col*48 + row)
+  float minX, minY, invW, invH;
+  const float* scale;
+};
+
+static void features_in_area(const ProjFrame& F, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) {
+  out.clear();
+  const int COLS = 64, ROWS = 48;
+  const int nMinCellX = std::max(0, (int)std::floor((x - F.minX - r) * F.invW));
+  if (nMinCellX >= COLS) return;
+  const int nMaxCellX = std::min(COLS - 1, (int)std::ceil((x - F.minX + r) * F.invW));
+  if (nMaxCellX < 0) return;
+  const int nMinCellY = std::max(0, (int)std::floor((y - F.minY - r) * F.invH));
+  if (nMinCellY >= ROWS) return;
+  const int nMaxCellY = std::min(ROWS - 1, (int)std::ceil((y - F.minY + r) * F.invH));
+  if (nMaxCellY < 0) return;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+    for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+      for (int j = F.gridStart[ix * ROWS + iy]; j < F.gridStart[ix * ROWS + iy + 1]; ++j) {
+        const int idx = F.gridIdx[j];
+        const KeyPoint& kp = F.kps[idx];
+        if (bCheckLevels) {
+          if (kp.octave < minLevel) continue;
+          if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+        }
+        const float distx = kp.x - x, disty = kp.y - y;
+        if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+      }
+}
+
+static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; ++i) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// cv::Mat x3Dc = Rcw*x3Dw+tcw  (src/ORBmatcher.cc:1408): one cv::gemm call; for 3x3 * 3x1 CV_32F OpenCV takes its small-matrix
+// path: float products summed left to right in float, then (float)(sum*alpha + c*beta) in double.
+static inline void transform_point(const float* R, const float* t, const float* X, float* out) {
+  for (int r = 0; r < 3; ++r) {
+    const float t0 = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2];
+    out[r] = (float)((double)t0 * 1.0 + (double)t[r] * 1.0);
+  }
+}
+
+static int search_by_projection_last(const ProjFrame& F, int n, const float* world, const uint8_t* desc, const int* octave, const float* angle,
+                                     const uint8_t* flags, const float* Rcw, const float* tcw, float fx, float fy, float cx, float cy, float mbf,
+                                     float maxX, float maxY, int mode, float th, int checkOri, int* match) {
+  const int HISTO_LENGTH = 30;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  std::vector<uint8_t> blocked(F.N, 0);        // CurrentFrame.mvpMapPoints[i2] && ->Observations() > 0
+  for (int i = 0; i < F.N; ++i) match[i] = -1;
+  int nmatches = 0;
+  std::vector<int> cand;
+  for (int i = 0; i < n; ++i) {
+    if (!(flags[i] & 1)) continue;
+    float c3[3];
+    transform_point(Rcw, tcw, world + 3 * i, c3);
+    const float xc = c3[0], yc = c3[1];
+    const float invzc = 1.0 / c3[2];
+    if (invzc < 0) continue;
+    float u = fx * xc * invzc + cx;
+    float v = fy * yc * invzc + cy;
+    if (!(std::isfinite(u) && std::isfinite(v))) continue;       // zc == 0: the reference goes on with inf/NaN (undefined casts)
+    if (u < F.minX || u > maxX) continue;
+    if (v < F.minY || v > maxY) continue;
+    const int nLastOctave = octave[i];
+    const float radius = th * F.scale[nLastOctave];
+    if (mode == 1) features_in_area(F, u, v, radius, nLastOctave, -1, cand);
+    else if (mode == 2) features_in_area(F, u, v, radius, 0, nLastOctave, cand);
+    else features_in_area(F, u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (blocked[i2]) continue;
+      if (F.uRight[i2] > 0) {
+        const float ur = u - mbf * invzc;
+        const float er = std::fabs(ur - F.uRight[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = descriptor_distance(desc + 32 * (size_t)i, F.desc + 32 * (size_t)i2);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= TH_HIGH) {
+      match[bestIdx2] = i;
+      blocked[bestIdx2] = (flags[i] & 2) ? 1 : 0;
+      nmatches++;
+      if (checkOri) {
+        float rot = angle[i] - F.kps[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int idx : rotHist[i]) { match[idx] = -1; nmatches--; }
+  }
+  return nmatches;
+}
+
+static int search_by_projection_map(const ProjFrame& F, int n, const float* proj, const float* viewCos, const int* level, const uint8_t* desc,
+                                    const uint8_t* flags, const uint8_t* curBlocked, float th, float nnratio, int* match) {
+  std::vector<uint8_t> blocked(F.N, 0);
+  for (int i = 0; i < F.N; ++i) { match[i] = -1; if (curBlocked) blocked[i] = curBlocked[i]; }
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;
+  std::vector<int> cand;
+  for (int iMP = 0; iMP < n; ++iMP) {
+    if (!(flags[iMP] & 1)) continue;
+    const int nPredictedLevel = level[iMP];
+    float r = viewCos[iMP] > 0.998 ? 2.5 : 4.0;
+    if (bFactor) r *= th;
+    features_in_area(F, proj[3 * iMP], proj[3 * iMP + 1], r * F.scale[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : cand) {
+      if (blocked[idx]) continue;
+      if (F.uRight[idx] > 0) {
+        const float er = std::fabs(proj[3 * iMP + 2] - F.uRight[idx]);
+        if (er > r * F.scale[nPredictedLevel]) continue;
+      }
+      const int dist = descriptor_distance(desc + 32 * (size_t)iMP, F.desc + 32 * (size_t)idx);
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.kps[idx].octave; bestIdx = idx; }
+      else if (dist < bestDist2) { bestLevel2 = F.kps[idx].octave; bestDist2 = dist; }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+      match[bestIdx] = iMP;
+      blocked[bestIdx] = (flags[iMP] & 2) ? 1 : 0;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+
 extern "C" {
 
 void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstride, uint8_t* dst, int dw, int dh, size_t dstride) {
@@ -1081,6 +1244,25 @@ int orc_stereo_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, i
 void orc_prologue(const uint8_t* src, int sw, int sh, size_t sstride, int cn, int rgb, const float* mapx, const float* mapy,
                   size_t mstride, uint8_t* dst, int W, int H, size_t dstride) {
   prologue_frame(src, sw, sh, sstride, cn, rgb, mapx, mapy, mstride, dst, W, H, dstride);
+}
+
+void orc_transform_point(const float* R, const float* t, const float* X, float* out) { transform_point(R, t, X, out); }
+
+int orc_search_by_projection_last(const void* kps, int N, const uint8_t* descCur, const float* uRight, const int* gridStart, const int* gridIdx,
+                                  const float* scale, float minX, float maxX, float minY, float maxY,
+                                  int n, const float* world, const uint8_t* desc, const int* octave, const float* angle, const uint8_t* flags,
+                                  const float* Rcw, const float* tcw, float fx, float fy, float cx, float cy, float mbf, int mode, float th,
+                                  int checkOri, int* match) {
+  ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale};
+  return search_by_projection_last(F, n, world, desc, octave, angle, flags, Rcw, tcw, fx, fy, cx, cy, mbf, maxX, maxY, mode, th, checkOri, match);
+}
+
+int orc_search_by_projection_map(const void* kps, int N, const uint8_t* descCur, const float* uRight, const int* gridStart, const int* gridIdx,
+                                 const float* scale, float minX, float maxX, float minY, float maxY,
+                                 int n, const float* proj, const float* viewCos, const int* level, const uint8_t* desc, const uint8_t* flags,
+                                 const uint8_t* curBlocked, float th, float nnratio, int* match) {
+  ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale};
+  return search_by_projection_map(F, n, proj, viewCos, level, desc, flags, curBlocked, th, nnratio, match);
 }
 
 }  // extern "C"

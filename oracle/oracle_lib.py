@@ -98,6 +98,12 @@ def lib():
     L.orc_stage_seconds.restype = None
     L.orc_frame_post.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.orc_frame_post.restype = None
+    L.orc_search_by_projection_last.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, vp] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int, vp]
+    L.orc_search_by_projection_last.restype = C.c_int
+    L.orc_search_by_projection_map.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]
+    L.orc_search_by_projection_map.restype = C.c_int
+    L.orc_transform_point.argtypes = [vp, vp, vp, vp]
+    L.orc_transform_point.restype = None
     L.orc_prologue.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]
     L.orc_prologue.restype = None
     L.orc_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]
@@ -128,6 +134,43 @@ def resize_linear(src, dw, dh):
     dst = np.empty((dh, dw), np.uint8)
     lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
     return dst
+
+
+def search_by_projection_last(kps, desc_cur, uRight, grid_start, grid_idx, scale, bounds, world_pos, desc, octave, angle, flags, Rcw, tcw,
+                              cam, mode=0, th=7.0, check_orientation=True):
+    """N2 restatement of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono): (match[N], nmatches)."""
+    f32, i32, u8 = np.float32, np.int32, np.uint8
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    a = [np.ascontiguousarray(x, t) for x, t in ((desc_cur, u8), (uRight, f32), (grid_start, i32), (grid_idx, i32), (scale, f32), (world_pos, f32),
+                                                   (desc, u8), (octave, i32), (angle, f32), (flags, u8), (Rcw, f32), (tcw, f32))]
+    match = np.zeros(max(kps.size, 1), i32)
+    nm = lib().orc_search_by_projection_last(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), *[float(v) for v in bounds],
+                                             a[9].size, _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(a[9]), _p(a[10]), _p(a[11]),
+                                             *[float(v) for v in cam], int(mode), float(th), int(bool(check_orientation)), _p(match))
+    return match[:kps.size], nm
+
+
+def search_by_projection_map(kps, desc_cur, uRight, grid_start, grid_idx, scale, bounds, proj, view_cos, level, desc, flags, cur_blocked=None,
+                             th=1.0, nnratio=0.8):
+    """N2 restatement of ORBmatcher::SearchByProjection(F, vpMapPoints, th): (match[N], nmatches)."""
+    f32, i32, u8 = np.float32, np.int32, np.uint8
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    a = [np.ascontiguousarray(x, t) for x, t in ((desc_cur, u8), (uRight, f32), (grid_start, i32), (grid_idx, i32), (scale, f32), (proj, f32),
+                                                   (view_cos, f32), (level, i32), (desc, u8), (flags, u8))]
+    cb = np.ascontiguousarray(cur_blocked, u8) if cur_blocked is not None else None
+    match = np.zeros(max(kps.size, 1), i32)
+    nm = lib().orc_search_by_projection_map(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), *[float(v) for v in bounds],
+                                            a[9].size, _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(a[9]), _p(cb) if cb is not None else None,
+                                            float(th), float(nnratio), _p(match))
+    return match[:kps.size], nm
+
+
+def transform_point(R, t, X):
+    """x3Dc = Rcw*x3Dw+tcw with cv::gemm's small-matrix float semantics."""
+    R, t, X = (np.ascontiguousarray(a, np.float32) for a in (R, t, X))
+    out = np.zeros(3, np.float32)
+    lib().orc_transform_point(_p(R), _p(t), _p(X), _p(out))
+    return out
 
 
 def prologue(frame, rgb=False, mapx=None, mapy=None):

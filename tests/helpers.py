@@ -53,3 +53,48 @@ def assert_stereo_close(u, d, uo, do, what=""):
             # depth = mbf / disparity: a 1e-3 px disparity tolerance maps to a relative depth tolerance of 1e-3/disparity
             disp = np.maximum(np.abs(do[m]) * 0 + 1e-2, 1e-2)
             assert float(np.max(rel * disp)) <= 1.0, "%s depth error" % what
+
+
+# ----------------------------------------------------------------------------- N2 scenarios (SearchByProjection)
+PROJ_CAM = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, mbf=386.1448)
+
+
+def projection_scenario(kps_last, desc_last, depth_last, w, h, seed, n_dup=150):
+    """Flattened LastFrame / local-map inputs for the N2 matchers from a last frame's keypoints and stereo depths:
+    world points by back-projection (last pose = identity), a small camera motion, random outlier / observation flags and
+    `n_dup` duplicated points (same world position, slightly perturbed descriptor) so that several points compete for one
+    current keypoint — that is what exercises the order-dependent blocking of the reference loops."""
+    rng = np.random.default_rng(seed)
+    c = PROJ_CAM
+    n0 = kps_last.size
+    z = np.where(depth_last > 0, depth_last, 1.0).astype(np.float32)
+    world = np.stack([(kps_last["x"] - c["cx"]) * z / c["fx"], (kps_last["y"] - c["cy"]) * z / c["fy"], z], 1).astype(np.float32)
+    flags = np.where(depth_last > 0, 1, 0).astype(np.uint8)
+    flags &= (rng.random(n0) > 0.1).astype(np.uint8)                    # outliers / no MapPoint
+    flags |= (rng.random(n0) < 0.7).astype(np.uint8) << 1                # Observations() > 0
+    dup = rng.choice(n0, n_dup, replace=False)
+    ddesc = desc_last[dup].copy()
+    for r in range(n_dup):                                               # flip 0..5 random bits
+        for b in rng.integers(0, 256, rng.integers(0, 6)):
+            ddesc[r, b >> 3] ^= np.uint8(1 << (b & 7))
+    order = rng.permutation(n0 + n_dup)
+    world = np.concatenate([world, world[dup]])[order]
+    desc = np.concatenate([desc_last, ddesc])[order]
+    octave = np.concatenate([kps_last["octave"], kps_last["octave"][dup]])[order].astype(np.int32)
+    angle = np.concatenate([kps_last["angle"], kps_last["angle"][dup]])[order].astype(np.float32)
+    flags = np.concatenate([flags, flags[dup] | 1])[order].astype(np.uint8)
+    a = 0.004
+    Rcw = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    tcw = np.array([0.03, -0.01, -0.12], np.float32)
+    # local-map style inputs: projections with the same pose (double precision here: they are inputs, not part of the function)
+    pc = world.astype(np.float64) @ Rcw.astype(np.float64).T + tcw.astype(np.float64)
+    invz = 1.0 / pc[:, 2]
+    u = c["fx"] * pc[:, 0] * invz + c["cx"]
+    v = c["fy"] * pc[:, 1] * invz + c["cy"]
+    proj = np.stack([u, v, u - c["mbf"] * invz], 1).astype(np.float32)
+    inview = (u > 0) & (u < w) & (v > 0) & (v < h) & (pc[:, 2] > 0)
+    mflags = ((flags & 1) & inview.astype(np.uint8)) | (flags & 2)
+    view_cos = rng.uniform(0.99, 1.0, world.shape[0]).astype(np.float32)
+    level = np.clip(octave + rng.integers(-1, 2, octave.size), 0, 7).astype(np.int32)
+    return dict(world=world, desc=desc, octave=octave, angle=angle, flags=flags, Rcw=Rcw, tcw=tcw, proj=proj, mflags=mflags.astype(np.uint8),
+                view_cos=view_cos, level=level, cam=(c["fx"], c["fy"], c["cx"], c["cy"], c["mbf"]), bounds=(0.0, float(w), 0.0, float(h)))

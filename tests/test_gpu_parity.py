@@ -419,3 +419,60 @@ def test_n4_prologue_golden_cv2(gpu_api):
     g.upload_raw(frames[:1], False)
     g.run(); g.sync()
     assert np.array_equal(g.level(0, 0, 0), z["gray_noremap"])
+
+
+# ----------------------------------------------------------------------------- N2: SearchByProjection on the device
+def _n2_frames(gpu_api, oracle, w, h, nf, seed, shift):
+    from helpers import projection_scenario
+    left, right = S.make_stereo_pair(w, h, seed)
+    oL, oR = oracle.OracleExtractor(nf, 1.2, 8, 20, 7), oracle.OracleExtractor(nf, 1.2, 8, 20, 7)
+    last = oracle.stereo_frame(oL, oR, left, right, None, 386.1448, 718.856)
+    gL, gR = gpu_api.ORBextractor(nf, 1.2, 8, 20, 7), gpu_api.ORBextractor(nf, 1.2, 8, 20, 7)
+    kps, dcur = gL(np.roll(left, shift, axis=1))
+    gR(np.roll(right, shift, axis=1))
+    uR, _ = gpu_api.compute_stereo_matches(gL, gR, 386.1448, 718.856)
+    sc = projection_scenario(last["kL"], last["dL"], last["depth"], w, h, seed + 1)
+    gL.frame_postprocess(*sc["bounds"])
+    _, gs, gi = oracle.frame_post(kps, None, *sc["bounds"])
+    return gL, gR, kps, dcur, uR[:kps.size], gs, gi, oL.scale_factors(), sc
+
+
+@pytest.mark.parametrize("mode,th,ori", [(0, 7.0, True), (0, 14.0, True), (1, 15.0, True), (2, 7.0, False)])
+def test_n2_search_by_projection_last_frame(gpu_api, oracle, mode, th, ori):
+    gL, gR, kps, dcur, uR, gs, gi, scale, sc = _n2_frames(gpu_api, oracle, 1241, 376, 2000, 81, 3)
+    want, nm_want = oracle.search_by_projection_last(kps, dcur, uR, gs, gi, scale, sc["bounds"], sc["world"], sc["desc"], sc["octave"],
+                                                     sc["angle"], sc["flags"], sc["Rcw"], sc["tcw"], sc["cam"], mode, th, ori)
+    got, nm = gL.search_by_projection_last(sc["world"], sc["desc"], sc["octave"], sc["angle"], sc["flags"], sc["Rcw"], sc["tcw"], sc["cam"],
+                                           sc["bounds"], mode, th, ori)
+    assert nm == nm_want and np.array_equal(got[:kps.size], want), "%d assignments differ" % int((got[:kps.size] != want).sum())
+    assert (got[kps.size:] == -1).all()
+    assert nm_want > 300
+    # order dependence is real in this scenario: with every point non-blocking the result differs
+    other, _ = oracle.search_by_projection_last(kps, dcur, uR, gs, gi, scale, sc["bounds"], sc["world"], sc["desc"], sc["octave"],
+                                                sc["angle"], sc["flags"] & 1, sc["Rcw"], sc["tcw"], sc["cam"], mode, th, ori)
+    assert not np.array_equal(other, want)
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0])
+def test_n2_search_by_projection_local_map(gpu_api, oracle, th):
+    gL, gR, kps, dcur, uR, gs, gi, scale, sc = _n2_frames(gpu_api, oracle, 960, 600, 1500, 83, 2)
+    rng = np.random.default_rng(4)
+    cur_blocked = np.zeros(gL.cap, np.uint8)
+    cur_blocked[:kps.size] = rng.random(kps.size) < 0.15
+    want, nm_want = oracle.search_by_projection_map(kps, dcur, uR, gs, gi, scale, sc["bounds"], sc["proj"], sc["view_cos"], sc["level"],
+                                                    sc["desc"], sc["mflags"], cur_blocked[:kps.size], th, 0.8)
+    got, nm = gL.search_by_projection_map(sc["proj"], sc["view_cos"], sc["level"], sc["desc"], sc["mflags"], sc["bounds"], cur_blocked, th, 0.8)
+    assert nm == nm_want and np.array_equal(got[:kps.size], want), "%d assignments differ" % int((got[:kps.size] != want).sum())
+    assert nm_want > 100
+    # no points / nothing in view
+    got, nm = gL.search_by_projection_map(sc["proj"][:0], sc["view_cos"][:0], sc["level"][:0], sc["desc"][:0], sc["mflags"][:0], sc["bounds"])
+    assert nm == 0 and (got == -1).all()
+
+
+def test_n2_requires_the_grid(gpu_api):
+    g = gpu_api.ORBextractor(500, 1.2, 8, 20, 7)
+    g(S.make_image(640, 480, 3))
+    with pytest.raises(gpu_api.IvgError) as e:
+        g.search_by_projection_map(np.zeros((1, 3), np.float32), np.ones(1, np.float32), np.zeros(1, np.int32), np.zeros((1, 32), np.uint8),
+                                   np.ones(1, np.uint8), (0, 640, 0, 480))
+    assert e.value.status == -6

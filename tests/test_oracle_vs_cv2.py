@@ -189,3 +189,151 @@ def test_prologue_golden_and_real_rectification_maps(oracle):
     assert np.array_equal(oracle.prologue(g["frame"], True, g["mapx"], g["mapy"]), g["gray_rgb"])
     assert np.array_equal(oracle.prologue(g["frame"], False), g["gray_noremap"])
     assert np.array_equal(oracle.prologue(g["cost"], False, g["mapx"], g["mapy"]), g["cost_remapped"])
+
+
+# ----------------------------------------------------------------------------- N2: SearchByProjection restatement
+def test_transform_point_matches_cv2_gemm(oracle):
+    """`Rcw*x3Dw+tcw` (src/ORBmatcher.cc:1408) is one cv::gemm call on CV_32F 3x3 / 3x1 matrices."""
+    rng = np.random.default_rng(9)
+    for _ in range(3000):
+        R = rng.normal(0, 1, (3, 3)).astype(np.float32)
+        X = rng.normal(0, 20, (3, 1)).astype(np.float32)
+        t = rng.normal(0, 5, (3, 1)).astype(np.float32)
+        assert np.array_equal(oracle.transform_point(R, t, X), cv2.gemm(R, X, 1, t, 1)[:, 0])
+
+
+def _py_features_in_area(kps, gs, gi, bounds, x, y, r, min_level, max_level):
+    f = np.float32
+    minX, maxX, minY, maxY = (f(b) for b in bounds)
+    invW, invH = f(64) / (maxX - minX), f(48) / (maxY - minY)
+    x, y, r = f(x), f(y), f(r)
+    c0 = max(0, int(np.floor((x - minX - r) * invW)))
+    c1 = min(63, int(np.ceil((x - minX + r) * invW)))
+    r0 = max(0, int(np.floor((y - minY - r) * invH)))
+    r1 = min(47, int(np.ceil((y - minY + r) * invH)))
+    if c0 >= 64 or c1 < 0 or r0 >= 48 or r1 < 0:
+        return []
+    check = min_level > 0 or max_level >= 0
+    out = []
+    for ix in range(c0, c1 + 1):
+        for iy in range(r0, r1 + 1):
+            for j in range(gs[ix * 48 + iy], gs[ix * 48 + iy + 1]):
+                k = kps[gi[j]]
+                if check and (k["octave"] < min_level or (max_level >= 0 and k["octave"] > max_level)):
+                    continue
+                if abs(f(k["x"]) - x) < r and abs(f(k["y"]) - y) < r:
+                    out.append(int(gi[j]))
+    return out
+
+
+def _popcount_rows(a, b):
+    return int(np.unpackbits(a ^ b).sum())
+
+
+def test_search_by_projection_oracle_matches_python_restatement(oracle):
+    """Independent Python restatement of both SearchByProjection variants (src/ORBmatcher.cc:45-133, 1372-1519) on a small frame."""
+    from helpers import projection_scenario
+    f = np.float32
+    w, h = 620, 300
+    left, right = S.make_stereo_pair(w, h, 71)
+    cur_l = np.roll(left, 2, axis=1)
+    cur_r = np.roll(right, 2, axis=1)
+    oL, oR = oracle.OracleExtractor(500, 1.2, 8, 20, 7), oracle.OracleExtractor(500, 1.2, 8, 20, 7)
+    last = oracle.stereo_frame(oL, oR, left, right, None, 386.1448, 718.856)
+    cur = oracle.stereo_frame(oL, oR, cur_l, cur_r, None, 386.1448, 718.856)
+    sc = projection_scenario(last["kL"], last["dL"], last["depth"], w, h, 5, n_dup=60)
+    kps, dcur, uR = cur["kL"], cur["dL"], cur["uRight"]
+    _, gs, gi = oracle.frame_post(kps, None, *sc["bounds"])
+    scale = oL.scale_factors()
+    fx, fy, cx, cy, mbf = (f(v) for v in sc["cam"])
+    for mode, th, ori in ((0, 7.0, True), (1, 15.0, True), (2, 7.0, False)):
+        match = np.full(kps.size, -1, np.int32)
+        blocked = np.zeros(kps.size, bool)
+        hist = [[] for _ in range(30)]
+        nm = 0
+        for i in range(sc["flags"].size):
+            if not sc["flags"][i] & 1:
+                continue
+            pc = cv2.gemm(sc["Rcw"], sc["world"][i].reshape(3, 1), 1, sc["tcw"].reshape(3, 1), 1)[:, 0]
+            invz = f(1.0 / np.float64(pc[2]))
+            if invz < 0:
+                continue
+            u = f(f(f(fx * pc[0]) * invz) + cx)
+            v = f(f(f(fy * pc[1]) * invz) + cy)
+            if u < 0 or u > w or v < 0 or v > h:
+                continue
+            o = int(sc["octave"][i])
+            radius = f(f(th) * scale[o])
+            lv = {0: (o - 1, o + 1), 1: (o, -1), 2: (0, o)}[mode]
+            best, bi = 256, -1
+            for i2 in _py_features_in_area(kps, gs, gi, sc["bounds"], u, v, radius, *lv):
+                if blocked[i2]:
+                    continue
+                if uR[i2] > 0 and abs(f(f(u - f(mbf * invz)) - uR[i2])) > radius:
+                    continue
+                d = _popcount_rows(sc["desc"][i], dcur[i2])
+                if d < best:
+                    best, bi = d, i2
+            if best <= 100:
+                match[bi] = i
+                blocked[bi] = bool(sc["flags"][i] & 2)
+                nm += 1
+                if ori:
+                    rot = f(sc["angle"][i] - kps["angle"][bi])
+                    if rot < 0:
+                        rot = f(rot + f(360))
+                    b = int(np.floor(f(rot * f(1.0 / 30)) + 0.5))
+                    hist[0 if b == 30 else b].append(bi)
+        if ori:
+            sizes = [len(x) for x in hist]
+            order = sorted(range(30), key=lambda b: (-sizes[b], b))          # ties keep the lower bin first, like the scan
+            i1, i2_, i3 = order[:3]
+            keep = {i1}
+            if not sizes[i2_] < 0.1 * sizes[i1]:
+                keep.add(i2_)
+                if not sizes[i3] < 0.1 * sizes[i1]:
+                    keep.add(i3)
+            keep = {b for b in keep if sizes[b] > 0}
+            for b in range(30):
+                if b not in keep:
+                    for idx in hist[b]:
+                        match[idx] = -1
+                        nm -= 1
+        m, n = oracle.search_by_projection_last(kps, dcur, uR, gs, gi, scale, sc["bounds"], sc["world"], sc["desc"], sc["octave"], sc["angle"],
+                                                sc["flags"], sc["Rcw"], sc["tcw"], sc["cam"], mode, th, ori)
+        assert n == nm and np.array_equal(m, match), "last-frame variant mode %d" % mode
+        assert nm > 50
+    # local-map variant
+    rng = np.random.default_rng(2)
+    cur_blocked = (rng.random(kps.size) < 0.1).astype(np.uint8)
+    for th in (1.0, 3.0):
+        match = np.full(kps.size, -1, np.int32)
+        blocked = cur_blocked.astype(bool).copy()
+        nm = 0
+        for i in range(sc["mflags"].size):
+            if not sc["mflags"][i] & 1:
+                continue
+            lev = int(sc["level"][i])
+            r = f(2.5) if np.float64(sc["view_cos"][i]) > 0.998 else f(4.0)
+            if th != 1.0:
+                r = f(r * f(th))
+            rad = f(r * scale[lev])
+            cand = []
+            for pos, idx in enumerate(_py_features_in_area(kps, gs, gi, sc["bounds"], sc["proj"][i, 0], sc["proj"][i, 1], rad, lev - 1, lev)):
+                if blocked[idx]:
+                    continue
+                if uR[idx] > 0 and abs(f(sc["proj"][i, 2] - uR[idx])) > rad:
+                    continue
+                cand.append((_popcount_rows(sc["desc"][i], dcur[idx]), pos, idx))
+            cand.sort()
+            if not cand or cand[0][0] > 100:
+                continue
+            if len(cand) > 1 and kps["octave"][cand[0][2]] == kps["octave"][cand[1][2]] and f(cand[0][0]) > f(f(0.8) * f(cand[1][0])):
+                continue
+            match[cand[0][2]] = i
+            blocked[cand[0][2]] = bool(sc["mflags"][i] & 2)
+            nm += 1
+        m, n = oracle.search_by_projection_map(kps, dcur, uR, gs, gi, scale, sc["bounds"], sc["proj"], sc["view_cos"], sc["level"], sc["desc"],
+                                               sc["mflags"], cur_blocked, th, 0.8)
+        assert n == nm and np.array_equal(m, match), "local-map variant th %.0f" % th
+        assert nm > 20
