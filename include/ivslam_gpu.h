@@ -224,7 +224,9 @@ int ivg_flush_l2(ivg_extractor* h, size_t bytes);
 #define IVG_K_STEREO 5
 #define IVG_K_MEDIAN 6
 #define IVG_K_PROLOGUE 7   /* N4: k_prologue (remap + cvtColor ingest) */
-#define IVG_NUM_KERNELS 8
+#define IVG_K_PROJ_CAND 8      /* N2: k_proj_candidates */
+#define IVG_K_PROJ_RESOLVE 9   /* N2: k_proj_resolve */
+#define IVG_NUM_KERNELS 10
 int ivg_profile_enable(ivg_extractor* h, int enable);
 int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches);
 /* Test hook: runs the warp-parallel replay of libstdc++'s std::nth_element(first, first+nth, last, key-greater) used by the

@@ -25,7 +25,7 @@ LIB_PATH = os.environ.get("IVSLAM_GPU_LIB") or os.path.join(_HERE, "lib", "libiv
 
 IVG_OK = 0
 KERNEL_NAMES = ("k_resize_level", "k_fast_cells", "k_gauss7", "k_level_select", "k_orient_describe", "k_stereo_match",
-                "k_stereo_median", "k_prologue")
+                "k_stereo_median", "k_prologue", "k_proj_candidates", "k_proj_resolve")
 
 
 class IvgError(RuntimeError):

@@ -108,7 +108,8 @@ struct ivg_extractor {
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
-  DevBuf<uint8_t> projIn; DevBuf<uint32_t> projCand; DevBuf<int> projInt;   // N2 scratch
+  DevBuf<uint8_t> projIn; DevBuf<uint2> projCand; DevBuf<int> projInt;   // N2 scratch
+  void* projHost = nullptr; size_t projHostBytes = 0;                       // N2 pinned staging (inputs, then match[] + nmatches)
   bool haveGrid = false, haveStereo = false;
   DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
   int mapW = 0, mapH = 0;
@@ -614,7 +615,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
-  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release();
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release(); if (h->projHost) { cudaFreeHost(h->projHost); h->projHost = nullptr; }
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
@@ -769,14 +770,23 @@ int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, in
 
 // ---------------------------------------------------------------------------------------- N2: SearchByProjection
 namespace {
-struct ProjUpload {   // packs the caller's host arrays into one device scratch buffer
+struct ProjUpload {   // packs the caller's host arrays into one pinned staging buffer -> one H2D copy
   ivg_extractor* h; size_t off = 0; std::vector<std::pair<size_t, std::pair<const void*, size_t>>> items;
   size_t add(const void* src, size_t bytes) { const size_t o = off; items.push_back({o, {src, bytes}}); off = (off + bytes + 15) & ~(size_t)15; return o; }
   int commit() {
     int rc = h->projIn.alloc(off + 16);
     if (rc) return rc;
+    const size_t need = std::max(off + 16, ((size_t)h->fs.kpCap + 1) * sizeof(int));   // also holds the results (match[] + nmatches)
+    if (h->projHostBytes < need) {
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->projHost) cudaFreeHost(h->projHost);
+      h->projHost = nullptr; h->projHostBytes = 0;
+      CK(cudaMallocHost(&h->projHost, 2 * need));
+      h->projHostBytes = 2 * need;
+    }
     for (auto& it : items)
-      if (it.second.first) CK(cudaMemcpyAsync(h->projIn.p + it.first, it.second.first, it.second.second, cudaMemcpyHostToDevice, h->stream));
+      if (it.second.first && it.second.second) std::memcpy((uint8_t*)h->projHost + it.first, it.second.first, it.second.second);
+    if (off) CK(cudaMemcpyAsync(h->projIn.p, h->projHost, off, cudaMemcpyHostToDevice, h->stream));
     return IVG_OK;
   }
 };
@@ -806,12 +816,15 @@ static int proj_common(ivg_extractor* h, int index, ProjArgs& A, int n, float mi
   A.accBin = reinterpret_cast<int8_t*>(ip + tentOff + 5 * (size_t)n);
   A.match = ip + tentOff + 5 * (size_t)n + ((size_t)n + 3) / 4;
   A.nmatches = A.match + K;
-  if (n > 0) { k_proj_candidates<<<(n + 7) / 8, 256, 0, h->stream>>>(A); h->launches++; }
-  k_proj_resolve<<<1, 32, 0, h->stream>>>(A); h->launches++;
+  if (n > 0) { ProfScope ps(h, IVG_K_PROJ_CAND); k_proj_candidates<<<(n + 7) / 8, 256, 0, h->stream>>>(A); }
+  { ProfScope ps(h, IVG_K_PROJ_RESOLVE); k_proj_resolve<<<1, 32, 0, h->stream>>>(A); }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(match, A.match, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  const size_t outBytes = ((size_t)K + 1) * sizeof(int);
+  if (h->projHostBytes < outBytes) return IVG_ERR_STATE;     // sized by ProjUpload::commit
+  CK(cudaMemcpyAsync(h->projHost, A.match, outBytes, cudaMemcpyDeviceToHost, h->stream));   // match[K] and nmatches are contiguous
   CK(cudaStreamSynchronize(h->stream));
+  std::memcpy(match, h->projHost, (size_t)K * sizeof(int));
+  *nmatches = ((const int*)h->projHost)[K];
   for (int i = K; i < cap; ++i) match[i] = -1;
   return IVG_OK;
 }

@@ -25,6 +25,7 @@ namespace ivg {
 
 constexpr int PJ_TH_HIGH = 100, PJ_HISTO = 30;
 constexpr unsigned PJ_NONE = (256u << 16) | 0xFFFFu;
+constexpr int PJ_TILE = 64;
 
 struct ProjArgs {
   // current frame (device)
@@ -41,7 +42,7 @@ struct ProjArgs {
   int mode;                       // 0: levels nLast-1..nLast+1, 1: forward (>= nLast), 2: backward (<= nLast), 3: local-map variant
   float th, nnratio; int checkOri;
   // work / results
-  uint32_t* cand; int candStride; int* candCount;   // [n][candStride]: dist << 16 | keypoint index, in enumeration order
+  uint2* cand; int candStride; int* candCount;      // [n][candStride]: (dist << 16 | keypoint index, octave | rotation bin << 8), in enumeration order
   uint4* tent;                                       // per point: best key, second key, i2a | i2b << 16, levA | levB << 8 | bin << 16 | flags << 24
   int* match; int* nmatches;                         // [cap], scalar
   int8_t* accBin; int* accIdx;                       // [n]
@@ -81,7 +82,9 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
   const uint8_t fl = A.flags[i];
   unsigned k1 = PJ_NONE, k2 = PJ_NONE;
   int cnt = 0;
-  uint32_t* list = A.cand + (size_t)i * A.candStride;
+  uint2* list = A.cand + (size_t)i * A.candStride;
+  const bool ori = A.mode < 3 && A.checkOri;
+  const float angI = ori ? A.angle[i] : 0.f;
   bool go = (fl & 1) != 0;
   float u = 0.f, v = 0.f, radius = 0.f, xr = 0.f;
   int minLevel = 0, maxLevel = -1;
@@ -147,11 +150,13 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
           const int j = j0 + lane;
           bool pass = false;
           int idx = 0;
+          unsigned meta = 0xFF00u;
           if (j < b) {
             idx = __ldg(gi + j);
             const float* k = reinterpret_cast<const float*>(kp0 + (size_t)idx * 28);
             const int oct = reinterpret_cast<const int*>(k)[5];
             pass = idx < N;
+            meta = ((unsigned)oct & 0xFFu) | ((ori ? (unsigned)pj_rot_bin(angI, k[3]) : 0xFFu) << 8);
             if (checkLevels && (oct < minLevel || (maxLevel >= 0 && oct > maxLevel))) pass = false;
             const float distx = __fsub_rn(k[0], u), disty = __fsub_rn(k[1], v);
             if (!(fabsf(distx) < radius && fabsf(disty) < radius)) pass = false;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
           if (pass) {
             const int pos = cnt + __popc(m & ltmask);
             const int dist = pj_hamming(dl, dc0 + (size_t)idx * 32);
-            list[pos] = ((unsigned)dist << 16) | (unsigned)idx;
+            list[pos] = make_uint2(((unsigned)dist << 16) | (unsigned)idx, meta);
             pj_top2_insert(k1, k2, ((unsigned)dist << 16) | (unsigned)pos);
           }
           cnt += __popc(m);
@@ -177,17 +182,8 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
   __syncwarp();
   if (lane == 0) {
     unsigned ia = 0xFFFFu, ib = 0xFFFFu, levA = 0xFF, levB = 0xFF, bin = 0xFF;
-    const uint8_t* kp0 = A.kp + (size_t)A.index * A.cap * 28;
-    if (k1 != PJ_NONE) {
-      ia = list[k1 & 0xFFFFu] & 0xFFFFu;
-      const float* k = reinterpret_cast<const float*>(kp0 + (size_t)ia * 28);
-      levA = (unsigned)reinterpret_cast<const int*>(k)[5] & 0xFFu;
-      if (A.mode < 3 && A.checkOri) bin = (unsigned)pj_rot_bin(A.angle[i], k[3]);
-    }
-    if (k2 != PJ_NONE) {
-      ib = list[k2 & 0xFFFFu] & 0xFFFFu;
-      levB = (unsigned)reinterpret_cast<const int*>(kp0 + (size_t)ib * 28)[5] & 0xFFu;
-    }
+    if (k1 != PJ_NONE) { const uint2 e = list[k1 & 0xFFFFu]; ia = e.x & 0xFFFFu; levA = e.y & 0xFFu; bin = (e.y >> 8) & 0xFFu; }
+    if (k2 != PJ_NONE) { const uint2 e = list[k2 & 0xFFFFu]; ib = e.x & 0xFFFFu; levB = e.y & 0xFFu; }
     A.candCount[i] = cnt;
     A.tent[i] = make_uint4(k1, k2, ia | (ib << 16), levA | (levB << 8) | (bin << 16) | ((unsigned)fl << 24));
   }
@@ -195,70 +191,136 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
 
 __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A) {
   __shared__ uint32_t blocked[2048];          // one bit per current keypoint (cap <= 65535)
+  __shared__ uint32_t mark[2048];             // scratch: keypoints taken by blocking points of the current chunk
+  __shared__ uint2 tile[32][PJ_TILE];         // the first PJ_TILE candidates of every point of the chunk that has to be replayed
   __shared__ int hist[PJ_HISTO];
   const int lane = threadIdx.x;
-  const int N = A.nPtr[A.index];
-  for (int w = lane; w < 2048; w += 32) blocked[w] = 0;
+  for (int w = lane; w < 2048; w += 32) { blocked[w] = 0; mark[w] = 0; }
   if (lane < PJ_HISTO) hist[lane] = 0;
   for (int c = lane; c < A.cap; c += 32) A.match[c] = -1;
   __syncwarp();
-  const uint8_t* kp0 = A.kp + (size_t)A.index * A.cap * 28;
+  const bool ori = A.mode < 3 && A.checkOri;
   int nm = 0;
+  auto is_blocked = [&](unsigned idx) { return ((blocked[idx >> 5] >> (idx & 31)) & 1u) != 0u; };
+  auto decide = [&](unsigned k1, unsigned k2, unsigned levA, unsigned levB) {
+    bool acc = k1 != PJ_NONE && (int)(k1 >> 16) <= PJ_TH_HIGH;
+    // local map: bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2  => no match
+    if (acc && A.mode == 3 && k2 != PJ_NONE && levA == levB && (float)(int)(k1 >> 16) > __fmul_rn(A.nnratio, (float)(int)(k2 >> 16))) acc = false;
+    return acc;
+  };
+
+  uint4 tNext = make_uint4(PJ_NONE, PJ_NONE, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  int cntNext = 0;
+  if (lane < A.n) { tNext = A.tent[lane]; cntNext = A.candCount[lane]; }
   for (int base = 0; base < A.n; base += 32) {
     const int me = base + lane;
-    uint4 t = make_uint4(PJ_NONE, PJ_NONE, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    if (me < A.n) t = A.tent[me];
+    const uint4 t = tNext;                      // the next chunk's records are fetched while this one is resolved
+    const int myCnt = cntNext;
+    tNext = make_uint4(PJ_NONE, PJ_NONE, 0xFFFFFFFFu, 0xFFFFFFFFu); cntNext = 0;
+    if (me + 32 < A.n) { tNext = A.tent[me + 32]; cntNext = A.candCount[me + 32]; }
     if (me < A.n) A.accBin[me] = -1;
-    unsigned todo = __ballot_sync(0xffffffffu, t.x != PJ_NONE);
-    while (todo) {
-      const int l = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int i = base + l;
-      unsigned k1 = __shfl_sync(0xffffffffu, t.x, l), k2 = __shfl_sync(0xffffffffu, t.y, l);
-      const unsigned ii = __shfl_sync(0xffffffffu, t.z, l), meta = __shfl_sync(0xffffffffu, t.w, l);
-      unsigned ia = ii & 0xFFFFu, ib = ii >> 16;
-      unsigned levA = meta & 0xFFu, levB = (meta >> 8) & 0xFFu, bin = (meta >> 16) & 0xFFu;
-      const unsigned fl = meta >> 24;
-      const bool dirty = ((blocked[ia >> 5] >> (ia & 31)) & 1u) || (k2 != PJ_NONE && ((blocked[ib >> 5] >> (ib & 31)) & 1u));
-      if (dirty) {   // rare: a keypoint this point wanted was taken by an earlier point with observations — rescan its list
-        const uint32_t* list = A.cand + (size_t)i * A.candStride;
-        const int cnt = A.candCount[i];
-        k1 = k2 = PJ_NONE;
-        for (int j = lane; j < cnt; j += 32) {
-          const unsigned e = list[j], idx = e & 0xFFFFu;
-          if (!((blocked[idx >> 5] >> (idx & 31)) & 1u)) pj_top2_insert(k1, k2, (e & 0xFFFF0000u) | (unsigned)j);
+    const bool valid = t.x != PJ_NONE;
+    const unsigned ia = t.z & 0xFFFFu, ib = t.z >> 16, fl = t.w >> 24;
+    const bool hasB = A.mode == 3 && t.y != PJ_NONE;     // the second best only matters for the local-map ratio test
+    const bool acc = decide(t.x, t.y, t.w & 0xFFu, (t.w >> 8) & 0xFFu);
+    const bool blocking = acc && (fl & 2);
+    // A point is "clean" when its decision cannot depend on the other points: its two best keypoints are free, nobody
+    // else in the chunk has the same best keypoint and (local map) its second best is not taken by a blocking point of
+    // the chunk.  Clean points commit in parallel; the others are replayed one at a time, in order.
+    bool slow = valid && (is_blocked(ia) || (hasB && is_blocked(ib)));
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? ia : (0x10000u | (unsigned)lane));
+    if (valid && (peers & ~(1u << lane))) slow = true;
+    if (A.mode == 3) {
+      if (blocking) atomicOr(&mark[ia >> 5], 1u << (ia & 31));
+      __syncwarp();
+      if (valid && hasB && ((mark[ib >> 5] >> (ib & 31)) & 1u)) slow = true;
+      __syncwarp();
+      if (blocking) mark[ia >> 5] = 0;
+      __syncwarp();
+    }
+    bool done = !valid;
+    // stage the candidate lists of the points that will be replayed: all loads are issued before the first store so the
+    // chunk pays one global-memory latency, not one per replayed point
+    const unsigned pref = __ballot_sync(0xffffffffu, slow);
+    for (unsigned rest = pref; rest;) {
+      int sl[4], sc[4];
+      uint2 ra[4], rb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        sl[q] = rest ? __ffs(rest) - 1 : -1;
+        if (rest) rest &= rest - 1;
+        sc[q] = sl[q] >= 0 ? __shfl_sync(0xffffffffu, myCnt, sl[q]) : 0;
+        const uint2* L = A.cand + (size_t)(base + max(sl[q], 0)) * A.candStride;
+        ra[q] = lane < sc[q] ? L[lane] : make_uint2(0, 0);
+        rb[q] = lane + 32 < sc[q] ? L[lane + 32] : make_uint2(0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (sl[q] >= 0) { tile[sl[q]][lane] = ra[q]; tile[sl[q]][lane + 32] = rb[q]; }
+    }
+    __syncwarp();
+    for (;;) {
+      const unsigned sm = __ballot_sync(0xffffffffu, slow && !done);
+      const int first = sm ? __ffs(sm) - 1 : 32;
+      if (!slow && !done && lane < first) {           // commit the clean points that precede the next replayed one
+        if (acc) {
+          A.match[ia] = me;
+          if (blocking) atomicOr(&blocked[ia >> 5], 1u << (ia & 31));
+          if (ori) { const unsigned bin = (t.w >> 16) & 0xFFu; A.accBin[me] = (int8_t)bin; A.accIdx[me] = (int)ia; atomicAdd(&hist[bin], 1); }
         }
-        pj_top2_reduce(k1, k2);
-        ia = ib = 0xFFFFu; levA = levB = 0xFF; bin = 0xFF;
-        if (k1 != PJ_NONE) {
-          ia = list[k1 & 0xFFFFu] & 0xFFFFu;
-          const float* k = reinterpret_cast<const float*>(kp0 + (size_t)ia * 28);
-          levA = (unsigned)reinterpret_cast<const int*>(k)[5] & 0xFFu;
-          if (A.mode < 3 && A.checkOri) bin = (unsigned)pj_rot_bin(A.angle[i], k[3]);
-        }
-        if (k2 != PJ_NONE) {
-          ib = list[k2 & 0xFFFFu] & 0xFFFFu;
-          levB = (unsigned)reinterpret_cast<const int*>(kp0 + (size_t)ib * 28)[5] & 0xFFu;
+        done = true;
+        nm += acc ? 1 : 0;
+      }
+      __syncwarp();
+      if (!sm) break;
+      // replay point base + first against the current blocked set
+      const int i = base + first;
+      const int cnt = __shfl_sync(0xffffffffu, myCnt, first);
+      const unsigned pfl = __shfl_sync(0xffffffffu, fl, first);
+      const uint2* list = A.cand + (size_t)i * A.candStride;
+      const bool staged = (pref >> first) & 1u;
+      unsigned k1 = PJ_NONE, k2 = PJ_NONE;
+      uint2 e1 = make_uint2(0, 0), e2 = make_uint2(0, 0);
+      for (int j = lane; j < cnt; j += 32) {
+        const uint2 e = (staged && j < PJ_TILE) ? tile[first][j] : list[j];
+        if (!is_blocked(e.x & 0xFFFFu)) {
+          const unsigned key = (e.x & 0xFFFF0000u) | (unsigned)j;
+          if (key < k1) { k2 = k1; e2 = e1; k1 = key; e1 = e; } else if (key < k2) { k2 = key; e2 = e; }
         }
       }
-      const int bestDist = (int)(k1 >> 16), bestDist2 = (int)(k2 >> 16);
-      bool accept = k1 != PJ_NONE && bestDist <= PJ_TH_HIGH;
-      if (accept && A.mode == 3) {
-        // bestLevel == bestLevel2 (-1 == -1 never happens here: a best exists) && bestDist > mfNNratio * bestDist2
-        const bool sameLevel = k2 != PJ_NONE && levA == levB;
-        if (sameLevel && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2)) accept = false;
+      unsigned K1 = k1, K2 = k2;
+      pj_top2_reduce(K1, K2);
+      unsigned nia = 0xFFFFu, nlevA = 0xFF, nlevB = 0xFF, nbin = 0xFF;
+      if (K1 != PJ_NONE) {
+        const int o = __ffs(__ballot_sync(0xffffffffu, k1 == K1)) - 1;      // the global best is some lane's own best
+        const unsigned ex = __shfl_sync(0xffffffffu, e1.x, o), ey = __shfl_sync(0xffffffffu, e1.y, o);
+        nia = ex & 0xFFFFu; nlevA = ey & 0xFFu; nbin = (ey >> 8) & 0xFFu;
       }
-      if (accept && lane == 0) {
-        A.match[ia] = i;
-        if (fl & 2) blocked[ia >> 5] |= 1u << (ia & 31);
-        if (A.mode < 3 && A.checkOri) { A.accBin[i] = (int8_t)bin; A.accIdx[i] = (int)ia; hist[bin]++; }
+      if (K2 != PJ_NONE) {
+        const unsigned m1 = __ballot_sync(0xffffffffu, k1 == K2), m2 = __ballot_sync(0xffffffffu, k2 == K2);
+        if (m1) nlevB = __shfl_sync(0xffffffffu, e1.y, __ffs(m1) - 1) & 0xFFu;
+        else nlevB = __shfl_sync(0xffffffffu, e2.y, __ffs(m2) - 1) & 0xFFu;
       }
-      nm += accept ? 1 : 0;
+      const bool accept = decide(K1, K2, nlevA, nlevB);
+      const bool blk = accept && (pfl & 2);
+      if (lane == first) {
+        if (accept) {
+          A.match[nia] = i;
+          if (blk) blocked[nia >> 5] |= 1u << (nia & 31);
+          if (ori) { A.accBin[i] = (int8_t)nbin; A.accIdx[i] = (int)nia; hist[nbin]++; }
+        }
+        done = true;
+      }
+      nm += (accept && lane == first) ? 1 : 0;
+      // a keypoint newly blocked here may be what a later, so far clean, point of the chunk wanted
+      if (blk && !done && lane > first && valid && (ia == nia || (hasB && ib == nia))) slow = true;
       __syncwarp();
     }
   }
   __syncwarp();
-  if (A.mode < 3 && A.checkOri) {
+#pragma unroll
+  for (int s = 16; s; s >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, s);
+  if (ori) {
     int ind1 = -1, ind2 = -1, ind3 = -1;
     {   // ComputeThreeMaxima, evaluated redundantly by every lane
       int max1 = 0, max2 = 0, max3 = 0;
@@ -281,7 +343,6 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A) {
     nm -= removed;
   }
   if (lane == 0) *A.nmatches = nm;
-  (void)N;
 }
 
 }  // namespace ivg
