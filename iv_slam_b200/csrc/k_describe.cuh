@@ -5,8 +5,9 @@
 // (:1263-1295): level-major concatenation, pt *= scale for levels > 0, size/octave/class_id fields.
 //
 // One CTA = 32 keypoint slots, one warp per keypoint (4 keypoints per warp), three phases:
-//   moments  IC_Angle reads the UNBLURRED level: 31 lanes each own one column u of the circular patch (rows bounded by
-//            the compile-time umax table), integer moments are exact and order-free;
+//   moments  IC_Angle reads the UNBLURRED level: lanes = 3 rows x 9 aligned words, 11 coalesced load instructions per
+//            keypoint, reduced with DP4A against the in-circle byte masks of the rows (the umax table); integer moments
+//            are exact and order-free;
 //   angle    ONE lane per keypoint: cv::fastAtan2's float polynomial without FMA and cos/sin of the angle
 //            evaluated in double and rounded to float — 32 keypoints share one pass through the double-precision code
 //            instead of every warp repeating it (the reference calls glibc cosf/sinf; measured disagreement of the two
@@ -54,15 +55,24 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
   __shared__ __align__(128) uint8_t spatch[8][2][DK_BOXW * DK_BOXH + 64];     // +64 keeps every buffer 128-byte aligned
   __shared__ __align__(8) uint64_t bars[8][2];
   __shared__ float2 spat[512];
+  __shared__ uint32_t sOnes[33 * 8];        // in-circle byte masks of the 31 patch rows (+2 empty rows), 8 words of 4 columns each
   __shared__ int sCx[DK_SLOTS], sCy[DK_SLOTS], sLevel[DK_SLOTS], sOut[DK_SLOTS];
   __shared__ float sM01[DK_SLOTS], sM10[DK_SLOTS], sAngle[DK_SLOTS], sA[DK_SLOTS], sB[DK_SLOTS], sResp[DK_SLOTS];
-  // umax of a radius-15 circular patch (src/ORBextractor.cc:458-475); the host checks its own table against this one
-  constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t img = blockIdx.y;
   const int* lc = fs.levelCount + img * MAX_LEVELS;
   for (int i = tid; i < 512; i += 256) spat[i] = g_patternT[i];
+  for (int i = tid; i < 33 * 8; i += 256) {
+    // umax[|v|] of a radius-15 circular patch (src/ORBextractor.cc:458-475) = {15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3}, packed
+    // in nibbles; the host checks its own table against it
+    const int v = i / 8 - HALF_PATCH, k = i & 7;
+    const int d = abs(v) <= HALF_PATCH ? (int)((0x3689ABCDDEEEFFFFull >> (4 * abs(v))) & 15ull) : -1;
+    uint32_t o = 0;
+    for (int bb = 0; bb < 4; ++bb)
+      if (abs(4 * k + bb - HALF_PATCH) <= d) o |= 1u << (8 * bb);
+    sOnes[i] = o;
+  }
   if (tid < 16) mbar_init(&bars[tid >> 1][tid & 1], 1);
 
   if (tid < DK_SLOTS) {
@@ -102,33 +112,40 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
   issue_patch(0);
   issue_patch(1);
 
-  // ---- moments
+  // ---- moments: lane = (row r of 3, word k of 9): every load instruction fetches three 36-byte row segments (the rows'
+  // 31 patch bytes as aligned words), 11 instructions cover the 31 rows.  A word is funnel-shifted with its right
+  // neighbour (one shuffle) to a fixed alignment (byte 0 of word 0 = column u = -15) and reduced with DP4A against the
+  // row's in-circle byte mask (sOnes: the umax table as masks):
+  //   s = sum of the in-circle pixels of the word,  t = sum of (byte index) * pixel
+  //   m10 = sum over words of t + (4k - 15) * s,    m01 = sum over words of v * s.     Integers: exact, order free.
+  // Keypoints are >= 19 px from the border, so rows y-15..y+17 and the 9 words stay inside the level's pitched plane.
+  const int mr = lane / 9, mk = lane - 9 * mr;
+  const bool mact = lane < 27;
 #pragma unroll 1
   for (int q = 0; q < DK_SLOTS / 8; ++q) {
     const int j = warp * (DK_SLOTS / 8) + q;
     const int level = sLevel[j];
     if (level < 0) continue;
     const LevelDev& L = fs.lv[level];
-    const uint8_t* ctr = fs.pyr + img * fs.planeBytes + L.planeOff + (size_t)sCy[j] * L.pitch + sCx[j];
-    // every lane loads its column of the 31x31 bounding square unconditionally (always inside the level: keypoints are
-    // >= 19 px from the border) so all 31 loads are in flight together; rows outside the circle are masked to zero
-    const int u = min(lane, 2 * HALF_PATCH) - HALF_PATCH, au = abs(u), pitch = L.pitch;
-    const bool live = lane <= 2 * HALF_PATCH;
-    int colsum = 0, m01 = 0;
-    {
-      int vals[2 * HALF_PATCH + 1];
+    const int xs = sCx[j] - HALF_PATCH;                     // first patch column
+    const int pitch = L.pitch;
+    const uint8_t* p = fs.pyr + img * fs.planeBytes + L.planeOff + (size_t)(sCy[j] - HALF_PATCH + (mact ? mr : 0)) * pitch + (xs & ~3) + 4 * (mact ? mk : 0);
+    const int sh = 8 * (xs & 3);
+    uint32_t w[11];
 #pragma unroll
-      for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) vals[v + HALF_PATCH] = __ldg(ctr + v * pitch + u);
-      colsum = live ? vals[HALF_PATCH] : 0;
+    for (int it = 0; it < 11; ++it) w[it] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)(3 * it) * pitch));
+    int S = 0, T = 0, m01 = 0;
 #pragma unroll
-      for (int v = 1; v <= HALF_PATCH; ++v) {
-        const bool in = live && au <= UMAX[v];
-        const int a = in ? vals[HALF_PATCH + v] : 0, b = in ? vals[HALF_PATCH - v] : 0;
-        colsum += a + b;
-        m01 += v * (a - b);
-      }
+    for (int it = 0; it < 11; ++it) {
+      const uint32_t wn = __shfl_down_sync(0xffffffffu, w[it], 1);
+      const uint32_t x = __funnelshift_r(w[it], wn, sh);
+      const uint32_t o = (mact && mk < 8) ? sOnes[(3 * it + mr) * 8 + mk] : 0u;
+      const int s = (int)__dp4a(x, o, 0u);
+      T = (int)__dp4a(x, (o * 0xFFu) & 0x03020100u, (unsigned)T);
+      S += s;
+      m01 += (3 * it + mr - HALF_PATCH) * s;
     }
-    int m10 = u * colsum;
+    int m10 = T + (4 * mk - HALF_PATCH) * S;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       m10 += __shfl_xor_sync(0xffffffffu, m10, o);
