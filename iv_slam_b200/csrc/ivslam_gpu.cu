@@ -113,7 +113,7 @@ struct ivg_extractor {
   bool haveGrid = false, haveStereo = false;
   DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
   int mapW = 0, mapH = 0;
-  size_t fastSmem = 0, resizeSmem = 0, selSmem = 0;
+  size_t fastSmem = 0, resizeSmem = 0, selSmem = 0, selSmemLat = 0;
   TmaMaps blurMaps{};                   // per level: 160 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
   TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
   bool resizeTma[MAX_LEVELS] = {false};
@@ -370,6 +370,7 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     fs.selCellCap = 128;
     fs.selCells = (int)align_up(maxCells, 4);
     h->selSmem = sel_smem_bytes(fs.selLevelCap, fs.selCellCap, fs.selCells);
+    h->selSmemLat = sel_smem_bytes(fs.selLevelCap, fs.selCellCap, fs.selCells, SEL_WARPS_LAT);
   }
   h->fastSmem = fastSmem; h->resizeSmem = resizeSmem;
   if (fastSmem > 200 * 1024 || resizeSmem > 200 * 1024) return IVG_ERR_CAPACITY;
@@ -481,7 +482,13 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS, h->fastSmem, h->stream>>>(fs); }
   { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
   if (h->kpMode == 1) { ProfScope ps(h, IVG_K_SELECT); k_octree_select<<<dim3(fs.nlevels, fs.nImages), 256, sizeof(OctShared), h->stream>>>(fs); }
-  else { ProfScope ps(h, IVG_K_SELECT); k_level_select<<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs); }
+  else {
+    // few CTAs (one per level and frame): give each every warp it can use; big batches fill the GPU with 8-warp CTAs
+    const bool lat = fs.nlevels * fs.nImages <= 2 * 148 && h->selSmemLat <= 200 * 1024;
+    ProfScope ps(h, IVG_K_SELECT);
+    if (lat) k_level_select<SEL_WARPS_LAT * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS_LAT * 32, h->selSmemLat, h->stream>>>(fs);
+    else k_level_select<SEL_WARPS * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs);
+  }
   { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps); }
   CK(cudaGetLastError());
   return IVG_OK;
@@ -527,7 +534,8 @@ int init_device_constants(int device) {
     }
     CK(cudaMemcpyToSymbol(g_patternT, pt.data(), sizeof(float2) * 512));
   }
-  CK(cudaFuncSetAttribute(k_level_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_level_select<SEL_WARPS * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_level_select<SEL_WARPS_LAT * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_octree_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OctShared)));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -17,7 +17,8 @@
 namespace ivg {
 
 constexpr int SEL_MAX_CELLS = 1024;      // cells per level the select kernel supports (host check)
-constexpr int SEL_WARPS = 8;
+constexpr int SEL_WARPS = 8;            // warps per CTA for large batches (throughput); small batches launch SEL_WARPS_LAT
+constexpr int SEL_WARPS_LAT = 32;       // one-frame-at-a-time: only nlevels CTAs exist, so each gets every warp an SM-quarter can hold
 // Shared memory is sized per handle (dynamic): FrameSet::selLevelCap level-list entries, selCellCap entries per warp for
 // a cell list, selCells per-cell scalars.  Lists longer than the caps are processed in global memory (same code).
 
@@ -130,20 +131,22 @@ struct SelShared {           // views into the dynamic shared memory block
   uint16_t* levelScratch;    // [2 * selLevelCap]
 };
 
-__host__ __device__ inline size_t sel_smem_bytes(int levelCap, int cellCap, int cells) {
-  return (size_t)8 * levelCap + (size_t)8 * SEL_WARPS * cellCap + (size_t)cells * (5 * 4 + 2) + 16 +
-         (size_t)4 * SEL_WARPS * cellCap + (size_t)4 * levelCap + 16;
+__host__ __device__ inline size_t sel_smem_bytes(int levelCap, int cellCap, int cells, int warps = SEL_WARPS) {
+  return (size_t)8 * levelCap + (size_t)8 * warps * cellCap + (size_t)cells * (5 * 4 + 2) + 16 +
+         (size_t)4 * warps * cellCap + (size_t)4 * levelCap + 16;
 }
 
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
+template <int MAX_THREADS>   // two instantiations: 8 warps (register budget of the throughput configuration) and 32 warps (latency)
+__global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sTotal, sCount;
   const int SEL_LEVEL_CAP = fs.selLevelCap, SEL_CELL_CAP = fs.selCellCap;
+  const int nWarps = blockDim.x >> 5;
   SelShared S;
   {
     unsigned char* p = smem_raw;
     S.levelBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * SEL_LEVEL_CAP;
-    S.cellBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * SEL_WARPS * SEL_CELL_CAP;
+    S.cellBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * nWarps * SEL_CELL_CAP;
     const int nc = fs.selCells;
     S.nTotal = reinterpret_cast<int*>(p); p += 4 * nc;
     S.nStored = reinterpret_cast<int*>(p); p += 4 * nc;
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
     S.thr = p; p += nc;
     S.noMore = p; p += nc;
     p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-    S.cellScratch = reinterpret_cast<uint16_t*>(p); p += (size_t)4 * SEL_WARPS * SEL_CELL_CAP;
+    S.cellScratch = reinterpret_cast<uint16_t*>(p); p += (size_t)4 * nWarps * SEL_CELL_CAP;
     S.levelScratch = reinterpret_cast<uint16_t*>(p);
   }
   const int level = blockIdx.x;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_level_select(FrameSet fs) {
                                              : reinterpret_cast<SelItem*>(fs.workLevel + img * fs.listCapTotal + L.listBase);
   const uint8_t* qual = fs.qual + img * fs.planeBytes + L.planeOff;
 
-  for (int c = warp; c < nCells; c += SEL_WARPS) {
+  for (int c = warp; c < nCells; c += nWarps) {
     const int n = S.nTotal[c];
     const int keep = min(max(S.nRetain[c], 0), n);
     if (keep == 0) continue;
