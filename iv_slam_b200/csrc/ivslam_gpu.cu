@@ -807,7 +807,7 @@ static int proj_common(ivg_extractor* h, int index, ProjArgs& A, int n, float mi
   if (cap < h->fs.kpCap) return IVG_ERR_CAPACITY;
   const int K = h->fs.kpCap;
   int rc;
-  if ((rc = h->projCand.alloc((size_t)std::max(n, 1) * K)) || (rc = h->projInt.alloc((size_t)std::max(n, 1) * 8 + K + 64))) return rc;
+  if ((rc = h->projCand.alloc((size_t)std::max(n, 1) * K)) || (rc = h->projInt.alloc((size_t)std::max(n, 1) * 12 + K + 64))) return rc;
   A.kp = h->outKp.p; A.desc = h->outDesc.p; A.uRight = h->haveStereo ? h->uRight.p : nullptr; A.nPtr = h->outN.p; A.index = index; A.cap = K;
   A.gridStart = h->gridStart.p; A.gridIdx = h->gridIdx.p;
   A.minX = minX; A.minY = minY; A.maxX = maxX; A.maxY = maxY;
@@ -816,13 +816,13 @@ static int proj_common(ivg_extractor* h, int index, ProjArgs& A, int n, float mi
   A.nLevels = h->nlevels;
   A.n = n;
   A.cand = h->projCand.p; A.candStride = K;
-  int* ip = h->projInt.p;                     // layout: candCount[n] | tent[4n] (16-B aligned) | accIdx[n] | accBin[n bytes] | match[K] | nmatches
+  int* ip = h->projInt.p;                     // layout: candCount[n] | tent[8n] (16-B aligned) | accIdx[n] | accBin[n bytes] | match[K] | nmatches
   A.candCount = ip;
   const size_t tentOff = ((size_t)n + 3) & ~(size_t)3;
   A.tent = reinterpret_cast<uint4*>(ip + tentOff);
-  A.accIdx = ip + tentOff + 4 * (size_t)n;
-  A.accBin = reinterpret_cast<int8_t*>(ip + tentOff + 5 * (size_t)n);
-  A.match = ip + tentOff + 5 * (size_t)n + ((size_t)n + 3) / 4;
+  A.accIdx = ip + tentOff + 8 * (size_t)n;
+  A.accBin = reinterpret_cast<int8_t*>(ip + tentOff + 9 * (size_t)n);
+  A.match = ip + tentOff + 9 * (size_t)n + ((size_t)n + 3) / 4;
   A.nmatches = A.match + K;
   if (n > 0) { ProfScope ps(h, IVG_K_PROJ_CAND); k_proj_candidates<<<(n + 7) / 8, 256, 0, h->stream>>>(A); }
   { ProfScope ps(h, IVG_K_PROJ_RESOLVE); k_proj_resolve<<<1, 32, 0, h->stream>>>(A); }

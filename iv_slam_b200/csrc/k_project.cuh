@@ -43,7 +43,8 @@ struct ProjArgs {
   float th, nnratio; int checkOri;
   // work / results
   uint2* cand; int candStride; int* candCount;      // [n][candStride]: (dist << 16 | keypoint index, octave | rotation bin << 8), in enumeration order
-  uint4* tent;                                       // per point: best key, second key, i2a | i2b << 16, levA | levB << 8 | bin << 16 | flags << 24
+  uint4* tent;                                       // per point, two records: {key1, key2, key3, count | flags << 24} and
+                                                     // {idx1 | idx2 << 16, idx3 | lev1 << 16 | lev2 << 24, lev3 | bin1 << 8 | bin2 << 16 | bin3 << 24, 0}
   int* match; int* nmatches;                         // [cap], scalar
   int8_t* accBin; int* accIdx;                       // [n]
 };
@@ -56,6 +57,9 @@ __device__ __forceinline__ int pj_hamming(const uint32_t (&a)[8], const uint8_t*
 
 __device__ __forceinline__ void pj_top2_insert(unsigned& k1, unsigned& k2, unsigned key) {
   if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+}
+__device__ __forceinline__ void pj_top3_insert(unsigned& k1, unsigned& k2, unsigned& k3, unsigned key) {
+  if (key < k1) { k3 = k2; k2 = k1; k1 = key; } else if (key < k2) { k3 = k2; k2 = key; } else if (key < k3) k3 = key;
 }
 __device__ __forceinline__ void pj_top2_reduce(unsigned& k1, unsigned& k2) {
 #pragma unroll
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
   if (i >= A.n) return;
   const int N = A.nPtr[A.index];
   const uint8_t fl = A.flags[i];
-  unsigned k1 = PJ_NONE, k2 = PJ_NONE;
+  unsigned k1 = PJ_NONE, k2 = PJ_NONE, k3 = PJ_NONE;
   int cnt = 0;
   uint2* list = A.cand + (size_t)i * A.candStride;
   const bool ori = A.mode < 3 && A.checkOri;
@@ -171,21 +175,32 @@ __global__ void __launch_bounds__(256) k_proj_candidates(ProjArgs A) {
             const int pos = cnt + __popc(m & ltmask);
             const int dist = pj_hamming(dl, dc0 + (size_t)idx * 32);
             list[pos] = make_uint2(((unsigned)dist << 16) | (unsigned)idx, meta);
-            pj_top2_insert(k1, k2, ((unsigned)dist << 16) | (unsigned)pos);
+            pj_top3_insert(k1, k2, k3, ((unsigned)dist << 16) | (unsigned)pos);
           }
           cnt += __popc(m);
         }
       }
     }
   }
-  pj_top2_reduce(k1, k2);
+  // the three smallest keys of the warp: three rounds of "global minimum, its owner pops"
+  unsigned K[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    unsigned m = k1;
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, sft));
+    K[r] = m;
+    if (m != PJ_NONE && k1 == m) { k1 = k2; k2 = k3; k3 = PJ_NONE; }      // keys are unique: exactly one owner
+  }
   __syncwarp();
   if (lane == 0) {
-    unsigned ia = 0xFFFFu, ib = 0xFFFFu, levA = 0xFF, levB = 0xFF, bin = 0xFF;
-    if (k1 != PJ_NONE) { const uint2 e = list[k1 & 0xFFFFu]; ia = e.x & 0xFFFFu; levA = e.y & 0xFFu; bin = (e.y >> 8) & 0xFFu; }
-    if (k2 != PJ_NONE) { const uint2 e = list[k2 & 0xFFFFu]; ib = e.x & 0xFFFFu; levB = e.y & 0xFFu; }
+    unsigned idx[3] = {0xFFFFu, 0xFFFFu, 0xFFFFu}, lev[3] = {0xFF, 0xFF, 0xFF}, bin[3] = {0xFF, 0xFF, 0xFF};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (K[r] != PJ_NONE) { const uint2 e = list[K[r] & 0xFFFFu]; idx[r] = e.x & 0xFFFFu; lev[r] = e.y & 0xFFu; bin[r] = (e.y >> 8) & 0xFFu; }
     A.candCount[i] = cnt;
-    A.tent[i] = make_uint4(k1, k2, ia | (ib << 16), levA | (levB << 8) | (bin << 16) | ((unsigned)fl << 24));
+    A.tent[2 * i] = make_uint4(K[0], K[1], K[2], (unsigned)min(cnt, 0xFFFF) | ((unsigned)fl << 24));
+    A.tent[2 * i + 1] = make_uint4(idx[0] | (idx[1] << 16), idx[2] | (lev[0] << 16) | (lev[1] << 24), lev[2] | (bin[0] << 8) | (bin[1] << 16) | (bin[2] << 24), 0u);
   }
 }
 
@@ -209,31 +224,51 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A) {
     return acc;
   };
 
-  uint4 tNext = make_uint4(PJ_NONE, PJ_NONE, 0xFFFFFFFFu, 0xFFFFFFFFu);
-  int cntNext = 0;
-  if (lane < A.n) { tNext = A.tent[lane]; cntNext = A.candCount[lane]; }
+  const uint4 kNoneA = make_uint4(PJ_NONE, PJ_NONE, PJ_NONE, 0u), kNoneB = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+  uint4 taNext = kNoneA, tbNext = kNoneB;
+  if (lane < A.n) { taNext = A.tent[2 * lane]; tbNext = A.tent[2 * lane + 1]; }
   for (int base = 0; base < A.n; base += 32) {
     const int me = base + lane;
-    const uint4 t = tNext;                      // the next chunk's records are fetched while this one is resolved
-    const int myCnt = cntNext;
-    tNext = make_uint4(PJ_NONE, PJ_NONE, 0xFFFFFFFFu, 0xFFFFFFFFu); cntNext = 0;
-    if (me + 32 < A.n) { tNext = A.tent[me + 32]; cntNext = A.candCount[me + 32]; }
+    const uint4 ta = taNext, tb = tbNext;       // the next chunk's records are fetched while this one is resolved
+    taNext = kNoneA; tbNext = kNoneB;
+    if (me + 32 < A.n) { taNext = A.tent[2 * (me + 32)]; tbNext = A.tent[2 * (me + 32) + 1]; }
     if (me < A.n) A.accBin[me] = -1;
-    const bool valid = t.x != PJ_NONE;
-    const unsigned ia = t.z & 0xFFFFu, ib = t.z >> 16, fl = t.w >> 24;
-    const bool hasB = A.mode == 3 && t.y != PJ_NONE;     // the second best only matters for the local-map ratio test
-    const bool acc = decide(t.x, t.y, t.w & 0xFFu, (t.w >> 8) & 0xFFu);
+    const bool valid = ta.x != PJ_NONE;
+    const unsigned fl = ta.w >> 24;
+    const int myCnt = (int)(ta.w & 0xFFFFu) == 0xFFFF ? A.candCount[min(me, A.n - 1)] : (int)(ta.w & 0xFFFFu);
+    // The point's three best candidates against the keypoints blocked so far: the first free one is its best, the
+    // second free one its second best (needed by the local-map ratio test only).  That is exact as long as enough of
+    // the three are free, or the three are the whole list; otherwise the point is replayed from its full list.
+    const unsigned key[3] = {ta.x, ta.y, ta.z};
+    const unsigned idx[3] = {tb.x & 0xFFFFu, tb.x >> 16, tb.y & 0xFFFFu};
+    const unsigned lev[3] = {(tb.y >> 16) & 0xFFu, tb.y >> 24, tb.z & 0xFFu};
+    const unsigned bins[3] = {(tb.z >> 8) & 0xFFu, (tb.z >> 16) & 0xFFu, tb.z >> 24};
+    unsigned kb = PJ_NONE, ks = PJ_NONE, ia = 0xFFFFu, ib = 0xFFFFu, levb = 0xFF, levs = 0xFF, binb = 0xFF;
+    int nfree = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (key[r] != PJ_NONE && !is_blocked(idx[r])) {
+        if (nfree == 0) { kb = key[r]; ia = idx[r]; levb = lev[r]; binb = bins[r]; }
+        else if (nfree == 1) { ks = key[r]; ib = idx[r]; levs = lev[r]; }
+        ++nfree;
+      }
+    }
+    const bool exhausted = myCnt <= 3;
+    const bool known = exhausted || nfree >= (A.mode == 3 ? 2 : 1);
+    const bool hasB = A.mode == 3 && ks != PJ_NONE;     // the second best only matters for the local-map ratio test
+    const bool acc = valid && known && decide(kb, ks, levb, levs);
     const bool blocking = acc && (fl & 2);
-    // A point is "clean" when its decision cannot depend on the other points: its two best keypoints are free, nobody
-    // else in the chunk has the same best keypoint and (local map) its second best is not taken by a blocking point of
-    // the chunk.  Clean points commit in parallel; the others are replayed one at a time, in order.
-    bool slow = valid && (is_blocked(ia) || (hasB && is_blocked(ib)));
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? ia : (0x10000u | (unsigned)lane));
-    if (valid && (peers & ~(1u << lane))) slow = true;
+    const bool hasA = valid && known && kb != PJ_NONE;
+    // A point is "clean" when its decision cannot depend on the other points of the chunk: nobody else in the chunk has
+    // the same best keypoint and (local map) its second best is not taken by a blocking point of the chunk.  Clean
+    // points commit in parallel; the others are replayed one at a time, in order.
+    bool slow = valid && !known;
+    const unsigned peers = __match_any_sync(0xffffffffu, hasA ? ia : (0x10000u | (unsigned)lane));
+    if (hasA && (peers & ~(1u << lane))) slow = true;
     if (A.mode == 3) {
       if (blocking) atomicOr(&mark[ia >> 5], 1u << (ia & 31));
       __syncwarp();
-      if (valid && hasB && ((mark[ib >> 5] >> (ib & 31)) & 1u)) slow = true;
+      if (hasA && hasB && ((mark[ib >> 5] >> (ib & 31)) & 1u)) slow = true;
       __syncwarp();
       if (blocking) mark[ia >> 5] = 0;
       __syncwarp();
@@ -266,7 +301,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A) {
         if (acc) {
           A.match[ia] = me;
           if (blocking) atomicOr(&blocked[ia >> 5], 1u << (ia & 31));
-          if (ori) { const unsigned bin = (t.w >> 16) & 0xFFu; A.accBin[me] = (int8_t)bin; A.accIdx[me] = (int)ia; atomicAdd(&hist[bin], 1); }
+          if (ori) { A.accBin[me] = (int8_t)binb; A.accIdx[me] = (int)ia; atomicAdd(&hist[binb], 1); }
         }
         done = true;
         nm += acc ? 1 : 0;
@@ -313,7 +348,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A) {
       }
       nm += (accept && lane == first) ? 1 : 0;
       // a keypoint newly blocked here may be what a later, so far clean, point of the chunk wanted
-      if (blk && !done && lane > first && valid && (ia == nia || (hasB && ib == nia))) slow = true;
+      if (blk && !done && lane > first && hasA && (ia == nia || (hasB && ib == nia))) slow = true;
       __syncwarp();
     }
   }
