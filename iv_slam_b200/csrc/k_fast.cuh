@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       for (int gb = 0; gb < nG4; gb += 64) {
         const int g0 = gb + lane, g1 = g0 + 32;
         const bool st0 = g0 < nG4, st1 = g1 < nG4;
-        const bool ld0 = st0 && xa + 4 * g0 < pitch, ld1 = st1 && xa + 4 * g1 < pitch;
+        const bool ld0 = st0 && xa + 4 * g0 < L.w, ld1 = st1 && xa + 4 * g1 < L.w;     // words past the image width (row padding) are never written: stage zeros
         const uint8_t* src = pix + (size_t)(gy0 + warp) * pitch + xa + 4 * g0;
         uint32_t* dst = sp + warp * SP + 2 * g0;
 #pragma unroll 2

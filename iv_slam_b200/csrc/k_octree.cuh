@@ -115,7 +115,12 @@ __global__ void __launch_bounds__(256) k_octree_select(FrameSet fs) {
   uint32_t seq = 0;
   auto alloc_node = [&]() {
     int id;
-    if (freeHead >= 0) { id = freeHead; freeHead = nodes[id].next; }
+    if (freeHead >= 0) {                        // lane 0 reads the link and broadcasts it: it is also the lane that rewrites the node
+      id = freeHead;
+      int nx = 0;
+      if (lane == 0) nx = nodes[id].next;
+      freeHead = __shfl_sync(0xffffffffu, nx, 0);
+    }
     else id = nextFresh < slots ? nextFresh++ : -1;
     return id;
   };
