@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   const int lead = cOff & 1;               // 1: pair 0 starts one column left of the detect range
   const int w0 = cOff >> 1;                // staged word of pair 0
   const int nPr = (lead + cw + 1) >> 1;    // pixel pairs per row
-  const int nChunks = (nPr + 31) >> 5;
   const int scoreTh = fs.scoreTh;
   const unsigned kK2 = ((unsigned)scoreTh + 1u) * 0x00010001u;      // th + 1 in both 16-bit lanes
   const unsigned kB = 0x80008000u - kK2;
@@ -133,39 +132,49 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     __syncthreads();
 
     // ---- B: opposing-pair rejection on diameters 0-8, 2-10, 4-12, 6-14
+    // A lane takes two adjacent pixel pairs (four pixels) per step: their ring samples overlap, so 11 64-bit loads serve
+    // both (22 32-bit loads otherwise).  Rows are walked from an even word so that the 64-bit loads are aligned; pair
+    // indices outside [0, nPr) (the word before the first pair, lanes past the end of the row) read staged neighbours /
+    // slack and are masked.
     uint16_t* wlist = slist + warp * segCap;        // this warp's private segment: no atomics, no ordering needed
     int wn = 0;
     {
       const unsigned ltmask = (1u << lane) - 1u;
+      const int wE = w0 & ~1, pOff = w0 - wE;       // first (even) word walked; its pair index is -pOff
+      const int nSteps = (nPr + pOff + 63) >> 6;    // 64 words per warp step
+      // directly on the packed pixels (no differences needed for a reject test):
+      //   bright possible  <=>  min over diameters of max(ring_k, ring_k+8) >= centre + th + 1
+      //   dark possible    <=>  max over diameters of min(ring_k, ring_k+8) <= centre - th - 1
+      auto reject_test = [&](unsigned C, unsigned r0_, unsigned r8, unsigned r2, unsigned r10, unsigned r4, unsigned r12, unsigned r6, unsigned r14) {
+        const unsigned a = __vminu2(vmin3(__vmaxu2(r0_, r8), __vmaxu2(r2, r10), __vmaxu2(r4, r12)), __vmaxu2(r6, r14));
+        const unsigned b = __vmaxu2(vmax3(__vminu2(r0_, r8), __vminu2(r2, r10), __vminu2(r4, r12)), __vminu2(r6, r14));
+        // bit 15 of each 16-bit lane: (a >= C + K) and (C >= b + K), K = th + 1; no borrow can cross lanes
+        const unsigned X = a + kB - C;
+        const unsigned Y = C + kB - b;
+        return ((X | Y) & 0x80008000u) != 0u;
+      };
       for (int y = warp; y < nSR; y += FC_WARPS) {
-        const uint32_t* ctr = sp + (y + 3) * SP + w0 + lane;
-        const uint32_t* cp3 = ctr + 3 * SP;  const uint32_t* cm3 = ctr - 3 * SP;
-        const uint32_t* cp2 = ctr + 2 * SP;  const uint32_t* cm2 = ctr - 2 * SP;
-        const int ebase = (y << sh) + lane;
-        for (int cb = 0; cb < nChunks; cb += 4, ctr += 128, cp3 += 128, cm3 += 128, cp2 += 128, cm2 += 128) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (cb + k < nChunks) {
-              const int o = 32 * k;
-              // directly on the packed pixels (no differences needed for a reject test):
-              //   bright possible  <=>  min over diameters of max(ring_k, ring_k+8) >= centre + th + 1
-              //   dark possible    <=>  max over diameters of min(ring_k, ring_k+8) <= centre - th - 1
-              // lanes past the end of the row read staged neighbours / slack and are masked below
-              const unsigned C = ctr[o];
-              const unsigned r0_ = cp3[o], r8 = cm3[o], r2 = cp2[o + 1], r10 = cm2[o - 1], r6 = cm2[o + 1], r14 = cp2[o - 1];
-              const unsigned r4 = __byte_perm(ctr[o + 1], ctr[o + 2], 0x5432), r12 = __byte_perm(ctr[o - 2], ctr[o - 1], 0x5432);
-              const unsigned a = __vminu2(vmin3(__vmaxu2(r0_, r8), __vmaxu2(r2, r10), __vmaxu2(r4, r12)), __vmaxu2(r6, r14));
-              const unsigned b = __vmaxu2(vmax3(__vminu2(r0_, r8), __vminu2(r2, r10), __vminu2(r4, r12)), __vminu2(r6, r14));
-              // bit 15 of each 16-bit lane: (a >= C + K) and (C >= b + K), K = th + 1; no borrow can cross lanes
-              const unsigned X = a + kB - C;
-              const unsigned Y = C + kB - b;
-              const int pi = (cb + k) * 32 + lane;
-              const bool pass = (((X | Y) & 0x80008000u) != 0u) & (pi < nPr);
-              const unsigned m = __ballot_sync(0xffffffffu, pass);
-              if (pass) wlist[wn + __popc(m & ltmask)] = (uint16_t)(ebase + (cb + k) * 32);   // fits 16 bits: the host bounds the band height
-              wn += __popc(m);
-            }
-          }
+        const uint2* ctr = reinterpret_cast<const uint2*>(sp + (y + 3) * SP + wE) + lane;
+        const uint2* cp3 = reinterpret_cast<const uint2*>(sp + (y + 6) * SP + wE) + lane;
+        const uint2* cm3 = reinterpret_cast<const uint2*>(sp + y * SP + wE) + lane;
+        const uint2* cp2 = reinterpret_cast<const uint2*>(sp + (y + 5) * SP + wE) + lane;
+        const uint2* cm2 = reinterpret_cast<const uint2*>(sp + (y + 1) * SP + wE) + lane;
+        const int ebase = (y << sh);
+        int pi = 2 * lane - pOff;
+        for (int st = 0; st < nSteps; ++st, ctr += 32, cp3 += 32, cm3 += 32, cp2 += 32, cm2 += 32, pi += 64) {
+          const uint2 ca = ctr[-1], cb = ctr[0], cc = ctr[1];        // words W-2 .. W+3 of the centre row
+          const uint2 t3 = cp3[0], b3 = cm3[0];
+          const uint2 pa = cp2[-1], pb = cp2[0], pc = cp2[1];
+          const uint2 ma = cm2[-1], mb = cm2[0], mc = cm2[1];
+          const bool passA = reject_test(cb.x, t3.x, b3.x, pb.y, ma.y, __byte_perm(cb.y, cc.x, 0x5432), __byte_perm(ca.x, ca.y, 0x5432), mb.y, pa.y) &
+                             (pi >= 0) & (pi < nPr);
+          const bool passB = reject_test(cb.y, t3.y, b3.y, pc.x, mb.x, __byte_perm(cc.x, cc.y, 0x5432), __byte_perm(ca.y, cb.x, 0x5432), mc.x, pb.x) &
+                             (pi + 1 < nPr);
+          const unsigned mA = __ballot_sync(0xffffffffu, passA), mB = __ballot_sync(0xffffffffu, passB);
+          if (passA) wlist[wn + __popc(mA & ltmask)] = (uint16_t)(ebase + pi);          // fits 16 bits: the host bounds the band height
+          wn += __popc(mA);
+          if (passB) wlist[wn + __popc(mB & ltmask)] = (uint16_t)(ebase + pi + 1);
+          wn += __popc(mB);
         }
       }
     }
