@@ -476,3 +476,44 @@ def test_n2_requires_the_grid(gpu_api):
         g.search_by_projection_map(np.zeros((1, 3), np.float32), np.ones(1, np.float32), np.zeros(1, np.int32), np.zeros((1, 32), np.uint8),
                                    np.ones(1, np.uint8), (0, 640, 0, 480))
     assert e.value.status == -6
+
+
+def test_n4_strided_raw_frames_and_batch(gpu_api, oracle):
+    """Raw frames that are views into a larger buffer (row padding, frame padding) take the pitched-copy path."""
+    rng = np.random.default_rng(5)
+    n, sh, sw = 3, 250, 333
+    big = rng.integers(0, 256, (n, sh + 7, sw + 19, 3), dtype=np.uint8)
+    frames = big[:, 3:3 + sh, 5:5 + sw, :]
+    cbig = rng.integers(0, 256, (n, sh + 2, sw + 9), dtype=np.uint8)
+    costs = cbig[:, 1:1 + sh, 4:4 + sw]
+    yy, xx = np.mgrid[0:240, 0:320].astype(np.float32)
+    mx, my = (xx * 1.02 + 1.5).astype(np.float32), (yy * 1.01 + 2.25).astype(np.float32)
+    g = gpu_api.ORBextractor(400, 1.2, 6, 20, 7, True)
+    g.set_rectify_maps(mx, my)
+    g.upload_raw(frames, True, costs)
+    g.run(); g.sync()
+    for b in range(n):
+        assert np.array_equal(g.level(0, 0, b), oracle.prologue(np.ascontiguousarray(frames[b]), True, mx, my)), "frame %d" % b
+        assert np.array_equal(g.level(0, 2, b), oracle.prologue(np.ascontiguousarray(costs[b]), False, mx, my)), "cost %d" % b
+
+
+def test_n2_without_stereo_and_offset_bounds(gpu_api, oracle):
+    """No stereo matching before the projection search (mvuRight all -1, e.g. monocular) and image bounds that do not
+    start at 0 (ComputeImageBounds of a distorted camera)."""
+    from helpers import projection_scenario
+    w, h, nf = 800, 420, 1000
+    left, right = S.make_stereo_pair(w, h, 91)
+    oL, oR = oracle.OracleExtractor(nf, 1.2, 8, 20, 7), oracle.OracleExtractor(nf, 1.2, 8, 20, 7)
+    last = oracle.stereo_frame(oL, oR, left, right, None, 386.1448, 718.856)
+    g = gpu_api.ORBextractor(nf, 1.2, 8, 20, 7)
+    kps, dcur = g(np.roll(left, 2, axis=1))
+    sc = projection_scenario(last["kL"], last["dL"], last["depth"], w, h, 92, n_dup=40)
+    bounds = (-7.5, w + 4.25, -3.0, h + 9.5)
+    g.frame_postprocess(*bounds)
+    _, gs, gi = oracle.frame_post(kps, None, *bounds)
+    uR = np.full(kps.size, -1, np.float32)
+    want, nm_want = oracle.search_by_projection_last(kps, dcur, uR, gs, gi, oL.scale_factors(), bounds, sc["world"], sc["desc"], sc["octave"],
+                                                     sc["angle"], sc["flags"], sc["Rcw"], sc["tcw"], sc["cam"], 0, 15.0, True)
+    got, nm = g.search_by_projection_last(sc["world"], sc["desc"], sc["octave"], sc["angle"], sc["flags"], sc["Rcw"], sc["tcw"], sc["cam"], bounds, 0, 15.0, True)
+    assert nm == nm_want and np.array_equal(got[:kps.size], want)
+    assert nm_want > 100
