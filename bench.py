@@ -185,6 +185,7 @@ def main():
     from iv_slam_b200.frontend import StereoFrontend
 
     torch.cuda.set_device(local)
+    numa_cpus = sharding.bind_to_gpu_numa_node(local) if world > 1 else None     # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -297,7 +298,8 @@ def main():
             "config": {"workload": "C3: batch of KITTI-shape 1241x376 stereo pairs, nFeatures 2000, 8 levels, scale 1.2, iniTh 20, minTh 7, introspection off",
                        "pairs_per_gpu_per_step": B, "chunk_pairs": args.chunk, "slots": args.slots,
                        "l2": "inputs of one step (%.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
-                       "parallelism": "frame-parallel, %d independent rank(s), no collective" % world},
+                       "parallelism": "frame-parallel, %d independent rank(s), no collective" % world,
+                       "numa": ("rank 0 bound to %d CPUs local to its GPU" % len(numa_cpus)) if numa_cpus else "no binding"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,

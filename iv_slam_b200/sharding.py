@@ -44,3 +44,26 @@ def gather_counts(local_counts, total, rank, world, device="cpu"):
         rs, re = frame_range(r, world, total)
         full[rs:re] = outs[r][:re - rs].cpu().numpy()
     return full
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restricts this process to the CPUs that are local to GPU `device_index` (NVML's CPU affinity mask), so that the
+    pinned host buffers it allocates afterwards live on that GPU's NUMA node and the H2D / D2H copies of different
+    ranks do not share one socket's memory controllers and inter-socket links.  Returns the CPU list, or None when NVML
+    or the affinity call is unavailable (single-socket boxes: nothing to do)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        return None
+    return None
