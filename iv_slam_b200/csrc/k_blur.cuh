@@ -7,9 +7,9 @@
 //   stage       tile + halo (160 x 70 bytes) lands in shared memory through ONE TMA box load (cp.async.bulk.tensor.3d over
 //               x, y, frame; out-of-image bytes arrive as zeros) signalled on an mbarrier; only tiles that touch an image
 //               edge then patch their halo by reflection from the bytes already in shared memory;
-//   horizontal  4 pixels per thread in packed 16-bit lanes: the row sums are < 2^16, so one IMAD on a register holding
-//               two pixels (x, x+2) is two exact multiply-adds — 8 masked funnel-shifted windows feed both the even
-//               and the odd pixel pair (28 instructions per 4 pixels);
+//   horizontal  4 pixels per thread with DP4A on byte windows: the Q8 taps fit a byte, so h(x) is two 4-byte dot products
+//               ({18,34,48,56} and {48,34,18,0}) over windows cut out of three loaded words by funnel shifts
+//               (6 SHF + 8 IDP.4A per 4 pixels); the row sums are < 2^16 and are stored two per word;
 //   vertical    4 pixels x 8 rows per thread from the packed 16-bit plane, one aligned 32-bit store per row.
 #pragma once
 #include "common.cuh"
@@ -82,19 +82,19 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs, const __grid_consta
   }
   __syncthreads();
 
-  const uint32_t M = 0x00FF00FFu;
   for (int i = tid; i < BL_PH * (BL_W / 4); i += 256) {
     const int r = i / (BL_W / 4), g = i - r * (BL_W / 4);
     const uint32_t* w = spx + r * BL_PW + (BL_X0 / 4 - 1) + g;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];        // pixels x-4..x-1, x..x+3, x+4..x+7
-    const uint32_t G0 = __funnelshift_r(w0, w1, 8) & M, G1 = __funnelshift_r(w0, w1, 16) & M, G2 = __funnelshift_r(w0, w1, 24) & M;
-    const uint32_t G3 = w1 & M;
-    const uint32_t G4 = __funnelshift_r(w1, w2, 8) & M, G5 = __funnelshift_r(w1, w2, 16) & M, G6 = __funnelshift_r(w1, w2, 24) & M;
-    const uint32_t G7 = w2 & M;
-    // lanes of G_j: pixels (x-3+j, x-1+j)
-    const uint32_t hE = 18u * (G0 + G6) + 34u * (G1 + G5) + 48u * (G2 + G4) + 56u * G3;   // h(x), h(x+2)
-    const uint32_t hO = 18u * (G1 + G7) + 34u * (G2 + G6) + 48u * (G3 + G5) + 56u * G4;   // h(x+1), h(x+3)
-    shs[i] = make_uint2(hE, hO);
+    // DP4A on byte windows: h(x+j) = {18,34,48,56} . p[x+j-3 .. x+j] + {48,34,18,0} . p[x+j+1 .. x+j+4]
+    const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
+    const uint32_t a0 = __funnelshift_r(w0, w1, 8), a1 = __funnelshift_r(w0, w1, 16), a2 = __funnelshift_r(w0, w1, 24);   // windows starting at x-3, x-2, x-1
+    const uint32_t b0 = __funnelshift_r(w1, w2, 8), b1 = __funnelshift_r(w1, w2, 16), b2 = __funnelshift_r(w1, w2, 24);   // windows starting at x+1, x+2, x+3
+    const uint32_t h0 = __dp4a(b0, KB, __dp4a(a0, KA, 0u));
+    const uint32_t h1 = __dp4a(b1, KB, __dp4a(a1, KA, 0u));
+    const uint32_t h2 = __dp4a(b2, KB, __dp4a(a2, KA, 0u));
+    const uint32_t h3 = __dp4a(w2, KB, __dp4a(w1, KA, 0u));
+    shs[i] = make_uint2(h0 | (h2 << 16), h1 | (h3 << 16));   // (h(x), h(x+2)), (h(x+1), h(x+3)): each < 2^16
   }
   __syncthreads();
 
