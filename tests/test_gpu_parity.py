@@ -40,7 +40,7 @@ def _check_frame(api, oracle, gL, gR, oL, oR, left, right, cost, mbf, maxD, what
     fr = assert_descriptors_close(dR, r["dR"], what + " right")
     n = kL.size
     assert_stereo_close(u[:n], d[:n], r["uRight"], r["depth"], what)
-    assert (u[n:] == -1).all() or n == u.size or True
+    assert (u[n:] == -1).all() and (d[n:] == -1).all(), "%s slots past the keypoint count must read as no match" % what
     return dict(n=n, matched=int((r["uRight"] >= 0).sum()), desc_identical=(fl, fr))
 
 
