@@ -6,8 +6,9 @@ from iv_slam_b200 import api, synthetic as S
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-L, R = S.make_stereo_batch(1241, 376, n, 100, distinct=16)
-a = (2000, 1.2, 8, 20, 7)
+W, H, NF = (int(v) for v in sys.argv[3:6]) if len(sys.argv) > 5 else (1241, 376, 2000)
+L, R = S.make_stereo_batch(W, H, n, 100, distinct=min(16, n))
+a = (NF, 1.2, 8, 20, 7)
 gL, gR = api.ORBextractor(*a), api.ORBextractor(*a)
 gL.upload(L); gR.upload(R)
 def step():
