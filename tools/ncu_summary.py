@@ -1,6 +1,6 @@
 """Post-process a full ncu capture (developer tool, runs where ncu is installed, no GPU needed):
    ncu_summary.py <report.ncu-rep> <images per launch> <summary.csv> <dram_bytes_per_image.json>"""
-import csv, io, json, subprocess, sys
+import csv, io, json, re, subprocess, sys
 rep, n_img, out_csv, out_json = sys.argv[1], int(sys.argv[2]), sys.argv[3], sys.argv[4]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -15,7 +15,7 @@ def to_bytes(v, u):
 for r in data:
     if len(r) <= max(idx):
         continue
-    name = r[idx[0]].split('(')[0]
+    name = re.sub(r'<.*>', '', r[idx[0]].split('(')[0].replace('void ', ''))
     key = (name, r[hdr.index('Grid Size')] if 'Grid Size' in hdr else '')
     if key in seen:            # left and right eye launch the same kernels: keep the first of each shape
         continue
