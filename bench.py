@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="stereo pairs per launch group")
     ap.add_argument("--slots", type=int, default=2)
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic base images per rank")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="pairs in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="pairs in the cpu_baseline sample (1024 pairs = ~17 CPU-seconds)")
     ap.add_argument("--ref-sample", type=int, default=128, help="pairs per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -325,7 +325,7 @@ def main():
             one_pair(i)
         line["single_pair_latency_ms"] = 1e3 * (time.perf_counter() - t1) / 50
         lL.close(); lR.close()
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N=1 only
             ncpu = os.cpu_count() or 1
             n_s = min(args.cpu_sample, B)
             fps_all, dt_all, _, _ = cpu_frontend_fps(Lh[:n_s], Rh[:n_s], ncpu)
