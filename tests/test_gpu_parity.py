@@ -517,3 +517,22 @@ def test_n2_without_stereo_and_offset_bounds(gpu_api, oracle):
     got, nm = g.search_by_projection_last(sc["world"], sc["desc"], sc["octave"], sc["angle"], sc["flags"], sc["Rcw"], sc["tcw"], sc["cam"], bounds, 0, 15.0, True)
     assert nm == nm_want and np.array_equal(got[:kps.size], want)
     assert nm_want > 100
+
+
+@pytest.mark.parametrize("w,h,nf,sf,nl", [(640, 480, 500, 1.2, 1),        # a single level: no resize at all
+                                           (1600, 1200, 3000, 1.1, 12),    # the maximum number of levels
+                                           (900, 700, 60, 2.0, 3),         # very few features, coarse pyramid
+                                           (512, 512, 1500, 1.2, 8)])      # square image: transposed grid aspect
+def test_extreme_parameters(gpu_api, oracle, w, h, nf, sf, nl):
+    left, right = S.make_stereo_pair(w, h, w + nl)
+    g = _pair(gpu_api, oracle, nf, 20, 7, False, sf, nl)
+    try:
+        g[2](left)
+        ok = True
+    except Exception:
+        ok = False
+    if not ok:
+        with pytest.raises(gpu_api.IvgError):
+            g[0](left)
+        return
+    _check_frame(gpu_api, oracle, *g, left, right, None, 150.0, 500.0, "%dx%d nf%d sf%.1f nl%d" % (w, h, nf, sf, nl))
