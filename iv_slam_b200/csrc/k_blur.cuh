@@ -10,7 +10,8 @@
 //   horizontal  4 pixels per thread with DP4A on byte windows: the Q8 taps fit a byte, so h(x) is two 4-byte dot products
 //               ({18,34,48,56} and {48,34,18,0}) over windows cut out of three loaded words by funnel shifts
 //               (6 SHF + 8 IDP.4A per 4 pixels); the row sums are < 2^16 and are stored two per word;
-//   vertical    4 pixels x 8 rows per thread from the packed 16-bit plane, one aligned 32-bit store per row.
+//   vertical    4 pixels x 8 rows per thread: the row sums of two vertically adjacent rows share a word, so IDP.2A (two
+//               16-bit x 8-bit products) takes a 7-tap column sum in four instructions; one aligned 32-bit store per row.
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"
@@ -33,7 +34,7 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs, const __grid_constant__ TmaMaps maps) {
   __shared__ __align__(128) uint32_t spx[BL_PH * BL_PW];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ __align__(16) uint2 shs[BL_PH * (BL_W / 4)];
+  __shared__ __align__(16) uint32_t shs[(BL_PH / 2) * BL_W];      // row sums, two vertically adjacent rows per word
 
   const uint32_t tt = __ldg(fs.blurTiles + blockIdx.x);       // host-built tile table: level | tile x | tile y
   const int level = tt >> 28;
@@ -82,46 +83,53 @@ __global__ void __launch_bounds__(256) k_gauss7(FrameSet fs, const __grid_consta
   }
   __syncthreads();
 
-  for (int i = tid; i < BL_PH * (BL_W / 4); i += 256) {
-    const int r = i / (BL_W / 4), g = i - r * (BL_W / 4);
-    const uint32_t* w = spx + r * BL_PW + (BL_X0 / 4 - 1) + g;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];        // pixels x-4..x-1, x..x+3, x+4..x+7
-    // DP4A on byte windows: h(x+j) = {18,34,48,56} . p[x+j-3 .. x+j] + {48,34,18,0} . p[x+j+1 .. x+j+4]
+  // horizontal: one item = two staged rows (2p, 2p+1) x 4 columns; the two rows' sums go into one word per column
+  // (row 2p in the low half), which is the operand layout of IDP.2A in the vertical pass
+  for (int i = tid; i < (BL_PH / 2) * (BL_W / 4); i += 256) {
+    const int p = i / (BL_W / 4), g = i - p * (BL_W / 4);
     const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
-    const uint32_t a0 = __funnelshift_r(w0, w1, 8), a1 = __funnelshift_r(w0, w1, 16), a2 = __funnelshift_r(w0, w1, 24);   // windows starting at x-3, x-2, x-1
-    const uint32_t b0 = __funnelshift_r(w1, w2, 8), b1 = __funnelshift_r(w1, w2, 16), b2 = __funnelshift_r(w1, w2, 24);   // windows starting at x+1, x+2, x+3
-    const uint32_t h0 = __dp4a(b0, KB, __dp4a(a0, KA, 0u));
-    const uint32_t h1 = __dp4a(b1, KB, __dp4a(a1, KA, 0u));
-    const uint32_t h2 = __dp4a(b2, KB, __dp4a(a2, KA, 0u));
-    const uint32_t h3 = __dp4a(w2, KB, __dp4a(w1, KA, 0u));
-    shs[i] = make_uint2(h0 | (h2 << 16), h1 | (h3 << 16));   // (h(x), h(x+2)), (h(x+1), h(x+3)): each < 2^16
+    uint32_t h[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const uint32_t* w = spx + (2 * p + rr) * BL_PW + (BL_X0 / 4 - 1) + g;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];        // pixels x-4..x-1, x..x+3, x+4..x+7
+      // DP4A on byte windows: h(x+j) = {18,34,48,56} . p[x+j-3 .. x+j] + {48,34,18,0} . p[x+j+1 .. x+j+4]
+      h[rr][0] = __dp4a(__funnelshift_r(w1, w2, 8), KB, __dp4a(__funnelshift_r(w0, w1, 8), KA, 0u));
+      h[rr][1] = __dp4a(__funnelshift_r(w1, w2, 16), KB, __dp4a(__funnelshift_r(w0, w1, 16), KA, 0u));
+      h[rr][2] = __dp4a(__funnelshift_r(w1, w2, 24), KB, __dp4a(__funnelshift_r(w0, w1, 24), KA, 0u));
+      h[rr][3] = __dp4a(w2, KB, __dp4a(w1, KA, 0u));
+    }
+    reinterpret_cast<uint4*>(shs)[i] = make_uint4(h[0][0] | (h[1][0] << 16), h[0][1] | (h[1][1] << 16), h[0][2] | (h[1][2] << 16), h[0][3] | (h[1][3] << 16));
   }
   __syncthreads();
 
   uint8_t* dst = fs.blur + frameOff;
   {
-    const int g = tid & 31, seg = tid >> 5;                 // 32 column groups x 8 row segments of 4 rows
+    const int g = tid & 31, seg = tid >> 5;                 // 32 column groups x 8 row segments of 8 rows
     const int gx = x0 + 4 * g;
     if (gx < L.pitch) {
-      uint32_t e[BL_RPS + 6], o[BL_RPS + 6];
+      // vertical: output row rr needs staged rows rr..rr+6 = four row pairs; IDP.2A multiplies the two 16-bit halves of a
+      // pair word by two byte weights, so a 7-tap column sum is four instructions whatever the parity of rr
+      const uint32_t WE = 18u | (34u << 8) | (48u << 16) | (56u << 24), WE2 = 48u | (34u << 8) | (18u << 16);
+      const uint32_t WO = (18u << 8) | (34u << 16) | (48u << 24), WO2 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+      uint4 P[BL_RPS / 2 + 3];
 #pragma unroll
-      for (int j = 0; j < BL_RPS + 6; ++j) { const uint2 v = shs[(seg * BL_RPS + j) * (BL_W / 4) + g]; e[j] = v.x; o[j] = v.y; }
+      for (int j = 0; j < BL_RPS / 2 + 3; ++j) P[j] = reinterpret_cast<const uint4*>(shs)[(seg * (BL_RPS / 2) + j) * (BL_W / 4) + g];
 #pragma unroll
       for (int rr = 0; rr < BL_RPS; ++rr) {
         const int gy = y0 + seg * BL_RPS + rr;
         if (gy >= L.h) break;
+        const int m = rr >> 1;
+        const uint32_t wa = (rr & 1) ? WO : WE, wb = (rr & 1) ? WO2 : WE2;
         uint32_t res[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t hv[7];
-#pragma unroll
-          for (int k = 0; k < 7; ++k) {
-            const uint32_t wv = (q & 1) ? o[rr + k] : e[rr + k];
-            hv[k] = (q & 2) ? (wv >> 16) : (wv & 0xFFFFu);
-          }
-          res[q] = (18u * (hv[0] + hv[6]) + 34u * (hv[1] + hv[5]) + 48u * (hv[2] + hv[4]) + 56u * hv[3] + 32768u) >> 16;
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t p0 = c == 0 ? P[m].x : c == 1 ? P[m].y : c == 2 ? P[m].z : P[m].w;
+          const uint32_t p1 = c == 0 ? P[m + 1].x : c == 1 ? P[m + 1].y : c == 2 ? P[m + 1].z : P[m + 1].w;
+          const uint32_t p2 = c == 0 ? P[m + 2].x : c == 1 ? P[m + 2].y : c == 2 ? P[m + 2].z : P[m + 2].w;
+          const uint32_t p3 = c == 0 ? P[m + 3].x : c == 1 ? P[m + 3].y : c == 2 ? P[m + 3].z : P[m + 3].w;
+          res[c] = __dp2a_hi(p3, wb, __dp2a_lo(p2, wb, __dp2a_hi(p1, wa, __dp2a_lo(p0, wa, 32768u)))) >> 16;
         }
-        // pixel order x, x+1, x+2, x+3 = (E lo, O lo, E hi, O hi) = q 0, 1, 2, 3
         *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = res[0] | (res[1] << 8) | (res[2] << 16) | (res[3] << 24);
       }
     }
