@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, in
   uint8_t* spx = rsm;
   uint16_t* sT = reinterpret_cast<uint16_t*>(rsm + (((size_t)SPB * D.rzRows + 15) & ~(size_t)15));
 
+  // the tile's vertical taps go to shared memory while the source box is in flight: (row offsets into sT, weights)
+  __shared__ int4 sTapY[RZ_H];
   if (useTma) {
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
@@ -70,8 +72,10 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, in
       mbar_expect_tx(&bar, (uint32_t)(SPB * D.rzRows));
       tma_load_3d(spx, &maps.m[level], &bar, sxa, sya, (int)blockIdx.z);
     }
+    if (tid < RZ_H && y0 + tid <= y1) { const ResizeTap t = ty[y0 + tid]; sTapY[tid] = make_int4((t.s0 - sya) * RZ_W, (t.s1 - sya) * RZ_W, t.c0, t.c1); }
     mbar_wait(&bar, 0);
   } else {
+    if (tid < RZ_H && y0 + tid <= y1) { const ResizeTap t = ty[y0 + tid]; sTapY[tid] = make_int4((t.s0 - sya) * RZ_W, (t.s1 - sya) * RZ_W, t.c0, t.c1); }
     for (int i = tid; i < nR * nW; i += 256) {
       const int r = i / nW, g = i - r * nW;
       const int gx = sxa + 4 * g;
@@ -100,10 +104,10 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, in
       for (int rr = 0; rr < RZ_RPS; ++rr) {
         const int y = y0 + seg * RZ_RPS + rr;
         if (y > y1) break;
-        const ResizeTap t = ty[y];
-        const uint2 A = *reinterpret_cast<const uint2*>(sT + (t.s0 - sya) * RZ_W + 4 * g);
-        const uint2 B = *reinterpret_cast<const uint2*>(sT + (t.s1 - sya) * RZ_W + 4 * g);
-        const int b0 = t.c0, b1 = t.c1;
+        const int4 t = sTapY[seg * RZ_RPS + rr];
+        const uint2 A = *reinterpret_cast<const uint2*>(sT + t.x + 4 * g);
+        const uint2 B = *reinterpret_cast<const uint2*>(sT + t.y + 4 * g);
+        const int b0 = t.z, b1 = t.w;
         const int v0 = (((b0 * (int)(A.x & 0xFFFF)) >> 16) + ((b1 * (int)(B.x & 0xFFFF)) >> 16) + 2) >> 2;
         const int v1 = (((b0 * (int)(A.x >> 16)) >> 16) + ((b1 * (int)(B.x >> 16)) >> 16) + 2) >> 2;
         const int v2 = (((b0 * (int)(A.y & 0xFFFF)) >> 16) + ((b1 * (int)(B.y & 0xFFFF)) >> 16) + 2) >> 2;
