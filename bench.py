@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024, help="pairs in the cpu_baseline sample (1024 pairs = ~17 CPU-seconds)")
     ap.add_argument("--ref-sample", type=int, default=128, help="pairs per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-streams", choices=["shared", "per-handle"], default="shared", help="kernel streams of the e2e pipeline")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,7 +205,7 @@ def main():
     pinL.array[...] = Lh
     pinR.array[...] = Rh
 
-    fe = StereoFrontend(params, W, H, args.chunk, args.slots, device=local)
+    fe = StereoFrontend(params, W, H, args.chunk, args.slots, device=local, share_kernel_stream=args.e2e_streams == "shared")
     out = fe.alloc_outputs(B, pinned=True)
 
     # ------------------------------------------------------------------ device-resident arm (`value`)

@@ -12,7 +12,7 @@ from . import api
 
 
 class StereoFrontend:
-    def __init__(self, params, width, height, chunk, slots=3, device=0, introspection=False):
+    def __init__(self, params, width, height, chunk, slots=3, device=0, introspection=False, share_kernel_stream=True):
         """params: dict(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST); chunk = stereo pairs per launch group."""
         self.params, self.w, self.h, self.chunk, self.device = params, width, height, chunk, device
         a = (params["nfeatures"], params["scaleFactor"], params["nlevels"], params["iniThFAST"], params["minThFAST"])
@@ -25,9 +25,10 @@ class StereoFrontend:
             # one kernel stream for everything on this device: kernels of different chunks / eyes never co-run (that
             # costs ~20 % at these sizes); the per-handle copy streams keep H2D/D2H overlapped with the kernels
             owner = self.slots[0][0] if self.slots else left
-            if left is not owner:
-                left.share_stream(owner)
-            right.share_stream(owner)
+            if share_kernel_stream:
+                if left is not owner:
+                    left.share_stream(owner)
+                right.share_stream(owner)
             self.slots.append((left, right))
         self.cap = self.slots[0][0].cap
 
