@@ -60,7 +60,7 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
 }
 
 #ifndef IVG_FC_THREADS
-#define IVG_FC_THREADS 160
+#define IVG_FC_THREADS 128
 #endif
 constexpr int FC_THREADS = IVG_FC_THREADS; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
 constexpr int FC_WARPS = FC_THREADS / 32;
