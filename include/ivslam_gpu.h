@@ -201,6 +201,19 @@ int ivg_search_by_projection_map(ivg_extractor* cur, int index, int n, const flo
                                  const uint8_t* desc, const uint8_t* flags, const uint8_t* cur_blocked, float minX, float maxX, float minY,
                                  float maxY, float th, float nnratio, int* match, int cap, int* nmatches);
 
+/* ivg_search_by_bow = ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ *   (src/ORBmatcher.cc:165-294) on frame `index` (F).  The caller walks the two DBoW2 feature vectors as the reference does
+ *   (:185-282) and hands over, in that traversal order, the key-frame keypoints of the shared vocabulary nodes: desc =
+ *   pKF->mDescriptors.row(realIdxKF), angle = pKF->mvKeysUn[realIdxKF].angle, flags bit0 = pMP && !pMP->isBad(),
+ *   node_slot[i] = which of F's node lists the point is matched against; F's lists as CSR (node_start[n_nodes + 1],
+ *   node_idx = the vIndicesF entries).  Any keypoint assigned is skipped by all later points (:219-220); acceptance is
+ *   bestDist1 <= TH_LOW (50) && bestDist1 < nnratio * bestDist2; then the rotation-histogram vote.  match / nmatches as
+ *   above (match[i2] = index of the point, i.e. vpMapPointMatches[i2] = vpMapPointsKF[realIdxKF of that point]).
+ *   Does not need the grid. */
+int ivg_search_by_bow(ivg_extractor* cur, int index, int n, const uint8_t* desc, const float* angle, const uint8_t* flags, const int* node_slot,
+                      int n_nodes, const int* node_start, const int* node_idx, float nnratio, int check_orientation, int* match, int cap,
+                      int* nmatches);
+
 /* ---- measurement helpers (bench.py) ---- */
 /* CUDA-event timer on the handle's stream: start records an event, stop records another, elapsed waits for it. */
 int ivg_timer_start(ivg_extractor* h);

@@ -70,6 +70,7 @@ def lib():
         "ivg_set_rectify_maps": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, sz]),
         "ivg_search_by_projection_last": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp] + [C.c_float] * 9 +
                                           [C.c_int, C.c_float, C.c_int, vp, C.c_int, i32p]),
+        "ivg_search_by_bow": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, vp, C.c_int, i32p]),
         "ivg_search_by_projection_map": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp] + [C.c_float] * 6 + [vp, C.c_int, i32p]),
         "ivg_upload_batch_raw": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, C.c_int, C.c_int, vp, sz, sz]),
         "ivg_run_batch": (C.c_int, [vp]),
@@ -334,6 +335,19 @@ class ORBextractor:
         _ck(lib().ivg_search_by_projection_map(self._h, index, n, _p(proj), _p(view_cos), _p(level), _p(desc), _p(flags), _p(cur_blocked),
                                                *[float(v) for v in bounds], float(th), float(nnratio), _p(match), self.cap, C.byref(nm)),
             "ivg_search_by_projection_map")
+        return match, nm.value
+
+    def search_by_bow(self, desc, angle, flags, node_slot, node_start, node_idx, nnratio=0.7, check_orientation=True, index=0):
+        """N2: ORBmatcher::SearchByBoW(pKF, F, matches) on frame `index`; points in the reference's traversal order."""
+        f32, i32, u8 = np.float32, np.int32, np.uint8
+        desc, angle, flags = np.ascontiguousarray(desc, u8), np.ascontiguousarray(angle, f32), np.ascontiguousarray(flags, u8)
+        node_slot, node_start, node_idx = (np.ascontiguousarray(a, i32) for a in (node_slot, node_start, node_idx))
+        n = flags.size
+        assert desc.shape == (n, 32) and angle.size == n and node_slot.size == n and node_start.size >= 1
+        match = np.zeros(self.cap, i32)
+        nm = C.c_int(0)
+        _ck(lib().ivg_search_by_bow(self._h, index, n, _p(desc), _p(angle), _p(flags), _p(node_slot), node_start.size - 1, _p(node_start),
+                                    _p(node_idx), float(nnratio), int(bool(check_orientation)), _p(match), self.cap, C.byref(nm)), "ivg_search_by_bow")
         return match, nm.value
 
     def upload_device(self, n, width, height, d_images, d_masks=None):

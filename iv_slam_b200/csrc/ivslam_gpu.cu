@@ -26,6 +26,7 @@
 #include "k_octree.cuh"
 #include "k_prologue.cuh"
 #include "k_project.cuh"
+#include "k_bow.cuh"
 #include "k_stereo.cuh"
 
 using namespace ivg;
@@ -874,6 +875,59 @@ int ivg_search_by_projection_map(ivg_extractor* cur, int index, int n, const flo
   A.pdesc = b + oD; A.flags = b + oF; A.curBlocked = cur_blocked ? b + oB : nullptr;
   A.mode = 3; A.th = th; A.nnratio = nnratio; A.checkOri = 0;
   return proj_common(cur, index, A, n, minX, maxX, minY, maxY, match, cap, nmatches);
+}
+
+int ivg_search_by_bow(ivg_extractor* cur, int index, int n, const uint8_t* desc, const float* angle, const uint8_t* flags, const int* node_slot,
+                      int n_nodes, const int* node_start, const int* node_idx, float nnratio, int check_orientation, int* match, int cap,
+                      int* nmatches) {
+  if (!cur || n < 0 || n_nodes < 0 || !match || !nmatches || (n > 0 && (!desc || !angle || !flags || !node_slot)) ||
+      (n_nodes > 0 && (!node_start || !node_idx)))
+    return IVG_ERR_INVALID;
+  if (!cur->haveResults) return IVG_ERR_STATE;
+  if (index < 0 || index >= cur->curBatch) return IVG_ERR_INVALID;
+  if (cap < cur->fs.kpCap) return IVG_ERR_CAPACITY;
+  CK(cudaSetDevice(cur->device));
+  const int K = cur->fs.kpCap;
+  const int total = n_nodes > 0 ? node_start[n_nodes] : 0;
+  if (total < 0) return IVG_ERR_INVALID;
+  // points grouped by node slot, caller's order kept inside a slot (nodes never interact: a keypoint of F is in one node)
+  std::vector<int> ptStart((size_t)n_nodes + 1, 0), ptIdx((size_t)std::max(n, 1));
+  for (int i = 0; i < n; ++i) if (node_slot[i] >= 0 && node_slot[i] < n_nodes) ++ptStart[(size_t)node_slot[i] + 1];
+  for (int s = 0; s < n_nodes; ++s) ptStart[(size_t)s + 1] += ptStart[s];
+  {
+    std::vector<int> cur_(ptStart.begin(), ptStart.end() - 1);
+    for (int i = 0; i < n; ++i) if (node_slot[i] >= 0 && node_slot[i] < n_nodes) ptIdx[(size_t)cur_[node_slot[i]]++] = i;
+  }
+  ProjUpload up{cur};
+  const size_t oD = up.add(desc, (size_t)n * 32), oA = up.add(angle, (size_t)n * 4), oF = up.add(flags, (size_t)n),
+               oNS = up.add(node_start, (size_t)(n_nodes + 1) * 4), oNI = up.add(node_idx, (size_t)total * 4),
+               oPS = up.add(ptStart.data(), ptStart.size() * 4), oPI = up.add(ptIdx.data(), (size_t)n * 4);
+  int rc = up.commit();
+  if (rc) return rc;
+  if ((rc = cur->projInt.alloc((size_t)K + 64 + 2 * (size_t)std::max(n, 1)))) return rc;
+  BowArgs A{};
+  const uint8_t* b = cur->projIn.p;
+  A.kp = cur->outKp.p; A.desc = cur->outDesc.p; A.nPtr = cur->outN.p; A.index = index; A.cap = K;
+  A.n = n; A.pdesc = b + oD; A.angle = reinterpret_cast<const float*>(b + oA); A.flags = b + oF;
+  A.nNodes = n_nodes; A.nodeStart = reinterpret_cast<const int*>(b + oNS); A.nodeIdx = reinterpret_cast<const int*>(b + oNI);
+  A.ptStart = reinterpret_cast<const int*>(b + oPS); A.ptIdx = reinterpret_cast<const int*>(b + oPI);
+  A.nnratio = nnratio; A.checkOri = check_orientation != 0;
+  int* ip = cur->projInt.p;                   // layout: match[K] | nmatches | hist[30] (+pad to 64) | accIdx[n] | accBin[n bytes]
+  A.match = ip; A.nmatches = ip + K; A.hist = ip + K + 1; A.accIdx = ip + K + 64; A.accBin = reinterpret_cast<int8_t*>(ip + K + 64 + n);
+  CK(cudaMemsetAsync(ip, 0xFF, (size_t)K * 4, cur->stream));                        // match = -1
+  CK(cudaMemsetAsync(ip + K, 0, 64 * 4, cur->stream));                             // nmatches, hist = 0
+  if (n > 0) CK(cudaMemsetAsync(A.accBin, 0xFF, (size_t)n, cur->stream));            // accBin = -1
+  if (n_nodes > 0 && n > 0) { ProfScope ps(cur, IVG_K_PROJ_CAND); k_bow_match<<<(n_nodes + 7) / 8, 256, 0, cur->stream>>>(A); }
+  { ProfScope ps(cur, IVG_K_PROJ_RESOLVE); k_bow_finish<<<1, 256, 0, cur->stream>>>(A); }
+  CK(cudaGetLastError());
+  const size_t outBytes = ((size_t)K + 1) * sizeof(int);
+  if (cur->projHostBytes < outBytes) return IVG_ERR_STATE;     // sized by ProjUpload::commit
+  CK(cudaMemcpyAsync(cur->projHost, A.match, outBytes, cudaMemcpyDeviceToHost, cur->stream));   // match[K] and nmatches are contiguous
+  CK(cudaStreamSynchronize(cur->stream));
+  std::memcpy(match, cur->projHost, (size_t)K * sizeof(int));
+  *nmatches = ((const int*)cur->projHost)[K];
+  for (int i = K; i < cap; ++i) match[i] = -1;
+  return IVG_OK;
 }
 
 // ---------------------------------------------------------------------------------------- N4: input prologue

@@ -1090,6 +1090,53 @@ static int search_by_projection_map(const ProjFrame& F, int n, const float* proj
   return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  src/ORBmatcher.cc:165-294, flattened: the points are the
+// key-frame keypoints of the shared vocabulary nodes in the reference's traversal order, nodeSlot[i] selects F's list.
+static int search_by_bow(const KeyPoint* kpsF, int N, const uint8_t* descF, int n, const uint8_t* desc, const float* angle, const uint8_t* flags,
+                         const int* nodeSlot, int nNodes, const int* nodeStart, const int* nodeIdx, float nnratio, int checkOri, int* match) {
+  const int HISTO_LENGTH = 30;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  for (int i = 0; i < N; ++i) match[i] = -1;
+  int nmatches = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!(flags[i] & 1)) continue;                       // !pMP || pMP->isBad()
+    const int slot = nodeSlot[i];
+    if (slot < 0 || slot >= nNodes) continue;
+    int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+    for (int j = nodeStart[slot]; j < nodeStart[slot + 1]; ++j) {
+      const int realIdxF = nodeIdx[j];
+      if (realIdxF < 0 || realIdxF >= N) continue;
+      if (match[realIdxF] >= 0) continue;               // vpMapPointMatches[realIdxF] already set
+      const int dist = descriptor_distance(desc + 32 * (size_t)i, descF + 32 * (size_t)realIdxF);
+      if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+      else if (dist < bestDist2) bestDist2 = dist;
+    }
+    if (bestDist1 <= TH_LOW) {
+      if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+        match[bestIdxF] = i;
+        if (checkOri) {
+          float rot = angle[i] - kpsF[bestIdxF].angle;
+          if (rot < 0.0) rot += 360.0f;
+          int bin = round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          rotHist[bin].push_back(bestIdxF);
+        }
+        nmatches++;
+      }
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { match[idx] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
 extern "C" {
 
 void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstride, uint8_t* dst, int dw, int dh, size_t dstride) {
@@ -1263,6 +1310,11 @@ int orc_search_by_projection_map(const void* kps, int N, const uint8_t* descCur,
                                  const uint8_t* curBlocked, float th, float nnratio, int* match) {
   ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale};
   return search_by_projection_map(F, n, proj, viewCos, level, desc, flags, curBlocked, th, nnratio, match);
+}
+
+int orc_search_by_bow(const void* kpsF, int N, const uint8_t* descF, int n, const uint8_t* desc, const float* angle, const uint8_t* flags,
+                      const int* nodeSlot, int nNodes, const int* nodeStart, const int* nodeIdx, float nnratio, int checkOri, int* match) {
+  return search_by_bow((const KeyPoint*)kpsF, N, descF, n, desc, angle, flags, nodeSlot, nNodes, nodeStart, nodeIdx, nnratio, checkOri, match);
 }
 
 }  // extern "C"

@@ -102,6 +102,8 @@ def lib():
     L.orc_search_by_projection_last.restype = C.c_int
     L.orc_search_by_projection_map.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]
     L.orc_search_by_projection_map.restype = C.c_int
+    L.orc_search_by_bow.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, vp]
+    L.orc_search_by_bow.restype = C.c_int
     L.orc_transform_point.argtypes = [vp, vp, vp, vp]
     L.orc_transform_point.restype = None
     L.orc_prologue.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]
@@ -162,6 +164,17 @@ def search_by_projection_map(kps, desc_cur, uRight, grid_start, grid_idx, scale,
     nm = lib().orc_search_by_projection_map(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), *[float(v) for v in bounds],
                                             a[9].size, _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(a[9]), _p(cb) if cb is not None else None,
                                             float(th), float(nnratio), _p(match))
+    return match[:kps.size], nm
+
+
+def search_by_bow(kps, desc_cur, desc, angle, flags, node_slot, node_start, node_idx, nnratio=0.7, check_orientation=True):
+    """N2 restatement of ORBmatcher::SearchByBoW(pKF, F, matches) on flattened inputs: (match[N], nmatches)."""
+    f32, i32, u8 = np.float32, np.int32, np.uint8
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    a = [np.ascontiguousarray(x, t) for x, t in ((desc_cur, u8), (desc, u8), (angle, f32), (flags, u8), (node_slot, i32), (node_start, i32), (node_idx, i32))]
+    match = np.zeros(max(kps.size, 1), i32)
+    nm = lib().orc_search_by_bow(_p(kps), kps.size, _p(a[0]), a[3].size, _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), a[5].size - 1, _p(a[5]), _p(a[6]),
+                                 float(nnratio), int(bool(check_orientation)), _p(match))
     return match[:kps.size], nm
 
 

@@ -98,3 +98,29 @@ def projection_scenario(kps_last, desc_last, depth_last, w, h, seed, n_dup=150):
     level = np.clip(octave + rng.integers(-1, 2, octave.size), 0, 7).astype(np.int32)
     return dict(world=world, desc=desc, octave=octave, angle=angle, flags=flags, Rcw=Rcw, tcw=tcw, proj=proj, mflags=mflags.astype(np.uint8),
                 view_cos=view_cos, level=level, cam=(c["fx"], c["fy"], c["cx"], c["cy"], c["mbf"]), bounds=(0.0, float(w), 0.0, float(h)))
+
+
+def bow_scenario(desc_kf, angle_kf, desc_f, seed, node_bits=6):
+    """Flattened SearchByBoW inputs.  A stand-in for the DBoW2 feature vectors: the 'vocabulary node' of a descriptor is
+    the top `node_bits` bits of its first byte (64 nodes by default, tens of keypoints each; matching keypoints mostly share
+    it; 3 bits give lists of hundreds of keypoints, longer than the kernel's shared-memory cache).  Points = the key-frame
+    keypoints in the reference's traversal order (nodes ascending, indices ascending inside a node); node lists of the
+    frame as CSR; nodes only the key frame has get slot -1 (the reference never visits them)."""
+    rng = np.random.default_rng(seed)
+    n_nodes = 1 << node_bits
+    node_f = (desc_f[:, 0] >> (8 - node_bits)).astype(np.int64)
+    node_kf = (desc_kf[:, 0] >> (8 - node_bits)).astype(np.int64)
+    present = np.unique(node_f)
+    slot_of = -np.ones(n_nodes, np.int64)
+    slot_of[present] = np.arange(present.size)
+    node_start = np.zeros(present.size + 1, np.int32)
+    node_idx = []
+    for s, nd in enumerate(present):
+        idx = np.nonzero(node_f == nd)[0]
+        node_idx.append(idx)
+        node_start[s + 1] = node_start[s] + idx.size
+    node_idx = np.concatenate(node_idx).astype(np.int32) if node_idx else np.zeros(0, np.int32)
+    order = np.lexsort((np.arange(desc_kf.shape[0]), node_kf))              # nodes ascending, index ascending
+    flags = (rng.random(order.size) > 0.15).astype(np.uint8)               # pMP && !isBad
+    return dict(desc=desc_kf[order], angle=angle_kf[order].astype(np.float32), flags=flags, node_slot=slot_of[node_kf[order]].astype(np.int32),
+                node_start=node_start, node_idx=node_idx, order=order)

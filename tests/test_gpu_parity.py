@@ -536,3 +536,18 @@ def test_extreme_parameters(gpu_api, oracle, w, h, nf, sf, nl):
             g[0](left)
         return
     _check_frame(gpu_api, oracle, *g, left, right, None, 150.0, 500.0, "%dx%d nf%d sf%.1f nl%d" % (w, h, nf, sf, nl))
+
+
+@pytest.mark.parametrize("ratio,ori,bits", [(0.7, True, 6), (0.9, True, 6), (0.75, False, 6), (0.8, True, 3), (0.7, True, 8)])
+def test_n2_search_by_bow(gpu_api, oracle, ratio, ori, bits):
+    from helpers import bow_scenario
+    w, h, nf = 1241, 376, 2000
+    left, _ = S.make_stereo_pair(w, h, 95)
+    k_kf, d_kf = oracle.OracleExtractor(nf, 1.2, 8, 20, 7)(left)
+    g = gpu_api.ORBextractor(nf, 1.2, 8, 20, 7)
+    k_f, d_f = g(np.roll(left, 3, axis=1))
+    sc = bow_scenario(d_kf, k_kf["angle"], d_f, 11, bits)
+    want, nm_want = oracle.search_by_bow(k_f, d_f, sc["desc"], sc["angle"], sc["flags"], sc["node_slot"], sc["node_start"], sc["node_idx"], ratio, ori)
+    got, nm = g.search_by_bow(sc["desc"], sc["angle"], sc["flags"], sc["node_slot"], sc["node_start"], sc["node_idx"], ratio, ori)
+    assert nm == nm_want and np.array_equal(got[:k_f.size], want), "%d assignments differ" % int((got[:k_f.size] != want).sum())
+    assert (got[k_f.size:] == -1).all() and nm_want > 400

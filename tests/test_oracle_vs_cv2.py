@@ -337,3 +337,59 @@ def test_search_by_projection_oracle_matches_python_restatement(oracle):
                                                sc["mflags"], cur_blocked, th, 0.8)
         assert n == nm and np.array_equal(m, match), "local-map variant th %.0f" % th
         assert nm > 20
+
+
+def test_search_by_bow_oracle_matches_python_restatement(oracle):
+    """Independent Python restatement of ORBmatcher::SearchByBoW(pKF, F, matches) (src/ORBmatcher.cc:165-294)."""
+    from helpers import bow_scenario
+    f = np.float32
+    w, h = 620, 300
+    left, _ = S.make_stereo_pair(w, h, 73)
+    e = oracle.OracleExtractor(600, 1.2, 8, 20, 7)
+    k_kf, d_kf = e(left)
+    k_f, d_f = e(np.roll(left, 2, axis=1))
+    sc = bow_scenario(d_kf, k_kf["angle"], d_f, 7)
+    for ratio, ori in ((0.7, True), (0.9, False)):
+        match = np.full(k_f.size, -1, np.int32)
+        hist = [[] for _ in range(30)]
+        nm = 0
+        for i in range(sc["flags"].size):
+            s = sc["node_slot"][i]
+            if not sc["flags"][i] & 1 or s < 0:
+                continue
+            b1, b2, bi = 256, 256, -1
+            for j in range(sc["node_start"][s], sc["node_start"][s + 1]):
+                idx = int(sc["node_idx"][j])
+                if match[idx] >= 0:
+                    continue
+                d = _popcount_rows(sc["desc"][i], d_f[idx])
+                if d < b1:
+                    b2, b1, bi = b1, d, idx
+                elif d < b2:
+                    b2 = d
+            if b1 <= 50 and f(b1) < f(f(ratio) * f(b2)):
+                match[bi] = i
+                nm += 1
+                if ori:
+                    rot = f(sc["angle"][i] - k_f["angle"][bi])
+                    if rot < 0:
+                        rot = f(rot + f(360))
+                    b = int(np.floor(f(rot * f(1.0 / 30)) + 0.5))
+                    hist[0 if b == 30 else b].append(bi)
+        if ori:
+            sizes = [len(x) for x in hist]
+            order = sorted(range(30), key=lambda b: (-sizes[b], b))
+            keep = {order[0]}
+            if not sizes[order[1]] < 0.1 * sizes[order[0]]:
+                keep.add(order[1])
+                if not sizes[order[2]] < 0.1 * sizes[order[0]]:
+                    keep.add(order[2])
+            keep = {b for b in keep if sizes[b] > 0}
+            for b in range(30):
+                if b not in keep:
+                    for idx in hist[b]:
+                        match[idx] = -1
+                        nm -= 1
+        m, n = oracle.search_by_bow(k_f, d_f, sc["desc"], sc["angle"], sc["flags"], sc["node_slot"], sc["node_start"], sc["node_idx"], ratio, ori)
+        assert n == nm and np.array_equal(m, match), "ratio %.1f" % ratio
+        assert nm > 100

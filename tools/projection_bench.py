@@ -38,3 +38,21 @@ for label, ndup in (("tracking-like (no duplicated points)", 0), ("adversarial (
     p = gL.profile_read()
     print("kernel time per call: candidates %.1f us, resolve %.1f us" % (p["k_proj_candidates"][0] * 1e3 / 20, p["k_proj_resolve"][0] * 1e3 / 20))
     gL.profile_enable(False)
+
+# SearchByBoW (key frame = the last frame's keypoints, vocabulary nodes simulated by the first descriptor byte)
+from helpers import bow_scenario
+sc = bow_scenario(last["dL"], last["kL"]["angle"], dcur, 3, 7)      # 128 nodes: DBoW2's level-4 nodes hold tens of keypoints
+g_ms, (gm, gn) = timeit(lambda: gL.search_by_bow(sc["desc"], sc["angle"], sc["flags"], sc["node_slot"], sc["node_start"], sc["node_idx"], 0.7, True), 200)
+c_ms, (cm, cn) = timeit(lambda: O.search_by_bow(kps, dcur, sc["desc"], sc["angle"], sc["flags"], sc["node_slot"], sc["node_start"], sc["node_idx"], 0.7, True), 200)
+print("SearchByBoW:        %d points, %d matches | device %.3f ms per call | CPU oracle %.3f ms | equal %s" % (sc["flags"].size, gn, g_ms, c_ms, bool(gn == cn and np.array_equal(gm[:kps.size], cm))))
+gL.profile_enable(True)
+for _ in range(20):
+    gL.search_by_bow(sc["desc"], sc["angle"], sc["flags"], sc["node_slot"], sc["node_start"], sc["node_idx"], 0.7, True)
+p = gL.profile_read()
+print("SearchByBoW kernel time per call: match %.1f us, finish %.1f us; node sizes: max %d candidates" % (p["k_proj_candidates"][0] * 1e3 / 20, p["k_proj_resolve"][0] * 1e3 / 20, int(np.diff(sc["node_start"]).max())))
+gL.profile_enable(False)
+import time as _t
+t = _t.perf_counter()
+for _ in range(200):
+    api.lib().ivg_sync(gL._h)
+print("ivg_sync round trip %.1f us" % ((_t.perf_counter() - t) / 200 * 1e6))

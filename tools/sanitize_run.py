@@ -24,7 +24,10 @@ cam = (500.0, 500.0, w / 2, h / 2, 100.0)
 match, nm = gL.search_by_projection_last(world, de[0, :m], k["octave"][0, :m], k["angle"][0, :m], flags, np.eye(3, dtype=np.float32), np.array([0.01, 0, 0], np.float32), cam, (0, w, 0, h), 0, 7.0, True)
 proj = np.stack([k["x"][0, :m] + 1, k["y"][0, :m], k["x"][0, :m] - 3], 1).astype(np.float32)
 match2, nm2 = gL.search_by_projection_map(proj, np.full(m, 0.999, np.float32), k["octave"][0, :m], de[0, :m], flags, (0, w, 0, h), None, 3.0, 0.8)
-print("stereo matches", int((u >= 0).sum()), "proj", nm, nm2)
+from helpers import bow_scenario
+bs = bow_scenario(de[0, :m], k["angle"][0, :m], de[0, :m], 1)
+match3, nm3 = gL.search_by_bow(bs["desc"], bs["angle"], bs["flags"], bs["node_slot"], bs["node_start"], bs["node_idx"], 0.7, True)
+print("stereo matches", int((u >= 0).sum()), "proj", nm, nm2, "bow", nm3)
 gL.set_keypoint_mode(1); gL.upload(L, cost); gL.run(); gL.sync(); gL.set_keypoint_mode(0)
 yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
 gL.set_rectify_maps(xx * 1.01 - 3, yy * 0.99 + 2)
