@@ -118,6 +118,7 @@ struct ivg_extractor {
   TmaMaps blurMaps{};                   // per level: 160 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
   TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
   bool resizeTma[MAX_LEVELS] = {false};
+  TmaMaps descMapsN{};                  // the same with 48 x 37 boxes
   TmaMaps descMaps{};                   // per level: 64 x 37 x 1 boxes over the blurred planes (k_orient_describe)
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
@@ -429,7 +430,9 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   }
   for (int l = 0; l < nl; ++l)
     if ((rc = make_level_map(&h->descMaps.m[l], h->blur.p + fs.lv[l].planeOff, fs.lv[l].w, fs.lv[l].h, fs.lv[l].pitch, fs.planeBytes,
-                             batch, DK_BOXW, DK_BOXH)))
+                             batch, DK_BOXW, DK_BOXH)) ||
+        (rc = make_level_map(&h->descMapsN.m[l], h->blur.p + fs.lv[l].planeOff, fs.lv[l].w, fs.lv[l].h, fs.lv[l].pitch, fs.planeBytes,
+                             batch, DK_BOXN, DK_BOXH)))
       return rc;
   for (int l = 0; l < nl; ++l)
     if ((rc = make_level_map(&h->blurMaps.m[l], h->pyr.p + fs.lv[l].planeOff, fs.lv[l].w, fs.lv[l].h, fs.lv[l].pitch, fs.planeBytes,
@@ -490,7 +493,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
     if (lat) k_level_select<SEL_WARPS_LAT * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS_LAT * 32, h->selSmemLat, h->stream>>>(fs);
     else k_level_select<SEL_WARPS * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs);
   }
-  { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps); }
+  { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN); }
   CK(cudaGetLastError());
   return IVG_OK;
 }

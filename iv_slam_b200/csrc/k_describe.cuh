@@ -50,8 +50,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 constexpr int DK_SLOTS = 64;             // keypoint slots per CTA
 constexpr int DK_PR = 18;                // |rotated pattern offset| <= 18 (pattern radius 13*sqrt(2) rounds to 18)
 constexpr int DK_BOXW = 64, DK_BOXH = 2 * DK_PR + 1;   // TMA box: 64 x 37 bytes
+constexpr int DK_BOXN = 48;                             // narrow box for keypoints whose 37 columns start within 11 bytes of a 16-byte boundary
 
-__global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __grid_constant__ TmaMaps maps) {
+__global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaMaps mapsN) {
   __shared__ __align__(128) uint8_t spatch[8][2][DK_BOXW * DK_BOXH + 64];     // +64 keeps every buffer 128-byte aligned
   __shared__ __align__(8) uint64_t bars[8][2];
   __shared__ float2 spat[512];
@@ -105,9 +106,12 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     const int j = warp * (DK_SLOTS / 8) + q;
     const int level = sLevel[j];
     if (level < 0 || lane != 0) return;
+    // three quarters of the keypoints fit a 48-byte-wide box: its 48-byte row pitch spreads the rotated samples over all 32
+    // banks (a 64-byte pitch only ever uses two bank offsets per column group) and moves a quarter fewer bytes
     const int xa = (sCx[j] - DK_PR) & ~15;
-    mbar_expect_tx(&bars[warp][q & 1], DK_BOXW * DK_BOXH);
-    tma_load_3d(spatch[warp][q & 1], &maps.m[level], &bars[warp][q & 1], xa, sCy[j] - DK_PR, (int)img);
+    const bool narrow = sCx[j] - DK_PR - xa + 2 * DK_PR + 1 <= DK_BOXN;
+    mbar_expect_tx(&bars[warp][q & 1], (narrow ? DK_BOXN : DK_BOXW) * DK_BOXH);
+    tma_load_3d(spatch[warp][q & 1], narrow ? &mapsN.m[level] : &maps.m[level], &bars[warp][q & 1], xa, sCy[j] - DK_PR, (int)img);
   };
   issue_patch(0);
   issue_patch(1);
@@ -179,7 +183,9 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     const LevelDev& L = fs.lv[level];
     const int cx = sCx[j], cy = sCy[j];
     mbar_wait(&bars[warp][q & 1], (useCount[q & 1]++) & 1);   // parity = loads already consumed from this buffer
-    const uint8_t* bctr = spatch[warp][q & 1] + DK_PR * DK_BOXW + (cx - ((cx - DK_PR) & ~15));
+    const int cOff = cx - DK_PR - ((cx - DK_PR) & ~15);
+    const int pw = cOff + 2 * DK_PR + 1 <= DK_BOXN ? DK_BOXN : DK_BOXW;       // row pitch of this keypoint's patch
+    const uint8_t* bctr = spatch[warp][q & 1] + DK_PR * pw + cOff + DK_PR;
     const float a = sA[j], b = sB[j];
     unsigned val = 0;
 #pragma unroll
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
       const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)));
       const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)));
       const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(p1.x, a), __fmul_rn(p1.y, b)));
-      const int t0 = bctr[iy0 * DK_BOXW + ix0], t1 = bctr[iy1 * DK_BOXW + ix1];
+      const int t0 = bctr[iy0 * pw + ix0], t1 = bctr[iy1 * pw + ix1];
       val |= (t0 < t1 ? 1u : 0u) << k;
     }
     __syncwarp();                                         // every lane is done with this buffer
