@@ -17,7 +17,10 @@
 namespace ivg {
 
 constexpr int SEL_MAX_CELLS = 1024;      // cells per level the select kernel supports (host check)
-constexpr int SEL_WARPS = 8;            // warps per CTA for large batches (throughput); small batches launch SEL_WARPS_LAT
+#ifndef IVG_SEL_WARPS
+#define IVG_SEL_WARPS 4
+#endif
+constexpr int SEL_WARPS = IVG_SEL_WARPS;            // warps per CTA for large batches (throughput); small batches launch SEL_WARPS_LAT
 constexpr int SEL_WARPS_LAT = 32;       // one-frame-at-a-time: only nlevels CTAs exist, so each gets every warp an SM-quarter can hold
 // Shared memory is sized per handle (dynamic): FrameSet::selLevelCap level-list entries, selCellCap entries per warp for
 // a cell list, selCells per-cell scalars.  Lists longer than the caps are processed in global memory (same code).
