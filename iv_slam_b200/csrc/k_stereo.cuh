@@ -90,13 +90,16 @@ __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
 constexpr int SM_KP = 8;                   // left keypoints per warp
 constexpr int SM_ROWB = 48;                // staged bytes per patch row: right strip at [0,21), left patch at [32,43)
 constexpr int SM_SLOT = 11 * SM_ROWB;      // one keypoint's 11 rows
-constexpr int SM_WARPS = 8;
+#ifndef IVG_SM_WARPS
+#define IVG_SM_WARPS 4
+#endif
+constexpr int SM_WARPS = IVG_SM_WARPS;
 
 // [b,0,b,0] with b = byte k of w: one 8-bit value in both 16-bit lanes
 __device__ __forceinline__ unsigned dup16(unsigned w, int k) { return __byte_perm(w, 0u, 0x4040u | (unsigned)k | ((unsigned)k << 8)); }
 
 #ifndef IVG_SM_MINB
-#define IVG_SM_MINB 5
+#define IVG_SM_MINB 10
 #endif
 __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(FrameSet fs, StereoArgs A) {
   __shared__ __align__(16) uint8_t patch[SM_WARPS][SM_KP][SM_SLOT];
