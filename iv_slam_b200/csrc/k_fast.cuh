@@ -19,8 +19,9 @@
 //              instructions (VIMNMX[3].U16x2).  Ring samples at even dx are one conflict-free LDS.32, samples at odd
 //              dx are two LDS.32 and one PRMT;
 //   B reject   every pixel pair takes the opposing-pair test on 4 of the 8 ring diameters (any 9-arc contains one end
-//              of every diameter): 11 LDS, 2 PRMT, 14 packed min/max.  ~7 % of the pairs survive; their positions are
-//              appended to the warp's list (order irrelevant);
+//              of every diameter): 2 PRMT and 14 packed min/max per pair; a lane takes two adjacent pairs per step so that
+//              eleven 64-bit loads serve both.  ~7 % of the pairs survive; their positions are appended to the warp's
+//              list (order irrelevant);
 //   C score    dense loop over the list: 16 packed differences and the exact score network — min over each 9-arc as a
 //              min3 of three 3-minima, max over arcs, both polarities: 88 packed min/max for two pixels;
 //   D nms      dense loop over the list: strict 3x3 maximum inside the cell's score map; survivors set a bit;
