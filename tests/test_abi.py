@@ -64,3 +64,13 @@ def test_product_does_not_reference_the_oracle():
                 if re.search(r"\boracle\b", txt):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_header_is_valid_c99_and_cxx11(tmp_path):
+    """include/ivslam_gpu.h is the boundary a C or C++ host binds: it must compile on its own in both languages."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ivslam_gpu.h"\nint main(void) { ivg_extractor* h = 0; (void)h; return IVG_OK; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
