@@ -277,9 +277,17 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   unsigned csum = 0;
   if (fs.weighted) {
     const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
+    // aligned words + DP4A against a byte mask that cuts the window's first and last word to [wx, wx + ww)
+    const int xa0 = c.wx & ~3, xe = c.wx + c.ww, nw = (xe - xa0 + 3) >> 2;
     for (int y = warp; y < c.wh; y += FC_WARPS) {
-      const uint8_t* qr = q + (size_t)(c.wy + y) * L.pitch + c.wx;
-      for (int x = lane; x < c.ww; x += 32) csum += __ldg(qr + x);
+      const uint32_t* qr = reinterpret_cast<const uint32_t*>(q + (size_t)(c.wy + y) * L.pitch + xa0);
+      for (int k = lane; k < nw; k += 32) {
+        const int b0 = xa0 + 4 * k;
+        unsigned m = 0x01010101u;
+        if (b0 < c.wx) m &= 0x01010101u << (8 * (c.wx - b0));
+        if (b0 + 4 > xe) m &= 0x01010101u >> (8 * (b0 + 4 - xe));
+        csum = __dp4a(__ldg(qr + k), m, csum);
+      }
     }
   }
 #pragma unroll

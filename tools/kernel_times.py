@@ -9,8 +9,10 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 W, H, NF = (int(v) for v in sys.argv[3:6]) if len(sys.argv) > 5 else (1241, 376, 2000)
 L, R = S.make_stereo_batch(W, H, n, 100, distinct=min(16, n))
 a = (NF, 1.2, 8, 20, 7)
-gL, gR = api.ORBextractor(*a), api.ORBextractor(*a)
-gL.upload(L); gR.upload(R)
+INTRO = len(sys.argv) > 6 and sys.argv[6] == 'intro'      # left eye with an introspection cost-map (BASELINE C2 style)
+gL, gR = api.ORBextractor(*a, INTRO), api.ORBextractor(*a)
+cost = np.stack([S.make_cost_map(W, H, 7 + i) for i in range(min(n, 4))] * ((n + 3) // 4))[:n] if INTRO else None
+gL.upload(L, cost); gR.upload(R)
 def step():
     gL.run(); gL.sync(); gR.run(); gR.sync()
     rc = api.lib().ivg_stereo_match_batch(gL._h, gR._h, 386.1448, 718.856, None, None, gL.cap, 1)
