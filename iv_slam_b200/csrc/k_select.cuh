@@ -180,25 +180,32 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
   }
   __syncthreads();
 
-  if (tid == 0) {
-    const int nDesired = L.nDesired;
-    if (fs.weighted) {
-      // cell weights, row-major, float accumulation order as in the reference (:942-987)
-      const uint32_t* cost = fs.cellCost + img * fs.cellCostStride + L.cellBase;
-      float wsum = 0.0f;
-      for (int c = 0; c < nCells; ++c) {
-        const float area = __fmul_rn((float)cells[c].ww, (float)cells[c].wh);
-        const float mean = __fdiv_rn((float)cost[c], area);
-        const float qs = (float)(1.0 / (1.0 + (double)__fdiv_rn(mean, 255.0f)));
-        const float qn = __fsub_rn(__fmul_rn(2.0f, qs), 1.0f);
-        S.nfc[c] = qn;                            // parked; converted to a budget below
-        wsum = __fadd_rn(wsum, qn);
-      }
-      for (int c = 0; c < nCells; ++c) {
-        const float v = ceilf(__fdiv_rn(__fmul_rn((float)nDesired, S.nfc[c]), wsum));
-        S.nfc[c] = (1.0f < v) ? v : 1.0f;         // std::max(1.0f, v); NaN -> 1
-      }
+  if (fs.weighted) {
+    // cell weights (:942-987): the per-cell divisions run in parallel, only the float sum keeps the reference's
+    // row-major accumulation order (thread 0), then the budgets are again per cell
+    __shared__ float sWsum;
+    const uint32_t* cost = fs.cellCost + img * fs.cellCostStride + L.cellBase;
+    for (int c = tid; c < nCells; c += blockDim.x) {
+      const float area = __fmul_rn((float)cells[c].ww, (float)cells[c].wh);
+      const float mean = __fdiv_rn((float)cost[c], area);
+      const float qs = (float)(1.0 / (1.0 + (double)__fdiv_rn(mean, 255.0f)));
+      S.nfc[c] = __fsub_rn(__fmul_rn(2.0f, qs), 1.0f);      // parked; converted to a budget below
     }
+    __syncthreads();
+    if (tid == 0) {
+      float wsum = 0.0f;
+      for (int c = 0; c < nCells; ++c) wsum = __fadd_rn(wsum, S.nfc[c]);
+      sWsum = wsum;
+    }
+    __syncthreads();
+    const float wsum = sWsum;
+    for (int c = tid; c < nCells; c += blockDim.x) {
+      const float v = ceilf(__fdiv_rn(__fmul_rn((float)L.nDesired, S.nfc[c]), wsum));
+      S.nfc[c] = (1.0f < v) ? v : 1.0f;           // std::max(1.0f, v); NaN -> 1
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
     int nNoMore = 0, nToDistribute = 0;
     for (int c = 0; c < nCells; ++c) {            // :1082-1097
       const int nKeys = S.nTotal[c];
