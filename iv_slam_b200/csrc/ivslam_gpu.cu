@@ -472,9 +472,8 @@ FrameSet active_fs(const ivg_extractor* h) {
 
 int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
   for (int l = 1; l < fs.nlevels; ++l) {
-    dim3 grid((fs.lv[l].w + RZ_W - 1) / RZ_W, (fs.lv[l].h + RZ_H - 1) / RZ_H, fs.nImages);
-    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 0, h->resizeMaps, h->resizeTma[l] ? 1 : 0); }
-    if (fs.weighted) { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, 1, h->resizeMapsQ, h->resizeTma[l] ? 1 : 0); }
+    dim3 grid((fs.lv[l].w + RZ_W - 1) / RZ_W, (fs.lv[l].h + RZ_H - 1) / RZ_H, fs.nImages * (fs.weighted ? 2 : 1));   // image (+ cost-map) planes
+    { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, h->resizeMaps, h->resizeMapsQ, h->resizeTma[l] ? 1 : 0); }
   }
   CK(cudaGetLastError());
   return IVG_OK;

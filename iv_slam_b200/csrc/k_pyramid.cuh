@@ -42,14 +42,18 @@ __global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ stag
   *reinterpret_cast<uint4*>(plane + f * planeBytes + (size_t)y * pitch + x16) = o;      // bytes past w land in the row padding
 }
 
-__global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, int which /*0 image, 1 cost-map*/,
-                                                      const __grid_constant__ TmaMaps maps, int useTma) {
+// blockIdx.z < nImages: image planes; blockIdx.z >= nImages (weighted batches only): the cost-map planes of the same
+// level — both pyramids of a level go out in one launch.
+__global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, const __grid_constant__ TmaMaps maps,
+                                                      const __grid_constant__ TmaMaps mapsQ, int useTma) {
   extern __shared__ __align__(128) unsigned char rsm[];
   __shared__ __align__(8) uint64_t bar;
   const LevelDev& D = fs.lv[level];
   const LevelDev& S = fs.lv[level - 1];
   const int x0 = blockIdx.x * RZ_W, y0 = blockIdx.y * RZ_H;
-  uint8_t* plane = (which ? fs.qual : fs.pyr) + (size_t)blockIdx.z * fs.planeBytes;
+  const int which = (int)blockIdx.z >= fs.nImages ? 1 : 0;           // 0 image, 1 cost-map
+  const int img = (int)blockIdx.z - which * fs.nImages;
+  uint8_t* plane = (which ? fs.qual : fs.pyr) + (size_t)img * fs.planeBytes;
   const uint8_t* src = plane + S.planeOff;
   uint8_t* dst = plane + D.planeOff;
   const ResizeTap* tx = fs.rtab + D.rtabX;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, in
     __syncthreads();
     if (tid == 0) {
       mbar_expect_tx(&bar, (uint32_t)(SPB * D.rzRows));
-      tma_load_3d(spx, &maps.m[level], &bar, sxa, sya, (int)blockIdx.z);
+      tma_load_3d(spx, which ? &mapsQ.m[level] : &maps.m[level], &bar, sxa, sya, img);
     }
     if (tid < RZ_H && y0 + tid <= y1) { const ResizeTap t = ty[y0 + tid]; sTapY[tid] = make_int4((t.s0 - sya) * RZ_W, (t.s1 - sya) * RZ_W, t.c0, t.c1); }
     mbar_wait(&bar, 0);
