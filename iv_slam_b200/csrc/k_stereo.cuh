@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
   // Up front lane k (< 8) loads keypoint k's record and lanes 3k..3k+2 look up its three CSR segments (octaves
   // levelL-1, levelL, levelL+1), so the per-keypoint dependent chain is: candidates -> descriptors -> patch rows.
   // Lanes 4k..4k+3 remember keypoint k's parameters for phase 2.
-  bool gDo = false;
-  float gUL = 0.f, gUR0 = 0.f, gScale = 1.f;
+  bool kHit = false;          // lane k (< 8): keypoint k found a match with distance < thOrbDist
+  float kUR0 = 0.f;           //               x of that right keypoint
   const uint8_t* dr0 = A.descR + pair * A.cap * 32;
   const int nBins = A.nRows * A.nLevels;
   const int* rs = A.rowStart + pair * (size_t)(nBins + 1);
@@ -190,37 +190,58 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
     for (int s = 16; s; s >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, s));
     const int bestDist = best >> 16;
     if (A.bestDist && lane == 0) A.bestDist[o] = bestDist;
-    bool doSad = false;
-    float scaleduR0 = 0.f, lscale = 1.f;
     if (bestDist < thOrbDist) {
       // x of the winning right keypoint: held by the lane that found it (iR is unique, so is the winner)
       const float uR0 = __shfl_sync(0xffffffffu, bestU, __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1);
-      const LevelDev& L = fs.lv[levelL];
+      if (lane == k) { kHit = true; kUR0 = uR0; }
+    }
+  }
+
+  // ---- phase 1b: lane k (< 8) derives keypoint k's SAD window from its own record: 8 keypoints in parallel
+  bool kDo = false;
+  float kSUR0 = 0.f, kScale = 1.f;
+  int kOffR = 0, kOffL = 0, kPitch = 0;
+  if (lane < SM_KP && iL0 + lane < A.cap) {
+    if (kHit) {
+      const LevelDev& L = fs.lv[myLev];
       const float sf = L.invScale;
-      lscale = L.scale;
-      const float scaleduL = roundf(__fmul_rn(uL, sf)), scaledvL = roundf(__fmul_rn(vL, sf));
-      scaleduR0 = roundf(__fmul_rn(uR0, sf));
+      kScale = L.scale;
+      const float scaleduL = roundf(__fmul_rn(myU, sf)), scaledvL = roundf(__fmul_rn(myV, sf));
+      kSUR0 = roundf(__fmul_rn(kUR0, sf));
       const int w = 5, Ls = 5;
-      const int cy = (int)scaledvL, cxL = (int)scaleduL, cxR = (int)scaleduR0;
-      const float iniu = scaleduR0 + (float)(Ls - w), endu = scaleduR0 + (float)(Ls + w + 1);
+      const int cy = (int)scaledvL, cxL = (int)scaleduL, cxR = (int)kSUR0;
+      const float iniu = kSUR0 + (float)(Ls - w), endu = kSUR0 + (float)(Ls + w + 1);
       bool ok = !(iniu < 0 || endu >= (float)L.w);
       ok = ok && !(cy - w < 0 || cy + w + 1 > L.h || cxL - w < 0 || cxL + w + 1 > L.w || cxR - Ls - w < 0);
       if (ok) {
-        // lanes 0..20: right strip columns cxR-10..cxR+10; lanes 21..31: left patch columns cxL-5..cxL+5
-        const uint8_t* src = lane < 21 ? A.pyrR + pair * A.planeBytes + L.planeOff + (size_t)(cy - w) * L.pitch + (cxR - Ls - w + lane)
-                                       : A.pyrL + pair * A.planeBytes + L.planeOff + (size_t)(cy - w) * L.pitch + (cxL - w + lane - 21);
-        uint8_t* dst = &patch[warp][k][lane < 21 ? lane : lane + 11];
-        uint8_t v[11];
-#pragma unroll
-        for (int dy = 0; dy < 11; ++dy) v[dy] = __ldg(src + (size_t)dy * L.pitch);
-#pragma unroll
-        for (int dy = 0; dy < 11; ++dy) dst[dy * SM_ROWB] = v[dy];
-        doSad = true;
+        kDo = true;
+        kPitch = L.pitch;
+        kOffR = (int)L.planeOff + (cy - w) * L.pitch + (cxR - Ls - w);
+        kOffL = (int)L.planeOff + (cy - w) * L.pitch + (cxL - w);
       }
     }
-    if (!doSad && lane == 0) { A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
-    if ((lane >> 2) == k) { gDo = doSad; gUL = uL; gUR0 = scaleduR0; gScale = lscale; }
+    if (!kDo && iL0 + lane < N) { const size_t o = pair * A.cap + iL0 + lane; A.uRight[o] = -1.f; A.depth[o] = -1.f; A.sad[o] = -1; }
   }
+
+  // ---- phase 1c: stage the 11 patch rows of every keypoint that goes on: lanes 0..20 the right strip (columns
+  // cxR-10..cxR+10), lanes 21..31 the left patch (columns cxL-5..cxL+5)
+  const unsigned doMask = __ballot_sync(0xffffffffu, kDo);
+  for (unsigned rest = doMask; rest;) {
+    const int k = __ffs(rest) - 1;
+    rest &= rest - 1;
+    const int offR = __shfl_sync(0xffffffffu, kOffR, k), offL = __shfl_sync(0xffffffffu, kOffL, k), pitch = __shfl_sync(0xffffffffu, kPitch, k);
+    const uint8_t* src = lane < 21 ? A.pyrR + pair * A.planeBytes + offR + lane : A.pyrL + pair * A.planeBytes + offL + (lane - 21);
+    uint8_t* dst = &patch[warp][k][lane < 21 ? lane : lane + 11];
+    uint8_t v[11];
+#pragma unroll
+    for (int dy = 0; dy < 11; ++dy) v[dy] = __ldg(src + (size_t)dy * pitch);
+#pragma unroll
+    for (int dy = 0; dy < 11; ++dy) dst[dy * SM_ROWB] = v[dy];
+  }
+  // lanes 4k..4k+3 take over keypoint k's parameters for phase 2
+  const bool gDo = __shfl_sync(0xffffffffu, (int)kDo, lane >> 2) != 0;
+  const float gUL = __shfl_sync(0xffffffffu, myU, lane >> 2), gUR0 = __shfl_sync(0xffffffffu, kSUR0, lane >> 2);
+  const float gScale = __shfl_sync(0xffffffffu, kScale, lane >> 2);
   if (!__any_sync(0xffffffffu, gDo)) return;
   __syncwarp();
 
