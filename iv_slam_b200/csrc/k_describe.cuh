@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
   // Keypoints are >= 19 px from the border, so rows y-15..y+17 and the 9 words stay inside the level's pitched plane.
   const int mr = lane / 9, mk = lane - 9 * mr;
   const bool mact = lane < 27;
+  uint32_t mOnes[11];                       // this lane's in-circle masks of its 11 (row, word) positions: constant for all keypoints
+#pragma unroll
+  for (int it = 0; it < 11; ++it) mOnes[it] = (mact && mk < 8) ? sOnes[(3 * it + mr) * 8 + mk] : 0u;
 #pragma unroll 1
   for (int q = 0; q < DK_SLOTS / 8; ++q) {
     const int j = warp * (DK_SLOTS / 8) + q;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     for (int it = 0; it < 11; ++it) {
       const uint32_t wn = __shfl_down_sync(0xffffffffu, w[it], 1);
       const uint32_t x = __funnelshift_r(w[it], wn, sh);
-      const uint32_t o = (mact && mk < 8) ? sOnes[(3 * it + mr) * 8 + mk] : 0u;
+      const uint32_t o = mOnes[it];
       const int s = (int)__dp4a(x, o, 0u);
       T = (int)__dp4a(x, (o * 0xFFu) & 0x03020100u, (unsigned)T);
       S += s;
