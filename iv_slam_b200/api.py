@@ -181,6 +181,9 @@ class ORBextractor:
         _ck(lib().ivg_extractor_create(C.byref(self._h), device, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST,
                                        int(bool(enableIntrospection))), "ivg_extractor_create")
         self.nfeatures, self.nlevels, self.device = nfeatures, nlevels, device
+        self.params = dict(nfeatures=nfeatures, scaleFactor=scaleFactor, nlevels=nlevels, iniThFAST=iniThFAST, minThFAST=minThFAST,
+                           introspection=bool(enableIntrospection))
+        self.mode = 0
         self.cap = lib().ivg_max_keypoints(self._h)
         self._batch = 0
         self._stream_owner = None
@@ -200,6 +203,7 @@ class ORBextractor:
     def set_keypoint_mode(self, mode):
         """0: ComputeKeyPointsOld (the reference's live path, default); 1: ComputeKeyPointsOctTree (dead code there)."""
         _ck(lib().ivg_extractor_set_mode(self._h, int(mode)), "ivg_extractor_set_mode")
+        self.mode = int(mode)
         self.cap = lib().ivg_max_keypoints(self._h)
 
     # -- getters of the reference class (ORBextractor.h:69-91)

@@ -1152,6 +1152,15 @@ int orc_fast9(const uint8_t* img, int w, int h, size_t stride, int th, int nms, 
   for (int i = 0; i < n && i < cap; ++i) { xs[i] = out[i].x; ys[i] = out[i].y; scores[i] = out[i].score; }
   return n;
 }
+// Same detector with thread-local scratch, for callers that run it on many small windows (the OpenCV-compat layer of
+// oracle/refbuild/, where the unmodified reference calls cv::FAST per cell).  Returns n triples (x, y, score).
+const int* orc_fast9_tl(const uint8_t* img, int w, int h, size_t stride, int th, int nms, int* n) {
+  thread_local std::vector<Corner> out; thread_local FastScratch fs;
+  fast9_nms(img, w, h, stride, th, nms != 0, out, fs);
+  *n = (int)out.size();
+  static_assert(sizeof(Corner) == 3 * sizeof(int), "Corner is three ints");
+  return out.empty() ? nullptr : &out[0].x;
+}
 float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
 void orc_fast_atan2_array(const float* y, const float* x, float* out, int n) { for (int i = 0; i < n; ++i) out[i] = fast_atan2(y[i], x[i]); }
 

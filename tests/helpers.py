@@ -55,6 +55,36 @@ def assert_stereo_close(u, d, uo, do, what=""):
             assert float(np.max(rel * disp)) <= 1.0, "%s depth error" % what
 
 
+def fuzz_case(seed):
+    """Seeded fuzz geometry shared by the oracle-vs-reference CPU tests and the GPU parity tests: image size, feature count,
+    scale factor, level count, threshold, introspection on/off; every fourth case is a pure-noise image."""
+    from iv_slam_b200 import synthetic as S
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(160, 1400)), int(rng.integers(120, 900))
+    nf = int(rng.integers(150, 4000))
+    sf = float(rng.choice([1.2, 1.2, 1.1, 1.3, 1.5]))
+    nl = int(rng.integers(3, 9))
+    ini = int(rng.choice([12, 20, 20, 35]))
+    intro = bool(rng.integers(0, 2))
+    noise = seed % 4 == 3                      # a few pure-noise images: almost every pixel passes the FAST reject test
+    if noise:
+        left = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        right = np.roll(left, -7, axis=1)
+    else:
+        left, right = S.make_stereo_pair(w, h, 2000 + seed)
+    cost = S.make_cost_map(w, h, 3000 + seed) if intro else None
+    what = "fuzz%d %dx%d nf%d sf%.1f nl%d ini%d intro%d" % (seed, w, h, nf, sf, nl, ini, intro)
+    return dict(w=w, h=h, nf=nf, sf=sf, nl=nl, ini=ini, intro=intro, left=left, right=right, cost=cost, what=what)
+
+
+def reference_mb(mbf, maxD):
+    """The reference's `mb` member for a wanted maxD, and the maxD it then really uses: Frame::ComputeStereoMatches computes
+    maxD = mbf/mb in float (Frame.cc:787-789), so a comparison with the unmodified reference must feed every
+    implementation that value."""
+    mb = np.float32(mbf) / np.float32(maxD)
+    return float(mb), float(np.float32(mbf) / mb)
+
+
 # ----------------------------------------------------------------------------- N2 scenarios (SearchByProjection)
 PROJ_CAM = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, mbf=386.1448)
 
