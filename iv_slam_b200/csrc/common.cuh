@@ -5,7 +5,7 @@
 //                     every plane holds all levels of one frame back to back, each level row-pitched
 //                     (pitch = width rounded up to 64 B, so rows are 16 B aligned for vector access).
 //   cellList[b]       u32 per possible FAST corner of every cell, row-major inside the cell (y<<20 | x<<8 | score)
-//   cellCount[b]      int2 per cell: corners at minTh, corners at iniTh;  cellCost[b]: u32 cost-map sum of the window
+//   cellCount[b]      int2 per cell: entries in the cell's list, corners at iniTh;  cellCost[b]: u32 cost-map sum of the window
 //   levelKp[b]        uint2 per kept keypoint per level (response bits, packed y/x/score) + levelCount[b][level]
 //   outKp/outDesc[b]  final cv::KeyPoint-layout records and 32-byte descriptors, reference order; outN[b]
 //   uRight/depth/sad  stereo results per left keypoint
@@ -54,6 +54,7 @@ struct ResizeTap { uint16_t s0, s1; int16_t c0, c1; };   // two source indices a
 struct FrameSet {
   int nlevels, nImages, weighted;
   int iniTh, minTh, scoreTh;
+  int fastRetry;           // k_fast_cells redoes a cell at minTh when the iniTh pass leaves <= this many corners (3: live path :1047, 0: OctTree :818)
   int nCellsTotal, kpCap;
   int cellCostStride;      // entries per frame in cellCost (nCellsTotal + slack used by the OctTree gather)
   int btTotal;

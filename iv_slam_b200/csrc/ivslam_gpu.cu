@@ -293,14 +293,14 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.fSS = (int)align_up(L.cellW + 6, 4);
     L.fBW = (L.cellW + 31) / 32;
     {
-      const int chunks = ((L.cellW + 2) / 2 + 31) / 32;                                   // 32-pair chunks per row
+      const int slots = (((L.cellW + 2) / 2 + 1 + 63) / 64) * 64;                         // pair slots a warp walks per row (64 per step)
       auto bytes = [&](int bh, int* seg) {
         const size_t ssBytes = align_up((size_t)L.fSS * (bh + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (bh + 2), 16);
-        *seg = ((bh + 2 + FC_WARPS - 1) / FC_WARPS) * 32 * chunks;                        // per-warp pair list: its rows, every pair
+        *seg = ((bh + 2 + FC_WARPS - 1) / FC_WARPS) * slots;                              // per-warp pair list: its rows, every slot
         return align_up((size_t)4 * L.fSP * (bh + 8), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * FC_WARPS * *seg;
       };
       L.fShift = 1;
-      while ((1 << L.fShift) < 32 * chunks) ++L.fShift;                                   // list entry = (score row << fShift) | pair index, 16 bits
+      while ((1 << L.fShift) < slots) ++L.fShift;                                         // list entry = (score row << fShift) | pair slot, 16 bits
       if ((65536 >> L.fShift) < 8) return IVG_ERR_CAPACITY;                               // cells wider than ~16k px
       int bh = std::min(L.cellH, (65536 >> L.fShift) - 2);
       while (bh > 4 && bytes(bh, &L.fSeg) > FAST_SMEM_BUDGET) --bh;                       // taller cells are processed in bands
@@ -467,6 +467,7 @@ FrameSet active_fs(const ivg_extractor* h) {
   fs.nImages = h->curBatch;
   fs.weighted = h->curWeighted ? 1 : 0;
   fs.cells = (h->curWeighted && h->kpMode == 0) ? h->dCellsWeighted.p : h->dCellsPlain.p;
+  fs.fastRetry = h->kpMode == 1 ? 0 : 3;
   return fs;
 }
 

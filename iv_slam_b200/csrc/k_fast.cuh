@@ -5,8 +5,11 @@
 // (introspective_ORB_SLAM/src/ORBextractor.cc:1045 and :1051) including their emission order, and cv::sum over the
 // cost-map window (:976-978).  SURVEY Appendix A.3:
 //   * the corner score S (largest threshold at which the pixel is still a 9-arc corner) does not depend on the
-//     threshold and "corner at th" <=> S >= th, so ONE score pass serves both iniThFAST and minThFAST; the
-//     "<= 3 keypoints => retry with minThFAST" rule (:1047-1052) only needs the two counts, taken here;
+//     threshold, "corner at th" <=> S >= th, and a corner with S >= th survives the 3x3 NMS of a run at any lower
+//     threshold iff it survives at th (the extra neighbours all score below th).  The cell is processed like the
+//     reference does (:1045-1052): once at iniThFAST — few pixels pass the reject test at that threshold, so the exact
+//     scoring, NMS and emission touch few candidates — and again at minThFAST only when that left <= 3 corners
+//     (fs.fastRetry; 0 in OctTree mode, :818-822).  cellCount = (entries in the list, corners at iniTh);
 //   * the reference runs FAST per cell window, so NMS never sees scores of the neighbouring cell: one CTA = one cell,
 //     scores outside the cell's own detect range simply do not exist (zero border);
 //   * with a cost-map the detect rows shrink to the stale window height of the last cell row: that is
@@ -18,10 +21,10 @@
 //              2 B of shared memory per pixel, and a word is already in the packed 16x2 layout of the DPX min/max
 //              instructions (VIMNMX[3].U16x2).  Ring samples at even dx are one conflict-free LDS.32, samples at odd
 //              dx are two LDS.32 and one PRMT;
-//   B reject   every pixel pair takes the opposing-pair test on 4 of the 8 ring diameters (any 9-arc contains one end
-//              of every diameter): 2 PRMT and 14 packed min/max per pair; a lane takes two adjacent pairs per step so that
-//              eleven 64-bit loads serve both.  ~7 % of the pairs survive; their positions are appended to the warp's
-//              list (order irrelevant);
+//   B reject   every pixel pair takes the opposing-pair test on the two cardinal ring diameters (any 9-arc contains one
+//              end of every diameter): 2 PRMT and 6 packed min/max per pair; a lane takes two adjacent pairs per step so
+//              that five 64-bit loads serve both.  ~2 % of the pairs survive at iniTh; each lane appends them to its own
+//              list, the lists are merged once per band (order irrelevant);
 //   C score    dense loop over the list: 16 packed differences and the exact score network — min over each 9-arc as a
 //              min3 of three 3-minima, max over arcs, both polarities: 88 packed min/max for two pixels;
 //   D nms      dense loop over the list: strict 3x3 maximum inside the cell's score map; survivors set a bit;
@@ -93,11 +96,16 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   const int lead = cOff & 1;               // 1: pair 0 starts one column left of the detect range
   const int w0 = cOff >> 1;                // staged word of pair 0
   const int nPr = (lead + cw + 1) >> 1;    // pixel pairs per row
-  const int scoreTh = fs.scoreTh;
+  // pass 0 runs at iniTh; a second pass at minTh follows only when the first one left too few corners (and minTh is lower:
+  // with iniTh <= minTh the retry is a subset of the first pass and the consumers filter the list by score)
+  int scoreTh = fs.iniTh;
+  int running = 0, nIniPass = 0, nHigh = 0, par = 0;
+  const bool countHigh = fs.iniTh < fs.minTh;     // rare configuration: count the corners at the higher threshold per thread
+
+  for (int pass = 0; pass < 2; ++pass) {
   const unsigned kK2 = ((unsigned)scoreTh + 1u) * 0x00010001u;      // th + 1 in both 16-bit lanes
   const unsigned kB = 0x80008000u - kK2;
-
-  int running = 0, nIni = 0, nMin = 0, par = 0;
+  running = 0;
 
   for (int r0 = 0; r0 < ch; r0 += BH) {
     const int r1 = min(r0 + BH, ch);
@@ -132,51 +140,61 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     }
     __syncthreads();
 
-    // ---- B: opposing-pair rejection on diameters 0-8, 2-10, 4-12, 6-14
-    // A lane takes two adjacent pixel pairs (four pixels) per step: their ring samples overlap, so 11 64-bit loads serve
-    // both (22 32-bit loads otherwise).  Rows are walked from an even word so that the 64-bit loads are aligned; pair
-    // indices outside [0, nPr) (the word before the first pair, lanes past the end of the row) read staged neighbours /
-    // slack and are masked.
+    // ---- B: opposing-pair rejection on the two cardinal diameters 0-8 (vertical) and 4-12 (horizontal)
+    // Any 9-arc contains one end of every diameter, so a bright (dark) corner needs a bright (dark) end on both.  Two
+    // diameters cost 5 shared loads and 12 packed min/max per four pixels and at iniTh they reject all but ~2 % of the
+    // pixel pairs; the pairs that pass go straight to the exact score.  A lane takes two adjacent pixel pairs per step
+    // (their samples overlap: five 64-bit loads serve both).  Rows are walked from an even word so that the 64-bit loads
+    // are aligned; the slots outside [0, nPr) (the word before the first pair, lanes past the end of the row) read staged
+    // neighbours / slack and are dropped when the lists are merged.  Every lane appends to its own lane-strided list
+    // (entry k of lane l at [32 k + l]): two predicated instructions per pair instead of a ballot-ranked append per step.
     uint16_t* wlist = slist + warp * segCap;        // this warp's private segment: no atomics, no ordering needed
     int wn = 0;
     {
       const unsigned ltmask = (1u << lane) - 1u;
-      const int wE = w0 & ~1, pOff = w0 - wE;       // first (even) word walked; its pair index is -pOff
-      const int nSteps = (nPr + pOff + 63) >> 6;    // 64 words per warp step
+      const int wE = w0 & ~1, pOff = w0 - wE;       // first (even) word walked; slot q holds pair q - pOff
+      const int nSteps = (nPr + pOff + 63) >> 6;    // 64 slots per warp step
       // directly on the packed pixels (no differences needed for a reject test):
       //   bright possible  <=>  min over diameters of max(ring_k, ring_k+8) >= centre + th + 1
       //   dark possible    <=>  max over diameters of min(ring_k, ring_k+8) <= centre - th - 1
-      auto reject_test = [&](unsigned C, unsigned r0_, unsigned r8, unsigned r2, unsigned r10, unsigned r4, unsigned r12, unsigned r6, unsigned r14) {
-        const unsigned a = __vminu2(vmin3(__vmaxu2(r0_, r8), __vmaxu2(r2, r10), __vmaxu2(r4, r12)), __vmaxu2(r6, r14));
-        const unsigned b = __vmaxu2(vmax3(__vminu2(r0_, r8), __vminu2(r2, r10), __vminu2(r4, r12)), __vminu2(r6, r14));
+      auto reject_test = [&](unsigned C, unsigned r0_, unsigned r8, unsigned r4, unsigned r12) {
+        const unsigned a = __vminu2(__vmaxu2(r0_, r8), __vmaxu2(r4, r12));
+        const unsigned b = __vmaxu2(__vminu2(r0_, r8), __vminu2(r4, r12));
         // bit 15 of each 16-bit lane: (a >= C + K) and (C >= b + K), K = th + 1; no borrow can cross lanes
         const unsigned X = a + kB - C;
         const unsigned Y = C + kB - b;
         return ((X | Y) & 0x80008000u) != 0u;
       };
+      uint16_t* lp = wlist + lane;
       for (int y = warp; y < nSR; y += FC_WARPS) {
         const uint2* ctr = reinterpret_cast<const uint2*>(sp + (y + 3) * SP + wE) + lane;
         const uint2* cp3 = reinterpret_cast<const uint2*>(sp + (y + 6) * SP + wE) + lane;
         const uint2* cm3 = reinterpret_cast<const uint2*>(sp + y * SP + wE) + lane;
-        const uint2* cp2 = reinterpret_cast<const uint2*>(sp + (y + 5) * SP + wE) + lane;
-        const uint2* cm2 = reinterpret_cast<const uint2*>(sp + (y + 1) * SP + wE) + lane;
-        const int ebase = (y << sh);
-        int pi = 2 * lane - pOff;
-        for (int st = 0; st < nSteps; ++st, ctr += 32, cp3 += 32, cm3 += 32, cp2 += 32, cm2 += 32, pi += 64) {
+        unsigned e = (unsigned)(y << sh) + 2u * lane;              // (score row, slot); fits 16 bits: the host bounds the band height
+        for (int st = 0; st < nSteps; ++st, ctr += 32, cp3 += 32, cm3 += 32, e += 64) {
           const uint2 ca = ctr[-1], cb = ctr[0], cc = ctr[1];        // words W-2 .. W+3 of the centre row
           const uint2 t3 = cp3[0], b3 = cm3[0];
-          const uint2 pa = cp2[-1], pb = cp2[0], pc = cp2[1];
-          const uint2 ma = cm2[-1], mb = cm2[0], mc = cm2[1];
-          const bool passA = reject_test(cb.x, t3.x, b3.x, pb.y, ma.y, __byte_perm(cb.y, cc.x, 0x5432), __byte_perm(ca.x, ca.y, 0x5432), mb.y, pa.y) &
-                             (pi >= 0) & (pi < nPr);
-          const bool passB = reject_test(cb.y, t3.y, b3.y, pc.x, mb.x, __byte_perm(cc.x, cc.y, 0x5432), __byte_perm(ca.y, cb.x, 0x5432), mc.x, pb.x) &
-                             (pi + 1 < nPr);
-          const unsigned mA = __ballot_sync(0xffffffffu, passA), mB = __ballot_sync(0xffffffffu, passB);
-          if (passA) wlist[wn + __popc(mA & ltmask)] = (uint16_t)(ebase + pi);          // fits 16 bits: the host bounds the band height
-          wn += __popc(mA);
-          if (passB) wlist[wn + __popc(mB & ltmask)] = (uint16_t)(ebase + pi + 1);
-          wn += __popc(mB);
+          if (reject_test(cb.x, t3.x, b3.x, __byte_perm(cb.y, cc.x, 0x5432), __byte_perm(ca.x, ca.y, 0x5432))) { *lp = (uint16_t)e; lp += 32; }
+          if (reject_test(cb.y, t3.y, b3.y, __byte_perm(cc.x, cc.y, 0x5432), __byte_perm(ca.y, cb.x, 0x5432))) { *lp = (uint16_t)(e + 1); lp += 32; }
         }
+      }
+      // merge the lane lists into one dense list, in place: row k of the lane-strided layout (entry k of every lane) is
+      // read by the whole warp before its survivors are written at [wn, wn + count) <= 32 k, so nothing unread is overwritten
+      const int cnt = (int)(lp - (wlist + lane)) >> 5;
+      const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+      for (int k = 0; k < maxc; ++k) {
+        int v = 0;
+        bool has = k < cnt;
+        if (has) {
+          v = wlist[32 * k + lane];
+          const int pi = (v & piMask) - pOff;
+          has = pi >= 0 && pi < nPr;
+          v -= pOff;                                               // list entry = (score row << sh) | pair index
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (has) wlist[wn + __popc(m & ltmask)] = (uint16_t)v;
+        wn += __popc(m);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -263,14 +281,17 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
             bits &= bits - 1;
             const int s = srow[k];
             list[off++] = pack_xys(c.x0 + xb + k, c.y0 + r0 + row, s);
-            nIni += s >= fs.iniTh;
-            nMin += s >= fs.minTh;
+            if (countHigh) nHigh += s >= fs.minTh;
           }
           if (++xw == BW) { xw = 0; ++row; }
         }
       }
     }
     __syncthreads();   // smem is restaged by the next band
+  }
+    if (pass == 0) nIniPass = running;
+    if (pass == 1 || running > fs.fastRetry || fs.minTh >= fs.iniTh) break;     // CTA-uniform
+    scoreTh = fs.minTh;
   }
 
   // ---- per-cell counters (+ cost-map window sum for the introspection budgets)
@@ -292,17 +313,17 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
-    nIni += __shfl_xor_sync(0xffffffffu, nIni, o);
-    nMin += __shfl_xor_sync(0xffffffffu, nMin, o);
+    if (countHigh) nHigh += __shfl_xor_sync(0xffffffffu, nHigh, o);
     csum += __shfl_xor_sync(0xffffffffu, csum, o);
   }
-  if (lane == 0) { sred[0][warp] = nIni; sred[1][warp] = nMin; sred[2][warp] = (int)csum; }
+  if (lane == 0) { sred[0][warp] = nHigh; sred[2][warp] = (int)csum; }
   __syncthreads();
   if (tid == 0) {
-    int a = 0, b = 0; unsigned s = 0;
+    int a = 0; unsigned s = 0;
 #pragma unroll
-    for (int w = 0; w < FC_WARPS; ++w) { a += sred[0][w]; b += sred[1][w]; s += (unsigned)sred[2][w]; }
-    fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = make_int2(b, a);   // x: corners at minTh, y: corners at iniTh
+    for (int w = 0; w < FC_WARPS; ++w) { a += sred[0][w]; s += (unsigned)sred[2][w]; }
+    // x: entries in the list (corners at the lower threshold), y: corners at iniTh
+    fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = countHigh ? make_int2(a, nIniPass) : make_int2(running, nIniPass);
     fs.cellCost[img * fs.cellCostStride + blockIdx.x] = s;
   }
 }
