@@ -187,6 +187,7 @@ class ORBextractor:
         self.cap = lib().ivg_max_keypoints(self._h)
         self._batch = 0
         self._stream_owner = None
+        self._inflight = []          # host arrays of asynchronous copies, kept alive until sync()
         _live.add(self)
 
     def close(self):
@@ -270,7 +271,13 @@ class ORBextractor:
 
     # -- split phases (bench / pipelining)
     def upload(self, images, masks=None):
+        """Asynchronous H2D of [n,H,W] u8 frames (rows may be strided, pixels must be contiguous).  The arrays are referenced
+        until sync(): the DMA may still be reading them when this returns."""
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.strides[2] == 1
         n, H, W = images.shape
+        if masks is not None:
+            assert masks.dtype == np.uint8 and masks.shape == images.shape and masks.strides[2] == 1
+        self._inflight.extend((images, masks))
         _ck(lib().ivg_upload_batch(self._h, n, _p(images), W, H, images.strides[1], images.strides[0], _p(masks),
                                    masks.strides[1] if masks is not None else 0, masks.strides[0] if masks is not None else 0), "ivg_upload_batch")
         self._batch = n
@@ -364,10 +371,15 @@ class ORBextractor:
         _ck(lib().ivg_run_batch(self._h), "ivg_run_batch")
 
     def download(self, kps, desc, cnt):
+        """Asynchronous D2H into caller arrays (referenced until sync())."""
+        assert kps.dtype == KP_DTYPE and desc.dtype == np.uint8 and cnt.dtype == np.int32
+        assert kps.flags.c_contiguous and desc.flags.c_contiguous and cnt.flags.c_contiguous
+        self._inflight.extend((kps, desc, cnt))
         _ck(lib().ivg_download_batch(self._h, _p(kps), _p(desc), kps.shape[-1], _p(cnt)), "ivg_download_batch")
 
     def sync(self):
         _ck(lib().ivg_sync(self._h), "ivg_sync")
+        self._inflight.clear()
 
     def share_stream(self, owner):
         """Run this extractor's kernels on `owner`'s stream (no kernel overlap between the two; copies still overlap)."""
@@ -453,6 +465,9 @@ def compute_stereo_matches_batch(left, right, mbf, maxD, uRight=None, depth=None
     if uRight is None:
         uRight = np.empty((n, left.cap), np.float32)
         depth = np.empty((n, left.cap), np.float32)
+    assert uRight.dtype == np.float32 and depth.dtype == np.float32 and uRight.flags.c_contiguous and depth.flags.c_contiguous
+    if not sync:
+        left._inflight.extend((uRight, depth))      # the D2H may still be writing them when this returns
     _ck(lib().ivg_stereo_match_batch(left._h, right._h, mbf, maxD, _p(uRight), _p(depth), uRight.shape[-1], int(sync)), "ivg_stereo_match_batch")
     return uRight, depth
 

@@ -96,7 +96,8 @@ struct ivg_extractor {
   cudaEvent_t evD2H = nullptr;          // copyOut: results of the last run have been read (next run may overwrite them)
   cudaEvent_t evStereo = nullptr;       // stream (left handle): matcher finished reading both handles
   cudaEvent_t evD2Hs = nullptr;         // copyOut (left handle): uRight/depth have been read
-  cudaEvent_t waitFor = nullptr;        // an event of another handle that must complete before we overwrite our buffers
+  cudaEvent_t evConsumed = nullptr;     // recorded (on the matcher's stream) when another handle's kernels have read our buffers
+  cudaEvent_t waitFor = nullptr;        // set to evConsumed (our own event) when it must complete before we overwrite our buffers
   long long launches = 0;
 
   // shape-dependent state
@@ -169,15 +170,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // u8 tensor (x, y, frame) over one pyramid level of a plane: TMA boxes of boxW x boxH x 1, zero fill outside the image
 int make_level_map(CUtensorMap* out, uint8_t* base, int w, int h, int pitch, size_t planeBytes, int frames, int boxW, int boxH) {
   static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
+  static std::once_flag once;      // two extractor threads (the reference's left/right threads) may build shapes concurrently
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
-      g_cuda_err = "cuTensorMapEncodeTiled entry point not available";
-      return IVG_ERR_CUDA;
-    }
-    fn = (PFN_encodeTiled)p;
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (PFN_encodeTiled)p;
+  });
+  if (!fn) { g_cuda_err = "cuTensorMapEncodeTiled entry point not available"; return IVG_ERR_CUDA; }
   const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
   const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)planeBytes};
   const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
@@ -583,6 +582,7 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
   if (!out) return IVG_ERR_INVALID;
   *out = nullptr;
   if (nfeatures < 1 || nlevels < 1 || nlevels > MAX_LEVELS || !(scaleFactor > 1.0f)) return IVG_ERR_INVALID;
+  if (device < 0 || device >= 64) return IVG_ERR_INVALID;     // per-device constants are tracked in a 64-entry table
   int rc = ivg_device_info(device, nullptr, 0, nullptr, nullptr);
   if (rc) return rc;
   CK(cudaSetDevice(device));
@@ -595,7 +595,7 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
   static bool done[64] = {false};
   {
     std::lock_guard<std::mutex> lk(mu);
-    if (device < 64 && !done[device]) {
+    if (!done[device]) {
       rc = init_device_constants(device);
       if (rc) { delete h; return rc; }
       done[device] = true;
@@ -608,7 +608,7 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
   }
   bool ok = cudaStreamCreateWithFlags(&h->copyIn, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->copyOut, cudaStreamNonBlocking) == cudaSuccess;
-  for (cudaEvent_t* e : {&h->evH2D, &h->evIngest, &h->evKernels, &h->evD2H, &h->evStereo, &h->evD2Hs})
+  for (cudaEvent_t* e : {&h->evH2D, &h->evIngest, &h->evKernels, &h->evD2H, &h->evStereo, &h->evD2Hs, &h->evConsumed})
     ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
   if (!ok || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->evDone, cudaEventDisableTiming) != cudaSuccess ||
@@ -638,7 +638,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->evDone) cudaEventDestroy(h->evDone);
   if (h->evT0) cudaEventDestroy(h->evT0);
   if (h->evT1) cudaEventDestroy(h->evT1);
-  for (cudaEvent_t e : {h->evH2D, h->evIngest, h->evKernels, h->evD2H, h->evStereo, h->evD2Hs}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->evH2D, h->evIngest, h->evKernels, h->evD2H, h->evStereo, h->evD2Hs, h->evConsumed}) if (e) cudaEventDestroy(e);
   if (h->copyIn) cudaStreamDestroy(h->copyIn);
   if (h->copyOut) cudaStreamDestroy(h->copyOut);
   if (h->stream && h->ownsStream) cudaStreamDestroy(h->stream);
@@ -686,7 +686,10 @@ int ivg_set_batch(ivg_extractor* h, int n, int width, int height, int with_cost)
   h->curBatch = n;
   h->curWeighted = with_cost && h->enableIntrospection;   // src/ORBextractor.cc:1231
   h->haveCost = with_cost != 0;
-  if (with_cost && !h->qual.p) {                           // cost-map planes are also needed by ivg_frame_postprocess
+  if (with_cost) {
+    // cost-map planes are also needed by ivg_frame_postprocess on handles without introspection (mvKeyQualScore is
+    // computed from the map regardless of the flag, Frame.cc:128-139).  build_shape only sizes `qual` for introspection
+    // handles, so size it here for the current shape and batch every time (a no-op once it is large enough).
     if ((rc = h->qual.alloc((size_t)h->maxBatch * h->fs.planeBytes))) return rc;
     h->fs.qual = h->qual.p;
   }
@@ -845,7 +848,7 @@ int ivg_search_by_projection_last(ivg_extractor* cur, int index, int n, const fl
                                   const float* angle, const uint8_t* flags, const float* Rcw, const float* tcw, float fx, float fy, float cx,
                                   float cy, float mbf, float minX, float maxX, float minY, float maxY, int mode, float th,
                                   int check_orientation, int* match, int cap, int* nmatches) {
-  if (!cur || (n > 0 && (!world_pos || !desc || !octave || !angle || !flags)) || !Rcw || !tcw || mode < 0 || mode > 2) return IVG_ERR_INVALID;
+  if (!cur || n < 0 || (n > 0 && (!world_pos || !desc || !octave || !angle || !flags)) || !Rcw || !tcw || mode < 0 || mode > 2) return IVG_ERR_INVALID;
   CK(cudaSetDevice(cur->device));
   ProjUpload up{cur};
   const size_t oW = up.add(world_pos, (size_t)n * 12), oD = up.add(desc, (size_t)n * 32), oO = up.add(octave, (size_t)n * 4),
@@ -865,7 +868,7 @@ int ivg_search_by_projection_last(ivg_extractor* cur, int index, int n, const fl
 int ivg_search_by_projection_map(ivg_extractor* cur, int index, int n, const float* proj, const float* view_cos, const int* level,
                                  const uint8_t* desc, const uint8_t* flags, const uint8_t* cur_blocked, float minX, float maxX, float minY,
                                  float maxY, float th, float nnratio, int* match, int cap, int* nmatches) {
-  if (!cur || (n > 0 && (!proj || !view_cos || !level || !desc || !flags))) return IVG_ERR_INVALID;
+  if (!cur || n < 0 || (n > 0 && (!proj || !view_cos || !level || !desc || !flags))) return IVG_ERR_INVALID;
   CK(cudaSetDevice(cur->device));
   ProjUpload up{cur};
   const size_t oP = up.add(proj, (size_t)n * 12), oV = up.add(view_cos, (size_t)n * 4), oL = up.add(level, (size_t)n * 4),
@@ -892,7 +895,9 @@ int ivg_search_by_bow(ivg_extractor* cur, int index, int n, const uint8_t* desc,
   CK(cudaSetDevice(cur->device));
   const int K = cur->fs.kpCap;
   const int total = n_nodes > 0 ? node_start[n_nodes] : 0;
-  if (total < 0) return IVG_ERR_INVALID;
+  if (total < 0 || (n_nodes > 0 && node_start[0] != 0)) return IVG_ERR_INVALID;
+  for (int s = 0; s < n_nodes; ++s) if (node_start[s + 1] < node_start[s]) return IVG_ERR_INVALID;   // CSR must be non-decreasing
+  for (int i = 0; i < total; ++i) if (node_idx[i] < 0 || node_idx[i] >= K) return IVG_ERR_INVALID;    // the kernels index keypoints with these
   // points grouped by node slot, caller's order kept inside a slot (nodes never interact: a keypoint of F is in one node)
   std::vector<int> ptStart((size_t)n_nodes + 1, 0), ptIdx((size_t)std::max(n, 1));
   for (int i = 0; i < n; ++i) if (node_slot[i] >= 0 && node_slot[i] < n_nodes) ++ptStart[(size_t)node_slot[i] + 1];
@@ -1145,7 +1150,8 @@ int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf,
   const size_t k = A.cap;
   // the right handle must not overwrite its pyramids/keypoints before the matcher has read them
   CK(cudaEventRecord(left->evStereo, left->stream));
-  right->waitFor = left->evStereo;
+  CK(cudaEventRecord(right->evConsumed, left->stream));          // the right handle's own event: survives the left handle
+  right->waitFor = right->evConsumed;
   CK(cudaStreamWaitEvent(left->copyOut, left->evStereo, 0));
   if (uRight) CK(cudaMemcpy2DAsync(uRight, (size_t)cap * 4, left->uRight.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, left->copyOut));
   if (depth) CK(cudaMemcpy2DAsync(depth, (size_t)cap * 4, left->depth.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, left->copyOut));

@@ -944,6 +944,7 @@ struct ProjFrame {
   const int* gridStart; const int* gridIdx;                      // 64 x 48 CSR of orc_frame_post (cell = col*48 + row)
   float minX, minY, invW, invH;
   const float* scale;
+  int nLevels;                                                   // entries in scale[]: points whose octave is outside are skipped (as the CUDA path does)
 };
 
 static void features_in_area(const ProjFrame& F, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) {
@@ -1016,6 +1017,7 @@ static int search_by_projection_last(const ProjFrame& F, int n, const float* wor
     if (u < F.minX || u > maxX) continue;
     if (v < F.minY || v > maxY) continue;
     const int nLastOctave = octave[i];
+    if (nLastOctave < 0 || nLastOctave >= F.nLevels) continue;   // the reference would index mvScaleFactors out of range
     const float radius = th * F.scale[nLastOctave];
     if (mode == 1) features_in_area(F, u, v, radius, nLastOctave, -1, cand);
     else if (mode == 2) features_in_area(F, u, v, radius, 0, nLastOctave, cand);
@@ -1065,6 +1067,7 @@ static int search_by_projection_map(const ProjFrame& F, int n, const float* proj
   for (int iMP = 0; iMP < n; ++iMP) {
     if (!(flags[iMP] & 1)) continue;
     const int nPredictedLevel = level[iMP];
+    if (nPredictedLevel < 0 || nPredictedLevel >= F.nLevels) continue;
     float r = viewCos[iMP] > 0.998 ? 2.5 : 4.0;
     if (bFactor) r *= th;
     features_in_area(F, proj[3 * iMP], proj[3 * iMP + 1], r * F.scale[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, cand);
@@ -1305,19 +1308,19 @@ void orc_prologue(const uint8_t* src, int sw, int sh, size_t sstride, int cn, in
 void orc_transform_point(const float* R, const float* t, const float* X, float* out) { transform_point(R, t, X, out); }
 
 int orc_search_by_projection_last(const void* kps, int N, const uint8_t* descCur, const float* uRight, const int* gridStart, const int* gridIdx,
-                                  const float* scale, float minX, float maxX, float minY, float maxY,
+                                  const float* scale, int nlevels, float minX, float maxX, float minY, float maxY,
                                   int n, const float* world, const uint8_t* desc, const int* octave, const float* angle, const uint8_t* flags,
                                   const float* Rcw, const float* tcw, float fx, float fy, float cx, float cy, float mbf, int mode, float th,
                                   int checkOri, int* match) {
-  ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale};
+  ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale, nlevels};
   return search_by_projection_last(F, n, world, desc, octave, angle, flags, Rcw, tcw, fx, fy, cx, cy, mbf, maxX, maxY, mode, th, checkOri, match);
 }
 
 int orc_search_by_projection_map(const void* kps, int N, const uint8_t* descCur, const float* uRight, const int* gridStart, const int* gridIdx,
-                                 const float* scale, float minX, float maxX, float minY, float maxY,
+                                 const float* scale, int nlevels, float minX, float maxX, float minY, float maxY,
                                  int n, const float* proj, const float* viewCos, const int* level, const uint8_t* desc, const uint8_t* flags,
                                  const uint8_t* curBlocked, float th, float nnratio, int* match) {
-  ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale};
+  ProjFrame F{(const KeyPoint*)kps, N, descCur, uRight, gridStart, gridIdx, minX, minY, 64.0f / (maxX - minX), 48.0f / (maxY - minY), scale, nlevels};
   return search_by_projection_map(F, n, proj, viewCos, level, desc, flags, curBlocked, th, nnratio, match);
 }
 

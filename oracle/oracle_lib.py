@@ -98,9 +98,9 @@ def lib():
     L.orc_stage_seconds.restype = None
     L.orc_frame_post.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.orc_frame_post.restype = None
-    L.orc_search_by_projection_last.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, vp] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int, vp]
+    L.orc_search_by_projection_last.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, vp] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int, vp]
     L.orc_search_by_projection_last.restype = C.c_int
-    L.orc_search_by_projection_map.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]
+    L.orc_search_by_projection_map.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int] + [C.c_float] * 4 + [C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]
     L.orc_search_by_projection_map.restype = C.c_int
     L.orc_search_by_bow.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_int, vp]
     L.orc_search_by_bow.restype = C.c_int
@@ -146,7 +146,7 @@ def search_by_projection_last(kps, desc_cur, uRight, grid_start, grid_idx, scale
     a = [np.ascontiguousarray(x, t) for x, t in ((desc_cur, u8), (uRight, f32), (grid_start, i32), (grid_idx, i32), (scale, f32), (world_pos, f32),
                                                    (desc, u8), (octave, i32), (angle, f32), (flags, u8), (Rcw, f32), (tcw, f32))]
     match = np.zeros(max(kps.size, 1), i32)
-    nm = lib().orc_search_by_projection_last(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), *[float(v) for v in bounds],
+    nm = lib().orc_search_by_projection_last(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), a[4].size, *[float(v) for v in bounds],
                                              a[9].size, _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(a[9]), _p(a[10]), _p(a[11]),
                                              *[float(v) for v in cam], int(mode), float(th), int(bool(check_orientation)), _p(match))
     return match[:kps.size], nm
@@ -161,7 +161,7 @@ def search_by_projection_map(kps, desc_cur, uRight, grid_start, grid_idx, scale,
                                                    (view_cos, f32), (level, i32), (desc, u8), (flags, u8))]
     cb = np.ascontiguousarray(cur_blocked, u8) if cur_blocked is not None else None
     match = np.zeros(max(kps.size, 1), i32)
-    nm = lib().orc_search_by_projection_map(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), *[float(v) for v in bounds],
+    nm = lib().orc_search_by_projection_map(_p(kps), kps.size, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), a[4].size, *[float(v) for v in bounds],
                                             a[9].size, _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(a[9]), _p(cb) if cb is not None else None,
                                             float(th), float(nnratio), _p(match))
     return match[:kps.size], nm

@@ -390,6 +390,24 @@ def test_n1_frame_postprocess(gpu_api, oracle, intro):
     assert (qual[0, :int(cnt[0])] == 1.0).all()
 
 
+def test_cost_map_on_a_handle_without_introspection_survives_growth(gpu_api, oracle):
+    """A cost-map on a handle created WITHOUT introspection is a supported use (mvKeyQualScore, Frame.cc:128-139).  The
+    cost planes must follow when the batch or the image grows (they are not part of the introspection-only allocation)."""
+    g = gpu_api.ORBextractor(1000, 1.2, 8, 20, 7, False)
+    for n, w, h in ((1, 480, 320), (4, 480, 320), (2, 960, 600), (5, 1241, 376)):
+        L = np.stack([S.make_image(w, h, 300 + i) for i in range(n)])
+        cost = np.stack([S.make_cost_map(w, h, 310 + i) for i in range(n)])
+        kps, desc, cnt = g.extract_batch(L, cost)
+        qual, gs, gi = g.frame_postprocess(0.0, float(w), 0.0, float(h))
+        for f in range(n):
+            m = int(cnt[f])
+            ko, do = oracle.OracleExtractor(1000, 1.2, 8, 20, 7, False)(L[f], cost[f])      # flag off: the map must not weight anything
+            assert_keypoints_equal(kps[f, :m], ko, "no-introspection %dx%d frame %d" % (w, h, f))
+            q, s_, i_ = oracle.frame_post(kps[f, :m], cost[f], 0.0, float(w), 0.0, float(h))
+            assert np.array_equal(qual[f, :m], q) and np.array_equal(gs[f], s_)
+            assert np.array_equal(g.level(0, 2, f), cost[f]), "cost plane of frame %d" % f
+
+
 # ----------------------------------------------------------------------------- N4: input prologue (remap + cvtColor fused into the upload)
 @pytest.mark.parametrize("cn,rgb,remap", [(1, False, True), (3, False, True), (3, True, True), (4, True, True), (3, False, False), (4, False, False)])
 def test_n4_prologue_matches_oracle(gpu_api, oracle, cn, rgb, remap):
