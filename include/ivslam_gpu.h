@@ -245,6 +245,8 @@ int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches);
 /* Test hook: runs the warp-parallel replay of libstdc++'s std::nth_element(first, first+nth, last, key-greater) used by the
  * selection kernel on n keys (n <= 4000) and returns the resulting permutation (original indices in their new order). */
 int ivg_debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order);
+/* the same replay by a 1024-thread CTA (what k_level_select uses for the level trim of a single frame) */
+int ivg_debug_nth_element_block(int device, const uint32_t* keys, int n, int nth, uint32_t* order);
 /* When enabled (default off) run_batch wraps the kernel sequence of a batch in a CUDA graph that is re-used while
  * shape/batch stay the same. */
 int ivg_set_graph_mode(ivg_extractor* h, int enable);

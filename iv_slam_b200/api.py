@@ -98,6 +98,7 @@ def lib():
         "ivg_profile_enable": (C.c_int, [vp, C.c_int]),
         "ivg_profile_read": (C.c_int, [vp, vp, vp]),
         "ivg_debug_nth_element": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+        "ivg_debug_nth_element_block": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -485,9 +486,10 @@ def compute_stereo_matches_keypoints(left, right, kL, dL, kR, dR, mbf, maxD):
     return u, d
 
 
-def debug_nth_element(keys, nth, device=0):
-    """Permutation produced by the GPU's warp-parallel nth_element replay (test hook)."""
+def debug_nth_element(keys, nth, device=0, block=False):
+    """Permutation produced by the GPU's warp-parallel (or, block=True, CTA-parallel) nth_element replay (test hook)."""
     keys = np.ascontiguousarray(keys, np.uint32)
     order = np.zeros(keys.size, np.uint32)
-    _ck(lib().ivg_debug_nth_element(device, _p(keys), keys.size, int(nth), _p(order)), "ivg_debug_nth_element")
+    fn = lib().ivg_debug_nth_element_block if block else lib().ivg_debug_nth_element
+    _ck(fn(device, _p(keys), keys.size, int(nth), _p(order)), "ivg_debug_nth_element")
     return order

@@ -96,6 +96,8 @@ struct ivg_extractor {
   cudaEvent_t evD2H = nullptr;          // copyOut: results of the last run have been read (next run may overwrite them)
   cudaEvent_t evStereo = nullptr;       // stream (left handle): matcher finished reading both handles
   cudaEvent_t evD2Hs = nullptr;         // copyOut (left handle): uRight/depth have been read
+  cudaStream_t aux = nullptr;           // side stream for the blur of small batches (forked from / joined into `stream`)
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t evConsumed = nullptr;     // recorded (on the matcher's stream) when another handle's kernels have read our buffers
   cudaEvent_t waitFor = nullptr;        // set to evConsumed (our own event) when it must complete before we overwrite our buffers
   long long launches = 0;
@@ -111,6 +113,7 @@ struct ivg_extractor {
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
   DevBuf<uint8_t> projIn; DevBuf<uint2> projCand; DevBuf<int> projInt;   // N2 scratch
+  void* outHost = nullptr; size_t outHostBytes = 0;                         // pinned staging for the results of the synchronous calls
   void* projHost = nullptr; size_t projHostBytes = 0;                       // N2 pinned staging (inputs, then match[] + nmatches)
   bool haveGrid = false, haveStereo = false;
   DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
@@ -132,6 +135,7 @@ struct ivg_extractor {
   DevBuf<int> gridStart, gridIdx;
   // stereo on caller-supplied keypoints
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
+  DevBuf<float> extU, extD; DevBuf<int> extS;        // results of ivg_stereo_match_keypoints (kept across calls)
   bool graphMode = false;
   cudaGraphExec_t graphExec = nullptr;   // captured kernel sequence of one run (re-captured when batch / mode / buffers change)
   int graphBatch = 0, graphLaunches = 0;
@@ -482,8 +486,19 @@ int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
 int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   int rc = launch_pyramid(h, fs);
   if (rc) return rc;
+  // one frame at a time: the blur only needs the pyramid, so it runs on a side stream next to FAST + selection and joins
+  // before the descriptors (a fork/join inside the captured graph in graph mode).  Big batches fill the GPU with either
+  // kernel alone and co-running them was measured slower, so they stay on one stream.
+  const bool fork = h->aux && !h->profile && fs.btTotal * fs.nImages <= 4 * 148;
+  if (fork) {
+    CK(cudaEventRecord(h->evFork, h->stream));
+    CK(cudaStreamWaitEvent(h->aux, h->evFork, 0));
+    h->launches++;
+    k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->aux>>>(fs, h->blurMaps);
+    CK(cudaEventRecord(h->evJoin, h->aux));
+  }
   { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS, h->fastSmem, h->stream>>>(fs); }
-  { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
+  if (!fork) { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
   if (h->kpMode == 1) { ProfScope ps(h, IVG_K_SELECT); k_octree_select<<<dim3(fs.nlevels, fs.nImages), 256, sizeof(OctShared), h->stream>>>(fs); }
   else {
     // few CTAs (one per level and frame): give each every warp it can use; big batches fill the GPU with 8-warp CTAs
@@ -492,7 +507,15 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
     if (lat) k_level_select<SEL_WARPS_LAT * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS_LAT * 32, h->selSmemLat, h->stream>>>(fs);
     else k_level_select<SEL_WARPS * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs);
   }
-  { ProfScope ps(h, IVG_K_DESCRIBE); k_orient_describe<<<dim3((fs.kpCap + DK_SLOTS - 1) / DK_SLOTS, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN); }
+  if (fork) CK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+  {
+    ProfScope ps(h, IVG_K_DESCRIBE);
+    // one frame at a time: 16 keypoint slots per CTA, so that ~2000 keypoints spread over 125 CTAs instead of 32
+    if ((fs.kpCap + DK_SLOTS_BATCH - 1) / DK_SLOTS_BATCH * fs.nImages < 2 * 148)
+      k_orient_describe<DK_SLOTS_LAT><<<dim3((fs.kpCap + DK_SLOTS_LAT - 1) / DK_SLOTS_LAT, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN);
+    else
+      k_orient_describe<DK_SLOTS_BATCH><<<dim3((fs.kpCap + DK_SLOTS_BATCH - 1) / DK_SLOTS_BATCH, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN);
+  }
   CK(cudaGetLastError());
   return IVG_OK;
 }
@@ -608,7 +631,8 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
   }
   bool ok = cudaStreamCreateWithFlags(&h->copyIn, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->copyOut, cudaStreamNonBlocking) == cudaSuccess;
-  for (cudaEvent_t* e : {&h->evH2D, &h->evIngest, &h->evKernels, &h->evD2H, &h->evStereo, &h->evD2Hs, &h->evConsumed})
+  ok = ok && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess;
+  for (cudaEvent_t* e : {&h->evH2D, &h->evIngest, &h->evKernels, &h->evD2H, &h->evStereo, &h->evD2Hs, &h->evConsumed, &h->evFork, &h->evJoin})
     ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
   if (!ok || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->evDone, cudaEventDisableTiming) != cudaSuccess ||
@@ -627,18 +651,19 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
-  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release(); if (h->projHost) { cudaFreeHost(h->projHost); h->projHost = nullptr; }
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release(); if (h->projHost) { cudaFreeHost(h->projHost); h->projHost = nullptr; } if (h->outHost) { cudaFreeHost(h->outHost); h->outHost = nullptr; }
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
-  h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->sortedR.release(); h->rowStart.release();
+  h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->extU.release(); h->extD.release(); h->extS.release(); h->sortedR.release(); h->rowStart.release();
   for (cudaEvent_t e : h->profEv) cudaEventDestroy(e);
   drop_graph(h);
   if (h->evDone) cudaEventDestroy(h->evDone);
   if (h->evT0) cudaEventDestroy(h->evT0);
   if (h->evT1) cudaEventDestroy(h->evT1);
-  for (cudaEvent_t e : {h->evH2D, h->evIngest, h->evKernels, h->evD2H, h->evStereo, h->evD2Hs, h->evConsumed}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->evH2D, h->evIngest, h->evKernels, h->evD2H, h->evStereo, h->evD2Hs, h->evConsumed, h->evFork, h->evJoin}) if (e) cudaEventDestroy(e);
+  if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
   if (h->copyIn) cudaStreamDestroy(h->copyIn);
   if (h->copyOut) cudaStreamDestroy(h->copyOut);
   if (h->stream && h->ownsStream) cudaStreamDestroy(h->stream);
@@ -1008,6 +1033,19 @@ int ivg_run_batch(ivg_extractor* h) {
   return IVG_OK;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+static int ensure_out_host(ivg_extractor* h, size_t bytes) {
+  if (h->outHostBytes >= bytes) return IVG_OK;
+  if (h->outHost) { cudaFreeHost(h->outHost); h->outHost = nullptr; h->outHostBytes = 0; }
+  CK(cudaHostAlloc(&h->outHost, bytes, cudaHostAllocPortable));
+  h->outHostBytes = bytes;
+  return IVG_OK;
+}
+
 int ivg_download_batch(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
   if (!h || !h->haveResults) return IVG_ERR_STATE;
   if (cap < h->fs.kpCap) return IVG_ERR_CAPACITY;
@@ -1047,8 +1085,30 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
   int rc = ivg_upload_batch(h, n, images, width, height, stride, frame_bytes, costs, cost_stride, cost_frame_bytes);
   if (rc) return rc;
   if ((rc = ivg_run_batch(h))) return rc;
-  if ((rc = ivg_download_batch(h, keypoints, descriptors, cap, n_out))) return rc;
-  return ivg_sync(h);
+  if (!keypoints || !descriptors || !n_out || is_pinned(keypoints)) {
+    if ((rc = ivg_download_batch(h, keypoints, descriptors, cap, n_out))) return rc;
+    return ivg_sync(h);
+  }
+  // Pageable result buffers (a std::vector<cv::KeyPoint>, a cv::Mat): a device-to-host copy straight into them goes through
+  // the driver's bounce buffers and blocks; land the records in the handle's pinned staging instead and copy only the
+  // n records each frame really produced.
+  const size_t k = h->fs.kpCap, per = k * 60;
+  if ((rc = ensure_out_host(h, (size_t)n * per + (size_t)n * sizeof(int)))) return rc;
+  uint8_t* stg = (uint8_t*)h->outHost;
+  int* cnt = reinterpret_cast<int*>(stg + (size_t)n * per);
+  CK(cudaStreamWaitEvent(h->copyOut, h->evKernels, 0));
+  CK(cudaMemcpyAsync(stg, h->outKp.p, (size_t)n * k * 28, cudaMemcpyDeviceToHost, h->copyOut));
+  CK(cudaMemcpyAsync(stg + (size_t)n * k * 28, h->outDesc.p, (size_t)n * k * 32, cudaMemcpyDeviceToHost, h->copyOut));
+  CK(cudaMemcpyAsync(cnt, h->outN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
+  CK(cudaEventRecord(h->evD2H, h->copyOut));
+  if ((rc = ivg_sync(h))) return rc;
+  for (int f = 0; f < n; ++f) {
+    const int m = std::min(std::max(cnt[f], 0), (int)k);
+    n_out[f] = cnt[f];
+    std::memcpy(reinterpret_cast<uint8_t*>(keypoints) + (size_t)f * cap * 28, stg + (size_t)f * k * 28, (size_t)m * 28);
+    std::memcpy(descriptors + (size_t)f * cap * 32, stg + (size_t)n * k * 28 + (size_t)f * k * 32, (size_t)m * 32);
+  }
+  return IVG_OK;
 }
 
 int ivg_extract(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride,
@@ -1153,6 +1213,19 @@ int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf,
   CK(cudaEventRecord(right->evConsumed, left->stream));          // the right handle's own event: survives the left handle
   right->waitFor = right->evConsumed;
   CK(cudaStreamWaitEvent(left->copyOut, left->evStereo, 0));
+  if (sync && uRight && depth && !is_pinned(uRight)) {           // pageable mvuRight / mvDepth: through the pinned staging (see ivg_extract_batch)
+    if ((rc = ensure_out_host(left, 2 * (size_t)n * k * 4))) return rc;
+    float* stg = (float*)left->outHost;
+    CK(cudaMemcpyAsync(stg, left->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
+    CK(cudaMemcpyAsync(stg + (size_t)n * k, left->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
+    CK(cudaEventRecord(left->evD2Hs, left->copyOut));
+    if ((rc = ivg_sync(left))) return rc;
+    for (int f = 0; f < n; ++f) {
+      std::memcpy(uRight + (size_t)f * cap, stg + (size_t)f * k, k * 4);
+      std::memcpy(depth + (size_t)f * cap, stg + (size_t)n * k + (size_t)f * k, k * 4);
+    }
+    return IVG_OK;
+  }
   if (uRight) CK(cudaMemcpy2DAsync(uRight, (size_t)cap * 4, left->uRight.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, left->copyOut));
   if (depth) CK(cudaMemcpy2DAsync(depth, (size_t)cap * 4, left->depth.p, k * 4, k * 4, n, cudaMemcpyDeviceToHost, left->copyOut));
   CK(cudaEventRecord(left->evD2Hs, left->copyOut));
@@ -1180,7 +1253,7 @@ int ivg_stereo_match_keypoints(ivg_extractor* left, ivg_extractor* right, const 
   if ((rc = left->extKpL.alloc((size_t)cap * 28)) || (rc = left->extDescL.alloc((size_t)cap * 32)) ||
       (rc = left->extKpR.alloc((size_t)cap * 28)) || (rc = left->extDescR.alloc((size_t)cap * 32)) || (rc = left->nExt.alloc(2)))
     return rc;
-  DevBuf<float> u, d; DevBuf<int> s;
+  DevBuf<float>&u = left->extU, &d = left->extD; DevBuf<int>& s = left->extS;
   if ((rc = u.alloc(cap)) || (rc = d.alloc(cap)) || (rc = s.alloc(cap))) return rc;
   CK(cudaEventRecord(right->evDone, right->stream));
   CK(cudaStreamWaitEvent(left->stream, right->evDone, 0));
@@ -1203,7 +1276,6 @@ int ivg_stereo_match_keypoints(ivg_extractor* left, ivg_extractor* right, const 
   if (!rc && uRight) { cudaError_t e = cudaMemcpyAsync(uRight, u.p, (size_t)nL * 4, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) rc = IVG_ERR_CUDA; }
   if (!rc && depth) { cudaError_t e = cudaMemcpyAsync(depth, d.p, (size_t)nL * 4, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) rc = IVG_ERR_CUDA; }
   cudaError_t e = cudaStreamSynchronize(st);
-  u.release(); d.release(); s.release();
   if (e != cudaSuccess) { g_cuda_err = cudaGetErrorString(e); return IVG_ERR_CUDA; }
   return rc;
 }
@@ -1264,7 +1336,10 @@ int ivg_flush_l2(ivg_extractor* h, size_t bytes) {
   CK(cudaMemsetAsync(scratch.p, 0x5a, bytes, h->stream));
   return IVG_OK;
 }
-int ivg_debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order) {
+static int debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order, int threads);
+int ivg_debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order) { return debug_nth_element(device, keys, n, nth, order, 32); }
+int ivg_debug_nth_element_block(int device, const uint32_t* keys, int n, int nth, uint32_t* order) { return debug_nth_element(device, keys, n, nth, order, 1024); }
+static int debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order, int threads) {
   if (!keys || !order || n < 1 || n > 4000 || nth < 0 || nth >= n) return IVG_ERR_INVALID;
   int rc = ivg_device_info(device, nullptr, 0, nullptr, nullptr);
   if (rc) return rc;
@@ -1274,7 +1349,7 @@ int ivg_debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint
   CK(cudaMemcpy(dk.p, keys, (size_t)n * 4, cudaMemcpyHostToDevice));
   const size_t smem = (size_t)n * 8 + (size_t)n * 4 + 16;
   CK(cudaFuncSetAttribute(k_debug_nth_element, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  k_debug_nth_element<<<1, 32, smem>>>(dk.p, n, nth, dord.p);
+  k_debug_nth_element<<<1, threads, smem>>>(dk.p, n, nth, dord.p);
   CK(cudaGetLastError());
   CK(cudaMemcpy(order, dord.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   dk.release(); dord.release();

@@ -4,12 +4,13 @@
 // computeDescriptors/computeOrbDescriptor (:1215-1222, :108-148), plus the final bookkeeping of operator()
 // (:1263-1295): level-major concatenation, pt *= scale for levels > 0, size/octave/class_id fields.
 //
-// One CTA = 32 keypoint slots, one warp per keypoint (4 keypoints per warp), three phases:
+// One CTA = DK_SLOTS keypoint slots (64 for batches, 16 when a launch would otherwise leave most SMs idle: one frame at a
+// time), one warp per keypoint (DK_SLOTS/8 keypoints per warp), three phases:
 //   moments  IC_Angle reads the UNBLURRED level: lanes = 3 rows x 9 aligned words, 11 coalesced load instructions per
 //            keypoint, reduced with DP4A against the in-circle byte masks of the rows (the umax table); integer moments
 //            are exact and order-free;
 //   angle    ONE lane per keypoint: cv::fastAtan2's float polynomial without FMA and cos/sin of the angle
-//            evaluated in double and rounded to float — 32 keypoints share one pass through the double-precision code
+//            evaluated in double and rounded to float — the CTA's keypoints share one pass through the double-precision code
 //            instead of every warp repeating it (the reference calls glibc cosf/sinf; measured disagreement of the two
 //            is ~1 descriptor bit in 5e7, SURVEY Q9 — the only source of non-identical descriptor bits);
 //   brief    the descriptor reads the BLURRED level: each lane owns one descriptor byte = 8 pattern pairs = 16 rotated
@@ -47,11 +48,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int DK_SLOTS = 64;             // keypoint slots per CTA
+constexpr int DK_SLOTS_BATCH = 64;       // keypoint slots per CTA, throughput configuration
+constexpr int DK_SLOTS_LAT = 16;         // latency configuration (small batches): 4x the CTAs, 2 keypoints per warp
 constexpr int DK_PR = 18;                // |rotated pattern offset| <= 18 (pattern radius 13*sqrt(2) rounds to 18)
 constexpr int DK_BOXW = 64, DK_BOXH = 2 * DK_PR + 1;   // TMA box: 64 x 37 bytes
 constexpr int DK_BOXN = 48;                             // narrow box for keypoints whose 37 columns start within 11 bytes of a 16-byte boundary
 
+template <int DK_SLOTS>
 __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaMaps mapsN) {
   __shared__ __align__(128) uint8_t spatch[8][2][DK_BOXW * DK_BOXH + 64];     // +64 keeps every buffer 128-byte aligned
   __shared__ __align__(8) uint64_t bars[8][2];

@@ -5,10 +5,11 @@
 //   (k_fast_cells in k_fast.cuh produced, per cell: the row-major corner list, the corner counts at iniThFAST /
 //    minThFAST for the "<= 3 keypoints => retry with minThFAST" rule (:1045-1052, post-NMS counts) and the cost-map
 //    window sum for IV-SLAM's introspection weighting (:976-984).)
-//   k_level_select one CTA per (level, frame): thread 0 replays the sequential budget logic (cell weights :942-987,
-//                 per-cell budgets :1028-1031/:1085-1096, the one-shot redistribution loop :1101-1133);
-//                 each warp then trims cells with the replayed std::nth_element (retainBest + resize, :1146-1148),
-//                 and thread 0 trims the level (:1162-1166).  Output order = reference order.
+//   k_level_select one CTA per (level, frame): warp 0 replays the budget logic (cell weights :942-987, per-cell budgets
+//                 :1028-1031/:1085-1096 lane-parallel, the one-shot redistribution loop :1101-1133 — a true recurrence,
+//                 SURVEY Q4 — on one lane); each warp then trims cells with the replayed std::nth_element (retainBest +
+//                 resize, :1146-1148), and warp 0 (or the whole CTA, one frame at a time) trims the level (:1162-1166).
+//                 Output order = reference order.
 // Deterministic: no atomics decide any order.
 #pragma once
 #include "common.cuh"
@@ -105,6 +106,93 @@ __device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uin
   __syncwarp();
 }
 
+// The same replay executed by a whole CTA (the one-frame-at-a-time configuration: one CTA per level, 32 warps): every
+// partition round handles all elements at once — stopper ranks from warp ballots plus a prefix over the warps' counts,
+// m from __syncthreads_count (the predicate F[i] < R[TR-1-i] is a prefix of trues), swaps in parallel.  Identical
+// permutation; every thread of the CTA must call it (n <= 65535, lists in shared memory).
+__device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int* wcnt /*[2*32]*/) {
+  if (n == 0 || nth == n) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+  int first = 0, last = n;
+  int depth = 2 * (31 - __clz(n));
+  const unsigned lt = (1u << lane) - 1u;
+  while (last - first > 3) {
+    if (depth == 0) {
+      if (tid == 0) { sel_heap_select(a + first, nth + 1 - first, last - first); sel_swap(a, first, nth); }
+      __syncthreads();
+      return;
+    }
+    --depth;
+    if (tid == 0) {
+      const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
+      if (sel_before(a[A], a[B])) {
+        if (sel_before(a[B], a[C])) sel_swap(a, first, B);
+        else if (sel_before(a[A], a[C])) sel_swap(a, first, C);
+        else sel_swap(a, first, A);
+      } else if (sel_before(a[A], a[C])) sel_swap(a, first, A);
+      else if (sel_before(a[B], a[C])) sel_swap(a, first, C);
+      else sel_swap(a, first, B);
+    }
+    __syncthreads();
+    const uint32_t pkey = a[first].key;
+    const int lo = first + 1, hi = last;
+    int TL = 0, TR = 0;
+    for (int base = lo; base < hi; base += nthr) {
+      const int j = base + tid;
+      const bool v = j < hi;
+      const uint32_t k = v ? a[j].key : 0u;
+      const bool isL = v && !(k > pkey), isR = v && !(pkey > k);
+      const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
+      if (lane == 0) { wcnt[warp] = __popc(mL); wcnt[32 + warp] = __popc(mR); }
+      __syncthreads();
+      // exclusive prefix of this warp's counts over the warps before it, and the totals: one lane per warp + a shuffle scan
+      int sl = lane < nw ? wcnt[lane] : 0, sr = lane < nw ? wcnt[32 + lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int vl = __shfl_up_sync(0xffffffffu, sl, o), vr = __shfl_up_sync(0xffffffffu, sr, o);
+        if (lane >= o) { sl += vl; sr += vr; }
+      }
+      const int tL = __shfl_sync(0xffffffffu, sl, 31), tR = __shfl_sync(0xffffffffu, sr, 31);
+      const int pL = warp ? __shfl_sync(0xffffffffu, sl, warp - 1) : 0, pR = warp ? __shfl_sync(0xffffffffu, sr, warp - 1) : 0;
+      if (isL) sF[TL + pL + __popc(mL & lt)] = (uint16_t)j;
+      if (isR) sR[TR + pR + __popc(mR & lt)] = (uint16_t)j;
+      TL += tL; TR += tR;
+      __syncthreads();
+    }
+    int m = 0;
+    const int lim = min(TL, TR);
+    for (int base = 0; base < lim; base += nthr) {
+      const int i = base + tid;
+      const bool ok = i < lim && sF[i] < sR[TR - 1 - i];
+      const int c = __syncthreads_count(ok);
+      m += c;
+      if (c != nthr) break;                                 // CTA-uniform
+    }
+    for (int i = tid; i < m; i += nthr) {
+      const int x = sF[i], y = sR[TR - 1 - i];
+      const SelItem t = a[x]; a[x] = a[y]; a[y] = t;
+    }
+    const int rprev = m > 0 ? (int)sR[TR - m] : hi;
+    const int cut = (m < TL && (int)sF[m] < rprev) ? (int)sF[m] : rprev;
+    __syncthreads();
+    if (cut <= nth) first = cut; else last = cut;
+  }
+  if (tid == 0) {
+    for (int i = first + 1; i < last; ++i) {
+      const SelItem v = a[i];
+      if (sel_before(v, a[first])) {
+        for (int j = i; j > first; --j) a[j] = a[j - 1];
+        a[first] = v;
+      } else {
+        int j = i;
+        while (sel_before(v, a[j - 1])) { a[j] = a[j - 1]; --j; }
+        a[j] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // test hook: one warp runs warp_nth_element on n (key, index) items staged in shared memory
 __global__ void k_debug_nth_element(const uint32_t* keys, int n, int nth, uint32_t* order) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -112,6 +200,14 @@ __global__ void k_debug_nth_element(const uint32_t* keys, int n, int nth, uint32
   uint16_t* sF = reinterpret_cast<uint16_t*>(a + n);
   uint16_t* sR = sF + n;
   const int lane = threadIdx.x;
+  if (blockDim.x > 32) {          // the CTA-wide replay of the one-frame-at-a-time configuration
+    __shared__ int wc[64];
+    for (int i = lane; i < n; i += blockDim.x) a[i] = SelItem{keys[i], (uint32_t)i};
+    __syncthreads();
+    block_nth_element(a, nth, n, sF, sR, wc);
+    for (int i = lane; i < n; i += blockDim.x) order[i] = a[i].val;
+    return;
+  }
   for (int i = lane; i < n; i += 32) a[i] = SelItem{keys[i], (uint32_t)i};
   __syncwarp();
   warp_nth_element(a, nth, n, sF, sR, lane);
@@ -205,29 +301,81 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    int nNoMore = 0, nToDistribute = 0;
-    for (int c = 0; c < nCells; ++c) {            // :1082-1097
-      const int nKeys = S.nTotal[c];
-      const float f = S.nfc[c];
-      if ((float)nKeys > f) { S.nRetain[c] = (int)f; S.noMore[c] = 0; }
-      else {
-        S.nRetain[c] = nKeys;
-        nToDistribute = (int)__fadd_rn((float)nToDistribute, __fsub_rn(f, (float)nKeys));
-        S.noMore[c] = 1; nNoMore++;
+  if (warp == 0) {
+    // :1082-1097.  Per cell the test and nToRetain are independent; nToDistribute is the reference's running
+    // `int += float` (int = (int)((float)int + float)).  When every term is a finite integer-valued float and the sum stays
+    // far below 2^24 all those additions are exact, so the running value equals the integer sum: lanes add in parallel.
+    // Anything else (NaN / inf budgets from degenerate cost-maps) replays the recurrence on lane 0.
+    int nNoMore = 0, isum = 0;
+    bool exact = true;
+    for (int base = 0; base < nCells; base += 32) {
+      const int c = base + lane;
+      bool nm = false; int d = 0;
+      if (c < nCells) {
+        const int nKeys = S.nTotal[c];
+        const float f = S.nfc[c];
+        if ((float)nKeys > f) { S.nRetain[c] = (int)f; S.noMore[c] = 0; }
+        else {
+          S.nRetain[c] = nKeys; S.noMore[c] = 1; nm = true;
+          const float df = __fsub_rn(f, (float)nKeys);
+          if (!(fabsf(df) < 8192.0f) || df != truncf(df)) exact = false; else d = (int)df;
+        }
       }
+      nNoMore += __popc(__ballot_sync(0xffffffffu, nm));
+      isum += d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+    exact = __all_sync(0xffffffffu, exact) && nCells <= SEL_MAX_CELLS;      // every partial sum stays below 1024 * 8192 = 2^23
+    int nToDistribute = isum;
+    __syncwarp();
+    if (!exact) {          // uniform
+      nToDistribute = 0;
+      if (lane == 0)
+        for (int c = 0; c < nCells; ++c)
+          if (S.noMore[c]) nToDistribute = (int)__fadd_rn((float)nToDistribute, __fsub_rn(S.nfc[c], (float)S.nTotal[c]));
+      nToDistribute = __shfl_sync(0xffffffffu, nToDistribute, 0);
     }
     if (nToDistribute > 0 && nNoMore < nCells) {  // the while loop runs exactly once (:1103-1133)
-      for (int c = 0; c < nCells; ++c) {
-        if (S.noMore[c]) continue;
-        const int nNew = (int)__fadd_rn(S.nfc[c], ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore))));
-        if (S.nTotal[c] > nNew) S.nRetain[c] = nNew;
-        else { S.nRetain[c] = S.nTotal[c]; nToDistribute += nNew - S.nTotal[c]; S.noMore[c] = 1; nNoMore++; }
+      // A true recurrence over the cells in order (a cell that cannot absorb its share changes the share of the cells after
+      // it).  Every lane replays it (the running values are warp-uniform); the cells' inputs sit in registers, one cell per
+      // lane, and are broadcast by shuffles, so the dependent chain per cell is a float add and a compare, not a trip
+      // through shared memory.  The share is only re-divided after a cell that saturates.
+      float share = ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
+      for (int base = 0; base < nCells; base += 32) {
+        const int c = base + lane;
+        const bool in = c < nCells;
+        bool nm = in ? S.noMore[c] != 0 : true;
+        const float f = in ? S.nfc[c] : 0.f;
+        const int nt = in ? S.nTotal[c] : 0;
+        int nr = in ? S.nRetain[c] : 0;
+        const int kend = min(32, nCells - base);
+        for (int k = 0; k < kend; ++k) {
+          if (__shfl_sync(0xffffffffu, (int)nm, k)) continue;
+          const int nNew = (int)__fadd_rn(__shfl_sync(0xffffffffu, f, k), share);
+          const int nTot = __shfl_sync(0xffffffffu, nt, k);
+          if (nTot > nNew) { if (lane == k) nr = nNew; }
+          else {
+            if (lane == k) { nr = nTot; nm = true; }
+            nToDistribute += nNew - nTot; nNoMore++;
+            share = ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
+          }
+        }
+        if (in) { S.nRetain[c] = nr; S.noMore[c] = nm ? 1 : 0; }
       }
     }
-    int run = 0;
-    for (int c = 0; c < nCells; ++c) { S.prefix[c] = run; run += min(max(S.nRetain[c], 0), S.nTotal[c]); }
-    sTotal = run;
+    __syncwarp();
+    int run = 0;      // prefix[c] = retained keypoints of the cells before c (warp scan)
+    for (int base = 0; base < nCells; base += 32) {
+      const int c = base + lane;
+      const int k = c < nCells ? min(max(S.nRetain[c], 0), S.nTotal[c]) : 0;
+      int incl = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (c < nCells) S.prefix[c] = run + incl - k;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) sTotal = run;
   }
   __syncthreads();
 
@@ -278,7 +426,12 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
   __threadfence_block();
   __syncthreads();
 
-  if (warp == 0) {
+  if (MAX_THREADS >= 512 && levelBuf == S.levelBuf && total > L.nDesired && L.nDesired > 0) {
+    // latency configuration: the level's trim is the longest serial piece of the frame, all 32 warps take part
+    __shared__ int sWcnt[64];
+    block_nth_element(levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, sWcnt);
+    if (tid == 0) { sCount = L.nDesired; fs.levelCount[img * MAX_LEVELS + level] = L.nDesired; }
+  } else if (warp == 0) {
     int count = total;
     if (total > L.nDesired) {
       if (L.nDesired == 0) count = 0;

@@ -62,7 +62,7 @@ def lib(variant="asbuilt"):
                                    C.c_int, vp, vp, i32p, vp, vp, i32p, vp, vp, C.c_int]
     L.ref_stereo_frame.restype = C.c_int
     L.ref_stereo_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
-                                   C.c_size_t, C.c_float, C.c_float, C.c_int, vp, vp]
+                                   C.c_size_t, C.c_float, C.c_float, C.c_int, vp, vp, vp]
     L.ref_stereo_batch.restype = C.c_int
     assert L.ref_fp_contract() == (1 if variant == "asbuilt" else 0)
     _libs[variant] = L
@@ -162,15 +162,18 @@ def stereo_frame(left, right, imgL, imgR, cost, mbf, mb, threads=2):
     return dict(kL=kL[:a], dL=dL[:a], kR=kR[:b], dR=dR[:b], uRight=uR[:a], depth=dep[:a])
 
 
-def stereo_batch(params, imgsL, imgsR, mbf, mb, workers, variant="asbuilt"):
-    """CPU timing: frame-parallel over `workers` threads. imgs: [n,H,W] u8 contiguous."""
+def stereo_batch(params, imgsL, imgsR, mbf, mb, workers, variant="asbuilt", costs=None):
+    """CPU timing: frame-parallel over `workers` threads. imgs (and optional left-eye cost-maps): [n,H,W] u8 contiguous."""
     imgsL = np.ascontiguousarray(imgsL, np.uint8)
     imgsR = np.ascontiguousarray(imgsR, np.uint8)
+    if costs is not None:
+        costs = np.ascontiguousarray(costs, np.uint8)
+        assert costs.shape == imgsL.shape
     n, H, W = imgsL.shape
     nL = np.zeros(n, np.int32)
     nM = np.zeros(n, np.int32)
     rc = lib(variant).ref_stereo_batch(params["nfeatures"], params["scaleFactor"], params["nlevels"], params["iniThFAST"],
-                                       params["minThFAST"], n, _p(imgsL), _p(imgsR), W, H, W, mbf, mb, workers, _p(nL), _p(nM))
+                                       params["minThFAST"], n, _p(imgsL), _p(imgsR), W, H, W, mbf, mb, workers, _p(nL), _p(nM), _p(costs))
     if rc:
         raise RuntimeError("reference batch failed rc=%d" % rc)
     return nL, nM

@@ -163,12 +163,14 @@ int ref_stereo_frame(void* left, void* right, const uint8_t* imgL, const uint8_t
 
 // Frame-parallel batch for CPU timing: `workers` threads, each with its own extractor pair, pulling frames from a shared
 // counter; every frame runs as ref_stereo_frame with threads=1.
+// `costs` (nullable): n cost-maps, same layout as the images, applied to the left eye of an introspection-enabled extractor
+// (the right extractor never weights, Tracking.cc:182-183).
 int ref_stereo_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, int n,
                      const uint8_t* imgsL, const uint8_t* imgsR, int w, int hgt, size_t stride,
-                     float mbf, float mb, int workers, int* nL_out, int* nMatched_out) {
+                     float mbf, float mb, int workers, int* nL_out, int* nMatched_out, const uint8_t* costs) {
   std::atomic<int> next(0), err(0);
   auto work = [&] {
-    RefExtractor eL(nfeatures, scaleFactor, nlevels, iniTh, minTh, false), eR(nfeatures, scaleFactor, nlevels, iniTh, minTh, false);
+    RefExtractor eL(nfeatures, scaleFactor, nlevels, iniTh, minTh, costs != nullptr), eR(nfeatures, scaleFactor, nlevels, iniTh, minTh, false);
     const int cap = nfeatures + 64;
     std::vector<cv::KeyPoint> kL(cap), kR(cap);
     std::vector<uint8_t> dL((size_t)cap * 32), dR((size_t)cap * 32);
@@ -178,7 +180,8 @@ int ref_stereo_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, i
       if (f >= n) break;
       int nl = 0, nr = 0;
       int rc = ref_stereo_frame(&eL, &eR, imgsL + (size_t)f * hgt * stride, imgsR + (size_t)f * hgt * stride, w, hgt, stride,
-                                nullptr, 0, mbf, mb, cap, kL.data(), dL.data(), &nl, kR.data(), dR.data(), &nr, uR.data(), dep.data(), 1);
+                                costs ? costs + (size_t)f * hgt * stride : nullptr, stride, mbf, mb, cap, kL.data(), dL.data(), &nl, kR.data(), dR.data(), &nr,
+                                uR.data(), dep.data(), 1);
       if (rc) { err = rc; break; }
       int m = 0;
       for (int i = 0; i < nl; ++i) m += uR[i] >= 0;

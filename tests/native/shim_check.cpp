@@ -45,12 +45,21 @@ extern "C" int shim_construct_only() {
 // Drop-in latency: one stereo frame at a time exactly like the reference's Frame constructor — two std::threads run the
 // two extractor objects (src/Frame.cc:115-125), join, then ComputeStereoMatches (:193).  Returns mean milliseconds.
 #include "ivslam_gpu.h"
+// graph bit 0: CUDA-graph replay of the kernel sequence; bit 1: the caller keeps its two images in page-locked memory
+// (cv::cuda::HostMem / cudaHostAlloc — a one-line change where the reference allocates imLeft/imRight) so the upload is a
+// plain asynchronous DMA instead of the driver's pageable bounce path.
 extern "C" double shim_frame_latency_ms(const unsigned char* left, const unsigned char* right, int w, int h, int nfeatures,
                                         int iniTh, int minTh, float mbf, float maxD, int iters, int graph) {
+  void* pin[2] = {nullptr, nullptr};
   try {
     ORB_SLAM2::ORBextractor exL(nfeatures, 1.2f, 8, iniTh, minTh), exR(nfeatures, 1.2f, 8, iniTh, minTh);
-    ivg_set_graph_mode(exL.handle(), graph);
-    ivg_set_graph_mode(exR.handle(), graph);
+    ivg_set_graph_mode(exL.handle(), graph & 1);
+    ivg_set_graph_mode(exR.handle(), graph & 1);
+    if (graph & 2) {
+      if (ivg_host_alloc(&pin[0], (size_t)w * h) || ivg_host_alloc(&pin[1], (size_t)w * h)) return -1.0;
+      std::memcpy(pin[0], left, (size_t)w * h); std::memcpy(pin[1], right, (size_t)w * h);
+      left = (const unsigned char*)pin[0]; right = (const unsigned char*)pin[1];
+    }
     cv::Mat imL(h, w, CV_8UC1, (void*)left, (size_t)w), imR(h, w, CV_8UC1, (void*)right, (size_t)w), none;
     std::vector<cv::KeyPoint> kL, kR;
     cv::Mat dL, dR;
@@ -64,7 +73,9 @@ extern "C" double shim_frame_latency_ms(const unsigned char* left, const unsigne
     for (int i = 0; i < 5; ++i) frame();
     const auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < iters; ++i) frame();
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+    for (void* p : pin) if (p) ivg_host_free(p);
+    return ms;
   } catch (const std::exception&) {
     return -1.0;
   }

@@ -22,8 +22,8 @@ def measure(iters=200):
     left, right = S.make_stereo_pair(1241, 376, 0)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     out = {}
-    for g in (0, 1):
-        out["graph" if g else "plain"] = L.shim_frame_latency_ms(p(left), p(right), 1241, 376, 2000, 20, 7, C.c_float(386.1448), C.c_float(718.856), iters, g)
+    for g, name in ((0, "plain"), (1, "graph"), (3, "graph_pinned_input")):
+        out[name] = L.shim_frame_latency_ms(p(left), p(right), 1241, 376, 2000, 20, 7, C.c_float(386.1448), C.c_float(718.856), iters, g)
     return out
 
 if __name__ == "__main__":
