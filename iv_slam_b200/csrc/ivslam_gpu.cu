@@ -8,6 +8,7 @@
 // and sequences the launches on the handle's stream.  No CPU fallback exists: without a usable GPU every entry
 // point returns an error.
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -22,6 +23,7 @@
 #include "k_fast.cuh"
 #include "k_frame.cuh"
 #include "k_pyramid.cuh"
+#include "k_pyramid_fused.cuh"
 #include "k_select.cuh"
 #include "k_octree.cuh"
 #include "k_prologue.cuh"
@@ -123,6 +125,8 @@ struct ivg_extractor {
   TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
   bool resizeTma[MAX_LEVELS] = {false};
   TmaMaps descMapsN{};                  // the same with 48 x 37 boxes
+  DevBuf<PyrSpan> pyrSpanX, pyrSpanY;   // k_pyramid_fused window tables (level-major)
+  int pyrTX = 0, pyrTY = 0; size_t pyrFusedBuf = 0, pyrFusedSmem = 0; int pyrTapOffX[MAX_LEVELS] = {0}, pyrTapOffY[MAX_LEVELS] = {0};   // 0 tiles: the fused cascade is not available for this shape
   TmaMaps descMaps{};                   // per level: 64 x 37 x 1 boxes over the blurred planes (k_orient_describe)
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
@@ -355,6 +359,52 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
       resizeSmem = std::max(resizeSmem, align_up((size_t)L.rzPitch * L.rzRows, 128) + (size_t)L.rzRows * RZ_W * 2);
     }
   }
+  std::vector<PyrSpan> spanX, spanY;
+  {
+    // k_pyramid_fused: windows of every level for every tile column / row (see k_pyramid_fused.cuh)
+    const int TX = std::max(1, (W + 99) / 100), TY = std::max(1, (H + 79) / 80);
+    spanX.assign((size_t)nl * TX, PyrSpan{0, 0, 0, 0, 0, 0}); spanY.assign((size_t)nl * TY, PyrSpan{0, 0, 0, 0, 0, 0});
+    auto build = [&](int T, bool isX, std::vector<PyrSpan>& out) {
+      for (int t = 0; t < T; ++t) {
+        for (int l = 1; l < nl; ++l) {
+          const int dim = isX ? fs.lv[l].w : fs.lv[l].h;
+          auto split = [&](int k) { const int v = (int)((long long)k * dim / T); return k == T ? (isX ? (int)align_up(dim, 4) : dim) : (isX ? (v & ~3) : v); };
+          out[(size_t)l * T + t].o0 = split(t); out[(size_t)l * T + t].o1 = split(t + 1);
+        }
+        for (int l = nl - 1; l >= 0; --l) {
+          PyrSpan& s = out[(size_t)l * T + t];
+          int e0 = s.o0, e1 = s.o1;
+          const int dim = isX ? fs.lv[l].w : fs.lv[l].h;
+          e1 = std::min(e1, dim);                         // the owned x-range of the last column ends on a word boundary past the width
+          if (l + 1 < nl) {
+            const PyrSpan& up = out[(size_t)(l + 1) * T + t];
+            if (up.t1 > up.t0) {
+              const ResizeTap* tp = taps.data() + (isX ? fs.lv[l + 1].rtabX : fs.lv[l + 1].rtabY);
+              const int a = tp[up.t0].s0, b = tp[up.t1 - 1].s1 + 1;
+              if (e1 > e0) { e0 = std::min(e0, a); e1 = std::max(e1, b); } else { e0 = a; e1 = b; }
+            }
+          }
+          s.t0 = e0; s.t1 = e1;                           // needed range; computed range = whole words around it
+          if (isX) { e0 &= ~3; e1 = std::min((int)align_up(e1, 4), fs.lv[l].pitch); }
+          s.e0 = e0; s.e1 = e1;
+        }
+      }
+    };
+    build(TX, true, spanX);
+    build(TY, false, spanY);
+    size_t buf = 16, tapEntries = 0;
+    for (int l = 0; l < nl; ++l) {
+      int mw = 0, mh = 0;
+      for (int t = 0; t < TX; ++t) mw = std::max(mw, spanX[(size_t)l * TX + t].e1 - spanX[(size_t)l * TX + t].e0);
+      for (int t = 0; t < TY; ++t) mh = std::max(mh, spanY[(size_t)l * TY + t].e1 - spanY[(size_t)l * TY + t].e0);
+      buf = std::max(buf, align_up((size_t)mw * mh, 16));
+      h->pyrTapOffX[l] = (int)tapEntries; tapEntries += (size_t)mw;
+      h->pyrTapOffY[l] = (int)tapEntries; tapEntries += (size_t)mh;
+    }
+    h->pyrTX = TX; h->pyrTY = TY; h->pyrFusedBuf = buf;
+    h->pyrFusedSmem = 2 * buf + tapEntries * sizeof(ResizeTap);
+    if (h->pyrFusedSmem > 160 * 1024 || nl < 2) { h->pyrTX = 0; h->pyrTY = 0; }
+  }
   fs.planeBytes = align_up(planeOff, (size_t)fs.lv[0].pitch * 4);   // multiple of the level-0 pitch: batched 3-D copies
   while (fs.planeBytes % fs.lv[0].pitch) fs.planeBytes += 256;
   fs.listCapTotal = listOff;
@@ -389,6 +439,7 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   if ((rc = h->dCellsPlain.alloc(h->cellsPlain.size()))) return rc;
   if ((rc = h->dCellsWeighted.alloc(h->cellsWeighted.size()))) return rc;
   if ((rc = h->rtab.alloc(taps.size()))) return rc;
+  if ((rc = h->pyrSpanX.alloc(spanX.size())) || (rc = h->pyrSpanY.alloc(spanY.size()))) return rc;
   std::vector<uint32_t> btab;
   for (int l = 0; l < nl; ++l)
     for (int ty = 0; ty < fs.lv[l].btY; ++ty)
@@ -412,6 +463,8 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   CK(cudaMemcpyAsync(h->dCellsWeighted.p, h->cellsWeighted.data(), h->cellsWeighted.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->blurTiles.p, btab.data(), btab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   if (!taps.empty()) CK(cudaMemcpyAsync(h->rtab.p, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->pyrSpanX.p, spanX.data(), spanX.size() * sizeof(PyrSpan), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->pyrSpanY.p, spanY.data(), spanY.size() * sizeof(PyrSpan), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->outN.p, 0, B * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->levelCount.p, 0, B * MAX_LEVELS * sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
@@ -475,6 +528,18 @@ FrameSet active_fs(const ivg_extractor* h) {
 }
 
 int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
+  const int planes = fs.nImages * (fs.weighted ? 2 : 1);
+  static const bool noFused = getenv("IVSLAM_NO_FUSED_PYRAMID") != nullptr;      // developer A/B switch
+  if (h->pyrTX > 0 && !noFused && (long long)planes * h->pyrTX * h->pyrTY <= 2 * 148) {
+    // one frame at a time: the whole cascade in one launch (k_pyramid_fused.cuh) instead of nlevels-1 dependent ones
+    ProfScope ps(h, IVG_K_RESIZE);
+    PyrFusedArgs A{};
+    A.spanX = h->pyrSpanX.p; A.spanY = h->pyrSpanY.p; A.TX = h->pyrTX; A.TY = h->pyrTY; A.bufBytes = (int)h->pyrFusedBuf;
+    for (int l = 0; l < MAX_LEVELS; ++l) { A.tapOffX[l] = h->pyrTapOffX[l]; A.tapOffY[l] = h->pyrTapOffY[l]; }
+    k_pyramid_fused<<<dim3(h->pyrTX * h->pyrTY, planes), PF_THREADS, h->pyrFusedSmem, h->stream>>>(fs, A);
+    CK(cudaGetLastError());
+    return IVG_OK;
+  }
   for (int l = 1; l < fs.nlevels; ++l) {
     dim3 grid((fs.lv[l].w + RZ_W - 1) / RZ_W, (fs.lv[l].h + RZ_H - 1) / RZ_H, fs.nImages * (fs.weighted ? 2 : 1));   // image (+ cost-map) planes
     { ProfScope ps(h, IVG_K_RESIZE); k_resize_level<<<grid, 256, h->resizeSmem, h->stream>>>(fs, l, h->resizeMaps, h->resizeMapsQ, h->resizeTma[l] ? 1 : 0); }
@@ -565,6 +630,7 @@ int init_device_constants(int device) {
   CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_octree_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OctShared)));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_pyramid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_stereo_index, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return IVG_OK;
 }
@@ -652,7 +718,7 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
   h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release(); if (h->projHost) { cudaFreeHost(h->projHost); h->projHost = nullptr; } if (h->outHost) { cudaFreeHost(h->outHost); h->outHost = nullptr; }
-  h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
+  h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->pyrSpanX.release(); h->pyrSpanY.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
   h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();

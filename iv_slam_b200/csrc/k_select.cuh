@@ -337,10 +337,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
       nToDistribute = __shfl_sync(0xffffffffu, nToDistribute, 0);
     }
     if (nToDistribute > 0 && nNoMore < nCells) {  // the while loop runs exactly once (:1103-1133)
-      // A true recurrence over the cells in order (a cell that cannot absorb its share changes the share of the cells after
-      // it).  Every lane replays it (the running values are warp-uniform); the cells' inputs sit in registers, one cell per
-      // lane, and are broadcast by shuffles, so the dependent chain per cell is a float add and a compare, not a trip
-      // through shared memory.  The share is only re-divided after a cell that saturates.
+      // A true recurrence over the cells in order: a cell that cannot absorb its share changes the share of the cells after
+      // it.  The running values are warp-uniform; one cell per lane.
       float share = ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
       for (int base = 0; base < nCells; base += 32) {
         const int c = base + lane;
@@ -349,17 +347,20 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
         const float f = in ? S.nfc[c] : 0.f;
         const int nt = in ? S.nTotal[c] : 0;
         int nr = in ? S.nRetain[c] : 0;
-        const int kend = min(32, nCells - base);
-        for (int k = 0; k < kend; ++k) {
-          if (__shfl_sync(0xffffffffu, (int)nm, k)) continue;
-          const int nNew = (int)__fadd_rn(__shfl_sync(0xffffffffu, f, k), share);
-          const int nTot = __shfl_sync(0xffffffffu, nt, k);
-          if (nTot > nNew) { if (lane == k) nr = nNew; }
-          else {
-            if (lane == k) { nr = nTot; nm = true; }
-            nToDistribute += nNew - nTot; nNoMore++;
-            share = ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
-          }
+        // the cells of this chunk that still take part, in order; between two cells that saturate every cell sees the same
+        // share, so all of them are evaluated at once and committed up to the first one that saturates
+        unsigned pending = __ballot_sync(0xffffffffu, !nm);
+        while (pending) {
+          const int nNew = (int)__fadd_rn(f, share);
+          const unsigned bs = __ballot_sync(0xffffffffu, !(nt > nNew)) & pending;
+          const int k = bs ? __ffs(bs) - 1 : 32;
+          if (((pending >> lane) & 1u) && lane < k) nr = nNew;
+          if (k == 32) break;
+          const int dk = __shfl_sync(0xffffffffu, nNew - nt, k);
+          if (lane == k) { nr = nt; nm = true; }
+          nToDistribute += dk; nNoMore++;
+          share = ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
+          pending &= ~((2u << k) - 1u);
         }
         if (in) { S.nRetain[c] = nr; S.noMore[c] = nm ? 1 : 0; }
       }
