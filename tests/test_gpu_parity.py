@@ -601,3 +601,28 @@ def test_zz_report_flip_fraction_vs_reference_as_built(gpu_api):
     print("CUDA vs reference as-built: %d frames, %d of %d descriptor bits differ (%.3g)"
           % (st["frames"], st["desc_bits_differing"], st["desc_bits"], st["desc_bits_differing"] / max(st["desc_bits"], 1)))
     assert st["desc_bits_differing"] <= 1e-3 * st["desc_bits"]
+
+
+def test_second_gpu_reproduces_the_first_and_one_host_result_array(gpu_api):
+    """frames are sharded over GPUs with no exchange; every GPU must produce, for its frames, exactly
+    the bytes GPU 0 produces, and the single-process driver lands all of them in ONE host result array at the frames' offsets."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on the box")
+    from iv_slam_b200.frontend import StereoFrontend
+    from iv_slam_b200.multi import MultiGpuStereoFrontend
+    c = S.CONFIGS["C1"]
+    params = {k: c[k] for k in ("nfeatures", "scaleFactor", "nlevels", "iniThFAST", "minThFAST")}
+    n = 10
+    L, R = S.make_stereo_batch(c["w"], c["h"], n, 500, distinct=5)
+    one = StereoFrontend(params, c["w"], c["h"], 4, 2, device=0)
+    ref = one.alloc_outputs(n, pinned=False)
+    one.process(L, R, ref, c["mbf"], c["maxD"])
+    one.finish()
+    multi = MultiGpuStereoFrontend(params, c["w"], c["h"], [0, 1], 4, 2)
+    out = multi.alloc_outputs(n)
+    multi.process(L, R, out, c["mbf"], c["maxD"])
+    for k in ("kL", "dL", "nL", "kR", "dR", "nR", "uRight", "depth"):
+        assert out[k].tobytes() == ref[k].tobytes(), "%s differs between the 2-GPU and the 1-GPU run" % k
+    assert int(out["nL"].min()) > 1500
+    multi.close(), one.close()
