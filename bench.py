@@ -639,7 +639,8 @@ def main():
             line["configs"] = cfgs
             try:
                 lat = shim_latency()
-                line["c1_single_pair"] = {"latency_ms": lat["graph"], "latency_ms_no_graph": lat["plain"], "cpu_ref_ms": cpu_ms_c1,
+                line["c1_single_pair"] = {"latency_ms": lat["graph"], "latency_ms_no_graph": lat["plain"],
+                                          "latency_ms_pinned_caller_images": lat.get("graph_pinned_input"), "cpu_ref_ms": cpu_ms_c1,
                                           "ratio": cpu_ms_c1 / lat["graph"],
                                           "how": "C++ shim (shim/ORBextractor.cc) driven like Frame::Frame: two std::threads + ComputeStereoMatches, 200 frames; "
                                                  "cpu_ref_ms = the reference's own code with its own threading on the same pair"}

@@ -166,14 +166,15 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
         return ((X | Y) & 0x80008000u) != 0u;
       };
       uint16_t* lp = wlist + lane;
-      for (int y = warp; y < nSR; y += FC_WARPS) {
-        const uint2* ctr = reinterpret_cast<const uint2*>(sp + (y + 3) * SP + wE) + lane;
-        const uint2* cp3 = reinterpret_cast<const uint2*>(sp + (y + 6) * SP + wE) + lane;
-        const uint2* cm3 = reinterpret_cast<const uint2*>(sp + y * SP + wE) + lane;
-        unsigned e = (unsigned)(y << sh) + 2u * lane;              // (score row, slot); fits 16 bits: the host bounds the band height
-        for (int st = 0; st < nSteps; ++st, ctr += 32, cp3 += 32, cm3 += 32, e += 64) {
+      const int up3 = 3 * (SP >> 1);                // three rows in 64-bit words (SP is even)
+      const uint2* row = reinterpret_cast<const uint2*>(sp + (warp + 3) * SP + wE) + lane;
+      unsigned e0 = (unsigned)(warp << sh) + 2u * lane;            // (score row, slot); fits 16 bits: the host bounds the band height
+      for (int y = warp; y < nSR; y += FC_WARPS, row += FC_WARPS * (SP >> 1), e0 += (unsigned)FC_WARPS << sh) {
+        const uint2* ctr = row;
+        unsigned e = e0;
+        for (int st = 0; st < nSteps; ++st, ctr += 32, e += 64) {
           const uint2 ca = ctr[-1], cb = ctr[0], cc = ctr[1];        // words W-2 .. W+3 of the centre row
-          const uint2 t3 = cp3[0], b3 = cm3[0];
+          const uint2 t3 = ctr[up3], b3 = ctr[-up3];
           if (reject_test(cb.x, t3.x, b3.x, __byte_perm(cb.y, cc.x, 0x5432), __byte_perm(ca.x, ca.y, 0x5432))) { *lp = (uint16_t)e; lp += 32; }
           if (reject_test(cb.y, t3.y, b3.y, __byte_perm(cc.x, cc.y, 0x5432), __byte_perm(ca.y, cb.x, 0x5432))) { *lp = (uint16_t)(e + 1); lp += 32; }
         }

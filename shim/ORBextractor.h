@@ -63,6 +63,11 @@ class ORBextractor {
   // The underlying C-ABI handle (used by the GPU Frame::ComputeStereoMatches replacement).
   ivg_extractor* handle() const { return mHandle; }
 
+  // CUDA device used by extractors constructed AFTER the call (the reference's constructor has no such argument, so it is
+  // process-wide state; default: environment variable IVSLAM_DEVICE, else device 0).
+  static void SetDevice(int device);
+  static int GetDevice();
+
  protected:
   int nfeatures;
   double scaleFactor;

@@ -1,21 +1,22 @@
 """Copies a tools/record_run.sh result set (gpurun_out/<tag>_*) into profiles/ and prints the numbers profiles/README.md quotes
-(developer tool; runs where ncu is installed, no GPU needed):  python tools/publish_record.py <tag>"""
+(developer tool; runs where ncu is installed, no GPU needed):  python tools/publish_record.py <tag> [prefix]"""
 import csv, io, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r2"      # file prefix under profiles/
 g = lambda n: os.path.join(ROOT, "gpurun_out", "%s_%s" % (tag, n))
 p = lambda n: os.path.join(ROOT, "profiles", n)
-subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), g("full.ncu-rep"), "64", p("r1_ncu_summary.csv"), "/tmp/dram.json"], stdout=subprocess.DEVNULL)
+subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), g("full.ncu-rep"), "64", p(rnd + "_ncu_summary.csv"), "/tmp/dram.json"], stdout=subprocess.DEVNULL)
 d = json.load(open("/tmp/dram.json"))
 d["k_stereo_match"] += d.pop("k_stereo_index", 0)
 out = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per image (per pair for k_stereo_match incl. k_stereo_index; all 7 levels for k_resize_level) from one ncu --set full capture at 64 images per launch (tools/record_run.sh, tools/ncu_summary.py)"}
 out.update(d)
 json.dump(out, open(p("ncu_dram_bytes_per_image.json"), "w"), indent=1)
-shutil.copy(g("bench.json"), p("r1_bench_n1.json"))
-shutil.copy(g("bench_ref.json"), p("r1_bench_reference_arm.json"))
-shutil.copy(g("launches.csv"), p("r1_ncu_launches.csv"))
-open(p("r1_kernel_times.txt"), "w").write(open(g("kernel_times.txt")).read() + open(g("latency.txt")).read().splitlines()[-1] + "\n")
-open(p("r1_n2_n4_measurements.txt"), "w").write(open(g("n2.txt")).read() + open(g("n4.txt")).read())
+shutil.copy(g("bench.json"), p(rnd + "_bench_n1.json"))
+shutil.copy(g("bench_ref.json"), p(rnd + "_bench_reference_arm.json"))
+shutil.copy(g("launches.csv"), p(rnd + "_ncu_launches.csv"))
+open(p(rnd + "_kernel_times.txt"), "w").write(open(g("kernel_times.txt")).read() + open(g("latency.txt")).read())
+open(p(rnd + "_n2_n4_measurements.txt"), "w").write(open(g("n2.txt")).read() + open(g("n4.txt")).read())
 b = json.load(open(g("bench.json")))
 r = json.load(open(g("bench_ref.json")))
 print("value %.0f  ms/step %.2f  e2e %.0f  launches %d" % (b["value"], b["ms_per_step"], b["e2e"]["value"], b["gpu_launches"]))
