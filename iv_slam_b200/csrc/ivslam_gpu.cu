@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -38,6 +39,7 @@ namespace {
 #ifndef IVG_FAST_SMEM_KB
 #define IVG_FAST_SMEM_KB 31
 #endif
+constexpr int EAGER_INDEX_MAX_BATCH = 8;     // batches up to this size are treated as the one-frame-at-a-time (latency) use
 constexpr size_t FAST_SMEM_BUDGET = IVG_FAST_SMEM_KB * 1024;   // k_fast_cells stages at most this much per CTA (taller cells are banded)
 
 thread_local std::string g_cuda_err;
@@ -76,8 +78,25 @@ struct DevBuf {
 
 }  // namespace
 
+// One-frame-at-a-time stereo (the drop-in use: two extractor threads, then ComputeStereoMatches): once two handles have been
+// matched, they are linked; from then on the handle whose run is enqueued SECOND enqueues the matcher right behind it with
+// the remembered calibration, and its results land in pinned staging while the host is still joining its threads.
+// ivg_stereo_match then only has to wait and copy (if the generations and the calibration still agree — otherwise the
+// speculative result is dropped and the call runs as usual).
+struct StereoLink {
+  std::mutex mu;
+  ivg_extractor* left = nullptr; ivg_extractor* right = nullptr;
+  float mbf = 0.f, maxD = 0.f;
+  unsigned long long genL = 0, genR = 0;          // generation of each side's last enqueued run
+  unsigned long long specGenL = 0, specGenR = 0;  // generations the last (speculative or explicit) matcher launch consumed
+  bool specValid = false; int specN = 0;
+};
+
 struct ivg_extractor {
   int device = 0;
+  std::shared_ptr<StereoLink> link;     // set by the first single-frame ivg_stereo_match of this handle with a partner
+  unsigned long long runGen = 0;        // bumped by every upload and run: identifies what the device buffers currently hold
+  void* specHost = nullptr; size_t specHostBytes = 0;   // pinned staging of the speculative matcher's uRight / depth (left handle)
   int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
   double scaleFactor = 1.2;
   bool enableIntrospection = false;
@@ -98,6 +117,8 @@ struct ivg_extractor {
   cudaEvent_t evD2H = nullptr;          // copyOut: results of the last run have been read (next run may overwrite them)
   cudaEvent_t evStereo = nullptr;       // stream (left handle): matcher finished reading both handles
   cudaEvent_t evD2Hs = nullptr;         // copyOut (left handle): uRight/depth have been read
+  bool eagerIndex = false;              // this handle is the right eye of single-frame stereo calls: build the matcher's row index as the tail of its own run
+  bool indexValid = false;              // sortedR / rowStart of THIS handle describe its current keypoints
   cudaStream_t aux = nullptr;           // side stream for the blur of small batches (forked from / joined into `stream`)
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t evConsumed = nullptr;     // recorded (on the matcher's stream) when another handle's kernels have read our buffers
@@ -141,6 +162,7 @@ struct ivg_extractor {
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
   DevBuf<float> extU, extD; DevBuf<int> extS;        // results of ivg_stereo_match_keypoints (kept across calls)
   bool graphMode = false;
+  bool graphEager = false;
   cudaGraphExec_t graphExec = nullptr;   // captured kernel sequence of one run (re-captured when batch / mode / buffers change)
   int graphBatch = 0, graphLaunches = 0;
   bool graphWeighted = false;
@@ -581,15 +603,30 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
     else
       k_orient_describe<DK_SLOTS_BATCH><<<dim3((fs.kpCap + DK_SLOTS_BATCH - 1) / DK_SLOTS_BATCH, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN);
   }
+  if (h->eagerIndex && fs.nImages <= EAGER_INDEX_MAX_BATCH) {
+    // Right eye of one-frame-at-a-time stereo: the matcher's (octave, row) index only depends on this handle's keypoints,
+    // so it is built here, off the critical path of ivg_stereo_match (it overlaps this eye's download and the host's join).
+    StereoArgs A{};
+    A.kpR = h->outKp.p; A.nR = h->outN.p; A.cap = fs.kpCap; A.nRows = fs.lv[0].h; A.nLevels = fs.nlevels;
+    A.sorted = h->sortedR.p; A.rowStart = h->rowStart.p;
+    ProfScope ps(h, IVG_K_STEREO);
+    k_stereo_index<<<fs.nImages, 256, ((size_t)A.nRows * A.nLevels + 1) * sizeof(int), h->stream>>>(A);
+  }
   CK(cudaGetLastError());
   return IVG_OK;
 }
 
 int launch_extract(ivg_extractor* h) {
   const FrameSet fs = active_fs(h);
+  if (h->eagerIndex && fs.nImages <= EAGER_INDEX_MAX_BATCH) {      // buffers first: no allocation inside a stream capture
+    const size_t nBins = (size_t)fs.lv[0].h * fs.nlevels;
+    int rc;
+    if ((nBins + 1) * sizeof(int) > 200 * 1024) h->eagerIndex = false;
+    else if ((rc = h->sortedR.alloc((size_t)fs.nImages * fs.kpCap)) || (rc = h->rowStart.alloc((size_t)fs.nImages * (nBins + 1)))) return rc;
+  }
   if (h->graphMode && !h->profile) {
     // one graph launch instead of ~11 kernel launches: matters for the one-frame-at-a-time (drop-in) use
-    if (!h->graphExec || h->graphBatch != fs.nImages || h->graphWeighted != (fs.weighted != 0)) {
+    if (!h->graphExec || h->graphBatch != fs.nImages || h->graphWeighted != (fs.weighted != 0) || h->graphEager != h->eagerIndex) {
       drop_graph(h);
       cudaGraph_t g = nullptr;
       const long long before = h->launches;
@@ -603,7 +640,7 @@ int launch_extract(ivg_extractor* h) {
       if (e != cudaSuccess) { g_cuda_err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); h->graphExec = nullptr; return IVG_ERR_CUDA; }
       h->graphLaunches = (int)(h->launches - before);
       h->launches = before;
-      h->graphBatch = fs.nImages; h->graphWeighted = fs.weighted != 0;
+      h->graphBatch = fs.nImages; h->graphWeighted = fs.weighted != 0; h->graphEager = h->eagerIndex;
     }
     CK(cudaGraphLaunch(h->graphExec, h->stream));
     h->launches += h->graphLaunches;
@@ -612,6 +649,7 @@ int launch_extract(ivg_extractor* h) {
     if (rc) return rc;
   }
   h->haveResults = true; h->havePyramid = true; h->haveGrid = false; h->haveStereo = false;
+  h->indexValid = h->eagerIndex && fs.nImages <= EAGER_INDEX_MAX_BATCH;
   return IVG_OK;
 }
 
@@ -712,6 +750,14 @@ int ivg_extractor_create(ivg_extractor** out, int device, int nfeatures, float s
 void ivg_extractor_destroy(ivg_extractor* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->link) {      // the partner keeps the (now dead) link; it is replaced at its next explicit match
+    std::lock_guard<std::mutex> lk(h->link->mu);
+    if (h->link->left == h) h->link->left = nullptr;
+    if (h->link->right == h) h->link->right = nullptr;
+    h->link->specValid = false;
+  }
+  h->link.reset();
+  if (h->specHost) { cudaFreeHost(h->specHost); h->specHost = nullptr; }
   // a shared kernel stream belongs to another handle (which may already be gone): the cudaFree calls below synchronise
   // the device anyway, so only streams this handle owns are touched
   if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
@@ -775,6 +821,7 @@ int ivg_set_batch(ivg_extractor* h, int n, int width, int height, int with_cost)
   int rc = ensure_shape(h, width, height, n);
   if (rc) return rc;
   h->curBatch = n;
+  h->runGen++;
   h->curWeighted = with_cost && h->enableIntrospection;   // src/ORBextractor.cc:1231
   h->haveCost = with_cost != 0;
   if (with_cost) {
@@ -1087,6 +1134,8 @@ int ivg_upload_batch_raw(ivg_extractor* h, int n, const uint8_t* frames, int src
   return IVG_OK;
 }
 
+static void maybe_speculate_stereo(ivg_extractor* h);
+
 int ivg_run_batch(ivg_extractor* h) {
   if (!h || !h->shapeReady || h->curBatch < 1) return IVG_ERR_STATE;
   CK(cudaSetDevice(h->device));
@@ -1096,6 +1145,8 @@ int ivg_run_batch(ivg_extractor* h) {
   CK(cudaStreamWaitEvent(h->stream, h->evD2Hs, 0));
   if ((rc = launch_extract(h))) return rc;
   CK(cudaEventRecord(h->evKernels, h->stream));
+  h->runGen++;
+  maybe_speculate_stereo(h);
   return IVG_OK;
 }
 
@@ -1167,7 +1218,8 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
   CK(cudaMemcpyAsync(stg + (size_t)n * k * 28, h->outDesc.p, (size_t)n * k * 32, cudaMemcpyDeviceToHost, h->copyOut));
   CK(cudaMemcpyAsync(cnt, h->outN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
   CK(cudaEventRecord(h->evD2H, h->copyOut));
-  if ((rc = ivg_sync(h))) return rc;
+  CK(cudaEventSynchronize(h->evD2H));      // results are on the host (=> the kernels and the upload before them are done); a
+                                           // speculative matcher that the other eye's thread may have queued behind is not waited for
   for (int f = 0; f < n; ++f) {
     const int m = std::min(std::max(cnt[f], 0), (int)k);
     n_out[f] = cnt[f];
@@ -1243,24 +1295,23 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
   A.nLevels = left->nlevels;
   const size_t nBins = (size_t)A.nRows * A.nLevels;
   if ((nBins + 1) * sizeof(int) > 200 * 1024) return IVG_ERR_CAPACITY;
-  if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (nBins + 1)))) return rc;
-  A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
-  { ProfScope ps(left, IVG_K_STEREO); k_stereo_index<<<nPairs, 256, (nBins + 1) * sizeof(int), left->stream>>>(A); }
+  if (right->indexValid && A.kpR == right->outKp.p && nPairs == right->curBatch && A.cap == right->fs.kpCap) {
+    A.sorted = right->sortedR.p; A.rowStart = right->rowStart.p;      // built by the right handle at the end of its own run
+  } else {
+    if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (nBins + 1)))) return rc;
+    A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
+    ProfScope ps(left, IVG_K_STEREO);
+    k_stereo_index<<<nPairs, 256, (nBins + 1) * sizeof(int), left->stream>>>(A);
+  }
   { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A); }
   { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());
   return IVG_OK;
 }
 
-int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD,
-                           float* uRight, float* depth, int cap, int sync) {
-  if (!left || !right || !left->haveResults || !right->haveResults) return IVG_ERR_STATE;
-  if (left->device != right->device || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels ||
-      left->curBatch != right->curBatch || left->fs.planeBytes != right->fs.planeBytes || left->fs.kpCap != right->fs.kpCap)
-    return IVG_ERR_STATE;
-  if (cap < left->fs.kpCap) return IVG_ERR_CAPACITY;
-  CK(cudaSetDevice(left->device));
-  const int n = left->curBatch;
+// matcher kernels of the current results of (left, right) on left's stream, ordered after right's work; leaves copyOut
+// of the left handle waiting for them
+static int stereo_enqueue(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD, int n) {
   CK(cudaEventRecord(right->evDone, right->stream));
   CK(cudaStreamWaitEvent(left->stream, right->evDone, 0));
   CK(cudaStreamWaitEvent(left->stream, left->evD2Hs, 0));        // previous uRight/depth have been read
@@ -1273,12 +1324,86 @@ int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf,
   int rc = stereo_launch(left, right, A, n);
   if (rc) return rc;
   left->haveStereo = true;
-  const size_t k = A.cap;
+  if (n <= EAGER_INDEX_MAX_BATCH) right->eagerIndex = true;      // from its next run on, the right handle builds the index itself
   // the right handle must not overwrite its pyramids/keypoints before the matcher has read them
   CK(cudaEventRecord(left->evStereo, left->stream));
   CK(cudaEventRecord(right->evConsumed, left->stream));          // the right handle's own event: survives the left handle
   right->waitFor = right->evConsumed;
   CK(cudaStreamWaitEvent(left->copyOut, left->evStereo, 0));
+  return IVG_OK;
+}
+
+static bool stereo_compatible(const ivg_extractor* left, const ivg_extractor* right) {
+  return left->haveResults && right->haveResults && left->device == right->device && left->W == right->W && left->H == right->H &&
+         left->nlevels == right->nlevels && left->curBatch == right->curBatch && left->fs.planeBytes == right->fs.planeBytes &&
+         left->fs.kpCap == right->fs.kpCap;
+}
+
+// called at the end of every run: the second of two linked handles to get here launches the matcher speculatively
+static void maybe_speculate_stereo(ivg_extractor* h) {
+  std::shared_ptr<StereoLink> link = h->link;
+  if (!link || h->profile || h->curBatch > EAGER_INDEX_MAX_BATCH) return;
+  std::lock_guard<std::mutex> lk(link->mu);
+  ivg_extractor *L = link->left, *R = link->right;
+  if (!L || !R || (h != L && h != R)) return;
+  (h == L ? link->genL : link->genR) = h->runGen;
+  if (!(link->genL > link->specGenL && link->genR > link->specGenR)) return;      // one side has no new run yet
+  if (link->genL != L->runGen || link->genR != R->runGen || L->profile || R->profile || !stereo_compatible(L, R)) return;
+  const int n = L->curBatch;
+  const size_t k = L->fs.kpCap, bytes = 2 * (size_t)n * k * 4;
+  if (L->specHostBytes < bytes) {
+    if (L->specHost) { cudaFreeHost(L->specHost); L->specHost = nullptr; L->specHostBytes = 0; }
+    if (cudaHostAlloc(&L->specHost, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return; }
+    L->specHostBytes = bytes;
+  }
+  link->specValid = false;
+  if (stereo_enqueue(L, R, link->mbf, link->maxD, n) != IVG_OK) return;
+  float* stg = (float*)L->specHost;
+  if (cudaMemcpyAsync(stg, L->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) != cudaSuccess ||
+      cudaMemcpyAsync(stg + (size_t)n * k, L->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) != cudaSuccess ||
+      cudaEventRecord(L->evD2Hs, L->copyOut) != cudaSuccess) { cudaGetLastError(); return; }
+  link->specGenL = link->genL; link->specGenR = link->genR; link->specN = n; link->specValid = true;
+}
+
+int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD,
+                           float* uRight, float* depth, int cap, int sync) {
+  if (!left || !right || !left->haveResults || !right->haveResults) return IVG_ERR_STATE;
+  if (!stereo_compatible(left, right)) return IVG_ERR_STATE;
+  if (cap < left->fs.kpCap) return IVG_ERR_CAPACITY;
+  CK(cudaSetDevice(left->device));
+  const int n = left->curBatch;
+  const size_t k = left->fs.kpCap;
+  int rc;
+  const bool small = n <= EAGER_INDEX_MAX_BATCH && sync && uRight && depth;
+  if (small && left->link && left->link == right->link) {
+    // the matcher may already be running (or done): launched by whichever extractor thread finished second
+    StereoLink& K = *left->link;
+    std::lock_guard<std::mutex> lk(K.mu);
+    if (K.specValid && K.left == left && K.right == right && K.specGenL == left->runGen && K.specGenR == right->runGen &&
+        K.mbf == mbf && K.maxD == maxD && K.specN == n) {
+      CK(cudaEventSynchronize(left->evD2Hs));
+      const float* stg = (const float*)left->specHost;
+      for (int f = 0; f < n; ++f) {
+        std::memcpy(uRight + (size_t)f * cap, stg + (size_t)f * k, k * 4);
+        std::memcpy(depth + (size_t)f * cap, stg + (size_t)n * k + (size_t)f * k, k * 4);
+      }
+      return IVG_OK;
+    }
+    K.specValid = false;
+  }
+  if ((rc = stereo_enqueue(left, right, mbf, maxD, n))) return rc;
+  if (small) {
+    // remember the pairing and the calibration: the next frame's matcher is launched by the extractor threads themselves
+    std::shared_ptr<StereoLink> link = left->link;
+    if (!link || link != right->link || link->left != left || link->right != right) {
+      link = std::make_shared<StereoLink>();
+      link->left = left; link->right = right;
+      left->link = link; right->link = link;
+    }
+    std::lock_guard<std::mutex> lk(link->mu);
+    link->mbf = mbf; link->maxD = maxD; link->specValid = false;
+    link->genL = link->specGenL = left->runGen; link->genR = link->specGenR = right->runGen;
+  }
   if (sync && uRight && depth && !is_pinned(uRight)) {           // pageable mvuRight / mvDepth: through the pinned staging (see ivg_extract_batch)
     if ((rc = ensure_out_host(left, 2 * (size_t)n * k * 4))) return rc;
     float* stg = (float*)left->outHost;

@@ -343,13 +343,32 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
   }
 }
 
+// first bin b with hist[0] + ... + hist[b] > k, and k minus the counts before it; executed by one warp (8 bins per lane)
+__device__ __forceinline__ void median_pick_bin(const int* hist, int k, int lane, int& bin, int& rest) {
+  int c[8], local = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i] = hist[8 * lane + i]; local += c[i]; }
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int owner = __ffs(__ballot_sync(0xffffffffu, incl > k)) - 1;      // callers guarantee k < total
+  int b = 0, r = k - (incl - local);
+  if (lane == owner) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (b == i && r >= c[i]) { r -= c[i]; ++b; }
+    b += 8 * lane;
+  }
+  bin = __shfl_sync(0xffffffffu, b, owner);
+  rest = __shfl_sync(0xffffffffu, r, owner);
+}
+
 __global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {
   __shared__ int hist[256];
   __shared__ int sel[3];   // [0] chosen high byte, [1] rank inside it, [2] median value
   const size_t pair = blockIdx.x;
   const int N = A.nL[pair];
   const int* sad = A.sad + pair * A.cap;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   hist[tid] = 0;
   __syncthreads();
   int cnt = 0;
@@ -357,16 +376,17 @@ __global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {
     const int s = sad[i];
     if (s >= 0) { atomicAdd(&hist[(s >> 8) & 0xFF], 1); ++cnt; }
   }
+  (void)cnt;
   __syncthreads();
-  if (tid == 0) {
-    int total = 0;
-    for (int b = 0; b < 256; ++b) total += hist[b];
-    sel[0] = -1;
-    if (total > 0) {
-      int k = total / 2, b = 0;                       // vDistIdx[size/2] of the ascending sort
-      while (k >= hist[b]) { k -= hist[b]; ++b; }
-      sel[0] = b; sel[1] = k;
-    }
+  if (tid < 32) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += hist[8 * lane + i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    int b = -1, k = 0;
+    if (t > 0) median_pick_bin(hist, t / 2, lane, b, k);    // vDistIdx[size/2] of the ascending sort
+    if (lane == 0) { sel[0] = b; sel[1] = k; }
   }
   __syncthreads();
   const int hb = sel[0];
@@ -378,10 +398,10 @@ __global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {
     if (s >= 0 && ((s >> 8) & 0xFF) == hb) atomicAdd(&hist[s & 0xFF], 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    int k = sel[1], b = 0;
-    while (k >= hist[b]) { k -= hist[b]; ++b; }
-    sel[2] = (hb << 8) | b;
+  if (tid < 32) {
+    int b, k;
+    median_pick_bin(hist, sel[1], lane, b, k);
+    if (lane == 0) sel[2] = (hb << 8) | b;
   }
   __syncthreads();
   const float median = (float)sel[2];

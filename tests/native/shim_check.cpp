@@ -2,6 +2,8 @@
 // way Frame::Frame does in the reference (src/Frame.cc:115-125, :193): two extractor objects, operator() on each eye,
 // then ComputeStereoMatches.  Built and called by tests/test_shim.py.
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <thread>
@@ -74,6 +76,25 @@ extern "C" double shim_frame_latency_ms(const unsigned char* left, const unsigne
     const auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < iters; ++i) frame();
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+    if (std::getenv("IVSLAM_LATENCY_BREAKDOWN")) {      // developer: where the frame time goes on the host side
+      double tExt = 0, tSt = 0, tOne = 0;
+      for (int i = 0; i < iters; ++i) {
+        const auto a = std::chrono::steady_clock::now();
+        std::thread tl([&] { exL(imL, none, kL, dL); });
+        std::thread tr([&] { exR(imR, none, kR, dR); });
+        tl.join(); tr.join();
+        const auto b = std::chrono::steady_clock::now();
+        ORB_SLAM2::ComputeStereoMatchesGPU(&exL, &exR, (int)kL.size(), mbf, maxD, u, d);
+        const auto c = std::chrono::steady_clock::now();
+        exL(imL, none, kL, dL);                           // one eye alone on the calling thread: no thread spawn, no contention
+        const auto e = std::chrono::steady_clock::now();
+        tExt += std::chrono::duration<double, std::micro>(b - a).count();
+        tSt += std::chrono::duration<double, std::micro>(c - b).count();
+        tOne += std::chrono::duration<double, std::micro>(e - c).count();
+      }
+      std::fprintf(stderr, "breakdown (us): two extractor threads spawn..join %.1f, ComputeStereoMatches %.1f, one operator() inline %.1f\n",
+                   tExt / iters, tSt / iters, tOne / iters);
+    }
     for (void* p : pin) if (p) ivg_host_free(p);
     return ms;
   } catch (const std::exception&) {

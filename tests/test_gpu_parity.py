@@ -293,6 +293,49 @@ def test_two_handles_from_two_threads(gpu_api, oracle):
     assert_stereo_close(u[:r["kL"].size], d[:r["kL"].size], r["uRight"], r["depth"])
 
 
+def test_speculative_stereo_across_frames(gpu_api, oracle):
+    """One frame at a time on a fixed handle pair (the drop-in use).  After the first explicit ivg_stereo_match the library
+    launches the matcher itself, right behind whichever extractor run is enqueued second; ivg_stereo_match then only collects
+    the result.  Every frame must still equal the oracle, whatever the order the two eyes run in, and a changed calibration
+    or an extra run of one eye must drop the speculative result instead of returning it."""
+    import threading
+    c = S.CONFIGS["C1"]
+    gL, gR, oL, oR = _pair(gpu_api, oracle, 2000, 20, 7, False)
+    gL.set_graph_mode(True), gR.set_graph_mode(True)
+    mb, maxD = reference_mb(c["mbf"], c["maxD"])
+    frames = [S.make_stereo_pair(c["w"], c["h"], 700 + i) for i in range(6)]
+
+    def check(i, mbf, md, order):
+        left, right = frames[i]
+        out = {}
+        if order == "threads":
+            tl = threading.Thread(target=lambda: out.__setitem__("L", gL(left)))
+            tr = threading.Thread(target=lambda: out.__setitem__("R", gR(right)))
+            tl.start(), tr.start(), tl.join(), tr.join()
+        elif order == "LR":
+            out["L"], out["R"] = gL(left), gR(right)
+        else:
+            out["R"], out["L"] = gR(right), gL(left)
+        u, d = gpu_api.compute_stereo_matches(gL, gR, mbf, md)
+        r = oracle.stereo_frame(oL, oR, left, right, None, mbf, md, threads=2)
+        assert_keypoints_equal(out["L"][0], r["kL"], "frame %d" % i)
+        n = r["kL"].size
+        assert np.array_equal(u[:n], r["uRight"]) and np.array_equal(d[:n], r["depth"]), "frame %d (%s): stereo result" % (i, order)
+
+    check(0, c["mbf"], maxD, "threads")          # explicit launch, links the pair
+    check(1, c["mbf"], maxD, "threads")          # speculative from here on
+    check(2, c["mbf"], maxD, "LR")
+    check(3, c["mbf"], maxD, "RL")
+    check(4, c["mbf"], 0.5 * maxD, "threads")    # calibration changed: the speculative result must not be used
+    check(5, c["mbf"], 0.5 * maxD, "threads")
+    gL(frames[0][0])                              # the left eye alone runs again: the pair's speculative state is stale
+    gR(frames[1][1])
+    gL(frames[1][0])
+    u, d = gpu_api.compute_stereo_matches(gL, gR, c["mbf"], maxD)
+    r = oracle.stereo_frame(oL, oR, frames[1][0], frames[1][1], None, c["mbf"], maxD, threads=2)
+    assert np.array_equal(u[:r["kL"].size], r["uRight"])
+
+
 def test_graph_mode_is_bit_identical(gpu_api):
     """CUDA-graph replay of the kernel sequence (single-frame latency mode) must not change a byte, across shape changes."""
     a = S.make_image(1241, 376, 21)
