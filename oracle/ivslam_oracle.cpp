@@ -6,15 +6,15 @@
 // only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs do.
 //
-// PARITY PIN: the reference (ut-amrl/IV_SLAM) has no tests or golden vectors for this
-// path and its pixel arithmetic lives in an un-vendored OpenCV (any of 2.4.3/3.x/4.x,
-// introspective_ORB_SLAM/CMakeLists.txt:37-46).  The reference C++ cannot be compiled in
-// this image (no OpenCV/Eigen/glog headers).  The pin is therefore this image's
-// opencv-python-headless 4.13.0: tests/test_oracle_vs_cv2.py checks every primitive
-// below (resize, GaussianBlur, FAST, fastAtan2) and the composed pipeline
-// (oracle/cv2_pipeline.py, which calls the real cv2 primitives in the reference's
-// order) byte-for-byte against this file, and tests/golden/ holds vectors generated
-// from cv2 by tests/golden/make_golden.py.
+// PARITY PIN: this restatement is checked against the reference itself.  oracle/_ref compiles the UNMODIFIED
+// introspective_ORB_SLAM/src/ORBextractor.cc (whole file) and Frame::ComputeStereoMatches (src/Frame.cc:758-932, cut
+// out verbatim) over an OpenCV-compat layer (oracle/refbuild/); tests/test_ref_pin.py requires bit-for-bit equality of
+// everything this file produces with that build on the BASELINE configurations, fuzz geometries, cost-map extremes
+// and the stereo stress case.  The pixel arithmetic of the un-vendored OpenCV (resize, GaussianBlur, FAST,
+// fastAtan2 — the reference pins no OpenCV version, introspective_ORB_SLAM/CMakeLists.txt:37-46) is pinned to this
+// image's opencv-python-headless 4.13.0 by tests/test_oracle_vs_cv2.py, byte for byte, and those same functions are
+// what the compat layer of oracle/_ref forwards to.  tests/golden/ holds vectors generated from cv2 by
+// tests/golden/make_golden.py.
 //
 // All file:line citations are relative to /root/reference/introspective_ORB_SLAM/.
 // Build: see oracle/Makefile  (g++ -O3 -march=native -ffp-contract=off, the reference's

@@ -2,6 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package (iv_slam_b200/) never imports it.
+(The unmodified reference sources built over an OpenCV-compat layer are oracle/_ref, loaded by oracle/ref_lib.py;
+tests/test_ref_pin.py holds the two to bit-for-bit equality.)
 
 The library is compiled with -march=native, so it is rebuilt per host CPU: the .so lives in
 oracle/_build/<hash of the CPU flags>/ and is (re)built on first use on a new machine.
