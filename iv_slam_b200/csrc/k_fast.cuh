@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       // merge the lane lists into one dense list, in place: row k of the lane-strided layout (entry k of every lane) is
       // read by the whole warp before its survivors are written at [wn, wn + count) <= 32 k, so nothing unread is overwritten
       const int cnt = (int)(lp - (wlist + lane)) >> 5;
+      __syncwarp();                                                // the lanes' appends are ordered before the merge's stores
       const int maxc = __reduce_max_sync(0xffffffffu, cnt);
       for (int k = 0; k < maxc; ++k) {
         int v = 0;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
           v -= pOff;                                               // list entry = (score row << sh) | pair index
         }
         const unsigned m = __ballot_sync(0xffffffffu, has);
+        __syncwarp();                                              // every lane has read its entry of row k
         if (has) wlist[wn + __popc(m & ltmask)] = (uint16_t)v;
         wn += __popc(m);
         __syncwarp();

@@ -34,3 +34,13 @@ gL.set_rectify_maps(xx * 1.01 - 3, yy * 0.99 + 2)
 bgr = np.stack([L[0], L[0], L[0]], -1).copy()
 kk, dd = gL.extract_raw(bgr, False, cost[0])
 print("raw keypoints", kk.size)
+# one frame at a time on a linked pair (graph mode): fused pyramid, 16-slot describe, forked blur, CTA-wide level trim,
+# eager stereo index and the speculative matcher, from two host threads
+import threading
+sL, sR = api.ORBextractor(*a), api.ORBextractor(*a)
+sL.set_graph_mode(True); sR.set_graph_mode(True)
+for i in range(3):
+    tl = threading.Thread(target=lambda: sL(L[i % 2])); tr = threading.Thread(target=lambda: sR(R[i % 2]))
+    tl.start(); tr.start(); tl.join(); tr.join()
+    us, ds = api.compute_stereo_matches(sL, sR, 100.0, 400.0)
+print("single-frame stereo matches", int((us >= 0).sum()))
