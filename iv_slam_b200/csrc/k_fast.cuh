@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
 
     // ---- A: stage pixel rows gy0 .. gy0+nR-1; warp = row, lane = group of 4 pixels
     const int gy0 = c.y0 + s0 - 3;
-    {
+    if (pass == 0 || ch > BH) {      // the minTh retry of a single-band cell finds its pixels still staged
       // per-thread source/destination pointers are set up once and bumped per row; two column groups per pass
       const int nG4 = SP >> 1;
       const int rstep = FC_WARPS * pitch, dstep = FC_WARPS * SP;
