@@ -110,16 +110,26 @@ __device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uin
 // partition round handles all elements at once — stopper ranks from warp ballots plus a prefix over the warps' counts,
 // m from __syncthreads_count (the predicate F[i] < R[TR-1-i] is a prefix of trues), swaps in parallel.  Identical
 // permutation; every thread of the CTA must call it (n <= 65535, lists in shared memory).
+// BN_THREADS threads take part (the first BN_THREADS of the CTA; the rest must not call it): they meet on named barrier 1, so
+// the barriers cost what 8 warps cost, not what the whole CTA costs.
+constexpr int BN_THREADS = 256;
+__device__ __forceinline__ void bn_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BN_THREADS) : "memory"); }
+__device__ __forceinline__ int bn_sync_count(bool p) {
+  int r;
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %1, 0;\nbar.red.popc.u32 %0, 1, %2, q;\n}" : "=r"(r) : "r"((int)p), "n"(BN_THREADS) : "memory");
+  return r;
+}
+
 __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int* wcnt /*[2*32]*/) {
   if (n == 0 || nth == n) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = BN_THREADS, nw = nthr >> 5;
   int first = 0, last = n;
   int depth = 2 * (31 - __clz(n));
   const unsigned lt = (1u << lane) - 1u;
   while (last - first > 3) {
     if (depth == 0) {
       if (tid == 0) { sel_heap_select(a + first, nth + 1 - first, last - first); sel_swap(a, first, nth); }
-      __syncthreads();
+      bn_sync();
       return;
     }
     --depth;
@@ -133,7 +143,7 @@ __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, ui
       else if (sel_before(a[B], a[C])) sel_swap(a, first, C);
       else sel_swap(a, first, B);
     }
-    __syncthreads();
+    bn_sync();
     const uint32_t pkey = a[first].key;
     const int lo = first + 1, hi = last;
     int TL = 0, TR = 0;
@@ -144,7 +154,7 @@ __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, ui
       const bool isL = v && !(k > pkey), isR = v && !(pkey > k);
       const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
       if (lane == 0) { wcnt[warp] = __popc(mL); wcnt[32 + warp] = __popc(mR); }
-      __syncthreads();
+      bn_sync();
       // exclusive prefix of this warp's counts over the warps before it, and the totals: one lane per warp + a shuffle scan
       int sl = lane < nw ? wcnt[lane] : 0, sr = lane < nw ? wcnt[32 + lane] : 0;
 #pragma unroll
@@ -157,14 +167,14 @@ __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, ui
       if (isL) sF[TL + pL + __popc(mL & lt)] = (uint16_t)j;
       if (isR) sR[TR + pR + __popc(mR & lt)] = (uint16_t)j;
       TL += tL; TR += tR;
-      __syncthreads();
+      bn_sync();
     }
     int m = 0;
     const int lim = min(TL, TR);
     for (int base = 0; base < lim; base += nthr) {
       const int i = base + tid;
       const bool ok = i < lim && sF[i] < sR[TR - 1 - i];
-      const int c = __syncthreads_count(ok);
+      const int c = bn_sync_count(ok);
       m += c;
       if (c != nthr) break;                                 // CTA-uniform
     }
@@ -174,7 +184,7 @@ __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, ui
     }
     const int rprev = m > 0 ? (int)sR[TR - m] : hi;
     const int cut = (m < TL && (int)sF[m] < rprev) ? (int)sF[m] : rprev;
-    __syncthreads();
+    bn_sync();
     if (cut <= nth) first = cut; else last = cut;
   }
   if (tid == 0) {
@@ -190,7 +200,7 @@ __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, ui
       }
     }
   }
-  __syncthreads();
+  bn_sync();
 }
 
 // test hook: one warp runs warp_nth_element on n (key, index) items staged in shared memory
@@ -204,7 +214,8 @@ __global__ void k_debug_nth_element(const uint32_t* keys, int n, int nth, uint32
     __shared__ int wc[64];
     for (int i = lane; i < n; i += blockDim.x) a[i] = SelItem{keys[i], (uint32_t)i};
     __syncthreads();
-    block_nth_element(a, nth, n, sF, sR, wc);
+    if (lane < BN_THREADS) block_nth_element(a, nth, n, sF, sR, wc);
+    __syncthreads();
     for (int i = lane; i < n; i += blockDim.x) order[i] = a[i].val;
     return;
   }
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
   if (MAX_THREADS >= 512 && levelBuf == S.levelBuf && total > L.nDesired && L.nDesired > 0) {
     // latency configuration: the level's trim is the longest serial piece of the frame, all 32 warps take part
     __shared__ int sWcnt[64];
-    block_nth_element(levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, sWcnt);
+    if (tid < BN_THREADS) block_nth_element(levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, sWcnt);
     if (tid == 0) { sCount = L.nDesired; fs.levelCount[img * MAX_LEVELS + level] = L.nDesired; }
   } else if (warp == 0) {
     int count = total;
