@@ -8,8 +8,10 @@
 //               byte is read from L2/HBM once per tile).  Scale factors whose source box would exceed the 256-element
 //               TMA box limit use a plain 32-bit load loop instead;
 //   horizontal  T[sy][d] = src[sy][sx0]*cx0 + src[sy][sx1]*cx1 for every staged source row, kept as (T >> 4) in 16 bits
-//               (the only form the vertical pass uses) — each source row is filtered once, not once per output row;
-//   vertical    dst = (((cy0*T0) >> 16) + ((cy1*T1) >> 16) + 2) >> 2, 4 pixels per thread, one aligned 32-bit store.
+//               (the only form the vertical pass uses) — each source row is filtered once, not once per output row; two
+//               adjacent columns per thread from one 4-byte window, one IDP.2A each;
+//   vertical    dst = (((cy0*T0) >> 16) + ((cy1*T1) >> 16) + 2) >> 2 with (c*T) >> 16 as the high word of c * (T << 16)
+//               (IMAD.HI), 4 pixels per thread, one aligned 32-bit store.
 // HBM-bound stencil (read level l-1, write level l); the cascade is strictly sequential across levels.
 #pragma once
 #include "common.cuh"
@@ -88,14 +90,34 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, co
     __syncthreads();
   }
   {
-    // thread owns one output column (two threads per column, interleaved rows)
-    const int d = tid & (RZ_W - 1), half = tid >> 7;
-    if (x0 + d <= x1) {
-      const ResizeTap t = tx[x0 + d];
-      const int a0 = t.s0 - sxa, a1 = t.s1 - sxa;
-      for (int r = half; r < nR; r += 2) {
-        const uint8_t* p = spx + r * SPB;
-        sT[r * RZ_W + d] = (uint16_t)((p[a0] * t.c0 + p[a1] * t.c1) >> 4);
+    // Horizontal pass: a thread owns TWO adjacent output columns (64 column pairs x 4 row phases).  With a scale above 1 their
+    // four source pixels lie inside the four bytes that start at the first column's left tap, so a row costs two aligned word
+    // loads, one funnel shift to that window, one more shift to the second column's taps and two IDP.2A (16-bit coefficients
+    // x 8-bit pixels); the two 16-bit results (T >> 4) are stored as one word.
+    const int pd = tid & 63, ph = tid >> 6;
+    const int xA = min(x0 + 2 * pd, D.w - 1), xB = min(x0 + 2 * pd + 1, D.w - 1);        // columns past the width only feed row padding
+    const ResizeTap tA = tx[xA], tB = tx[xB];
+    const unsigned cA = (unsigned)(uint16_t)tA.c0 | ((unsigned)(uint16_t)tA.c1 << 16);
+    const unsigned cB = (unsigned)(uint16_t)tB.c0 | ((unsigned)(uint16_t)tB.c1 << 16);
+    const int a0 = tA.s0 - sxa;                                   // byte offset of the window in a staged row
+    const int dB = (int)tB.s0 - (int)tA.s0;                        // 1 or 2 for scales up to 2 (0: both columns clamped at the right edge)
+    const int shA = 8 * (a0 & 3), shB = 8 * min(max(dB, 0), 2);    // the right tap of a clamped column has weight 0
+    if (x0 + 2 * pd <= x1) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(spx + ph * SPB) + (a0 >> 2);
+      uint32_t* o = reinterpret_cast<uint32_t*>(sT) + ph * (RZ_W / 2) + pd;
+      if (dB <= 2) {
+        for (int r = ph; r < nR; r += 4, p += SPB, o += 2 * RZ_W) {      // SPB words = 4 rows of SPB bytes
+          const unsigned w = __funnelshift_r(p[0], p[1], shA);
+          const unsigned TA = __dp2a_lo(cA, w, 0u), TB = __dp2a_lo(cB, w >> shB, 0u);
+          *o = (TA >> 4) | ((TB >> 4) << 16);
+        }
+      } else {      // scale factors above 2: the second column has its own window
+        const int b0 = tB.s0 - sxa, wB = (b0 >> 2) - (a0 >> 2), shB2 = 8 * (b0 & 3);
+        for (int r = ph; r < nR; r += 4, p += SPB, o += 2 * RZ_W) {
+          const unsigned TA = __dp2a_lo(cA, __funnelshift_r(p[0], p[1], shA), 0u);
+          const unsigned TB = __dp2a_lo(cB, __funnelshift_r(p[wB], p[wB + 1], shB2), 0u);
+          *o = (TA >> 4) | ((TB >> 4) << 16);
+        }
       }
     }
   }
@@ -111,12 +133,13 @@ __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, co
         const int4 t = sTapY[seg * RZ_RPS + rr];
         const uint2 A = *reinterpret_cast<const uint2*>(sT + t.x + 4 * g);
         const uint2 B = *reinterpret_cast<const uint2*>(sT + t.y + 4 * g);
-        const int b0 = t.z, b1 = t.w;
-        const int v0 = (((b0 * (int)(A.x & 0xFFFF)) >> 16) + ((b1 * (int)(B.x & 0xFFFF)) >> 16) + 2) >> 2;
-        const int v1 = (((b0 * (int)(A.x >> 16)) >> 16) + ((b1 * (int)(B.x >> 16)) >> 16) + 2) >> 2;
-        const int v2 = (((b0 * (int)(A.y & 0xFFFF)) >> 16) + ((b1 * (int)(B.y & 0xFFFF)) >> 16) + 2) >> 2;
-        const int v3 = (((b0 * (int)(A.y >> 16)) >> 16) + ((b1 * (int)(B.y >> 16)) >> 16) + 2) >> 2;
-        *reinterpret_cast<uint32_t*>(dst + (size_t)y * D.pitch + gx) = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+        const unsigned b0 = (unsigned)t.z, b1 = (unsigned)t.w;
+        // (b * T) >> 16 as the high word of b * (T << 16): one multiply per tap, no shift
+        const unsigned v0 = (__umulhi(b0, A.x << 16) + __umulhi(b1, B.x << 16) + 2u) >> 2;
+        const unsigned v1 = (__umulhi(b0, A.x & 0xFFFF0000u) + __umulhi(b1, B.x & 0xFFFF0000u) + 2u) >> 2;
+        const unsigned v2 = (__umulhi(b0, A.y << 16) + __umulhi(b1, B.y << 16) + 2u) >> 2;
+        const unsigned v3 = (__umulhi(b0, A.y & 0xFFFF0000u) + __umulhi(b1, B.y & 0xFFFF0000u) + 2u) >> 2;
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * D.pitch + gx) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
       }
     }
   }
