@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
   __shared__ float2 spat[512];
   __shared__ uint32_t sOnes[33 * 8];        // in-circle byte masks of the 31 patch rows (+2 empty rows), 8 words of 4 columns each
   __shared__ int sCx[DK_SLOTS], sCy[DK_SLOTS], sLevel[DK_SLOTS], sOut[DK_SLOTS];
-  __shared__ float sM01[DK_SLOTS], sM10[DK_SLOTS], sAngle[DK_SLOTS], sA[DK_SLOTS], sB[DK_SLOTS], sResp[DK_SLOTS];
+  __shared__ float sM01[DK_SLOTS], sM10[DK_SLOTS], sA[DK_SLOTS], sB[DK_SLOTS], sResp[DK_SLOTS];
+  __shared__ float sRec[DK_SLOTS][7];       // the keypoint's cv::KeyPoint record, assembled by the lane that computes its angle
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t img = blockIdx.y;
@@ -172,7 +173,17 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     const float rad = __fmul_rn(angle, factorPI);
     double sn, cs;
     sincos((double)rad, &sn, &cs);
-    sAngle[tid] = angle; sA[tid] = (float)cs; sB[tid] = (float)sn;
+    sA[tid] = (float)cs; sB[tid] = (float)sn;
+    // the 28-byte output record (src/ORBextractor.cc:1286-1291: pt *= scale for levels > 0, size, angle, response, octave, class_id)
+    const int level = sLevel[tid];
+    const LevelDev& L = fs.lv[level];
+    sRec[tid][0] = level ? __fmul_rn((float)sCx[tid], L.scale) : (float)sCx[tid];
+    sRec[tid][1] = level ? __fmul_rn((float)sCy[tid], L.scale) : (float)sCy[tid];
+    sRec[tid][2] = L.sizeField;
+    sRec[tid][3] = angle;
+    sRec[tid][4] = sResp[tid];
+    sRec[tid][5] = __int_as_float(level);
+    sRec[tid][6] = __int_as_float(-1);
   }
   __syncthreads();
 
@@ -186,7 +197,6 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
       if (q + 2 < DK_SLOTS / 8) issue_patch(q + 2);
       continue;
     }
-    const LevelDev& L = fs.lv[level];
     const int cx = sCx[j], cy = sCy[j];
     mbar_wait(&bars[warp][q & 1], (useCount[q & 1]++) & 1);   // parity = loads already consumed from this buffer
     const int cOff = cx - DK_PR - ((cx - DK_PR) & ~15);
@@ -208,17 +218,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     if (q + 2 < DK_SLOTS / 8) issue_patch(q + 2);
     const int outIdx = sOut[j];
     fs.outDesc[(img * fs.kpCap + outIdx) * 32 + lane] = (uint8_t)val;
-    if (lane < 7) {
-      float f;
-      if (lane == 0) f = level ? __fmul_rn((float)cx, L.scale) : (float)cx;
-      else if (lane == 1) f = level ? __fmul_rn((float)cy, L.scale) : (float)cy;
-      else if (lane == 2) f = L.sizeField;
-      else if (lane == 3) f = sAngle[j];
-      else if (lane == 4) f = sResp[j];
-      else if (lane == 5) f = __int_as_float(level);
-      else f = __int_as_float(-1);
-      reinterpret_cast<float*>(fs.outKp + (img * fs.kpCap + outIdx) * 28)[lane] = f;
-    }
+    if (lane < 7) reinterpret_cast<float*>(fs.outKp + (img * fs.kpCap + outIdx) * 28)[lane] = sRec[j][lane];
   }
 }
 
