@@ -32,6 +32,7 @@ struct LevelDev {
   int kpOff;              // offset of this level inside levelKp (prefix sum of kpCapLevel)
   int kpCapLevel;         // keypoints this level can emit: nDesired (live path) or nDesired + 3 (OctTree mode)
   int fSP, fSS, fBH, fBW, fSeg, fShift; // k_fast_cells: staged words per row, score bytes per row, rows per band, bitmap words per row, list entries per warp
+  int fBX;                // 2 when the level's cells are processed in several bands (one overlap score row per side), else 0
   int btBase, btX, btY;   // blur tile numbering
   int rzPitch, rzRows;    // k_resize_level: staged source bytes per row / rows of one output tile (this level as destination)
   int rtabX, rtabY;       // offsets into the resize tap tables (level >= 1)

@@ -324,16 +324,17 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     {
       const int slots = (((L.cellW + 2) / 2 + 1 + 63) / 64) * 64;                         // pair slots a warp walks per row (64 per step)
       auto bytes = [&](int bh, int* seg) {
-        const size_t ssBytes = align_up((size_t)L.fSS * (bh + 4), 16), bitBytes = align_up((size_t)4 * L.fBW * (bh + 2), 16);
-        *seg = ((bh + 2 + FC_WARPS - 1) / FC_WARPS) * slots;                              // per-warp pair list: its rows, every slot
-        return align_up((size_t)4 * L.fSP * (bh + 8), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * FC_WARPS * *seg;
+        const int bx = bh < L.cellH ? 2 : 0;                                              // banded cells carry one overlap score row per side
+        const size_t ssBytes = align_up((size_t)L.fSS * (bh + 2 + bx), 16), bitBytes = align_up((size_t)4 * L.fBW * (bh + 2), 16);
+        *seg = ((bh + bx + FC_WARPS - 1) / FC_WARPS) * slots;                             // per-warp pair list: its rows, every slot
+        return align_up((size_t)4 * L.fSP * (bh + 6 + bx), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * FC_WARPS * *seg;
       };
       L.fShift = 1;
       while ((1 << L.fShift) < slots) ++L.fShift;                                         // list entry = (score row << fShift) | pair slot, 16 bits
       if ((65536 >> L.fShift) < 8) return IVG_ERR_CAPACITY;                               // cells wider than ~16k px
       int bh = std::min(L.cellH, (65536 >> L.fShift) - 2);
       while (bh > 4 && bytes(bh, &L.fSeg) > FAST_SMEM_BUDGET) --bh;                       // taller cells are processed in bands
-      L.fBH = bh;
+      L.fBH = bh; L.fBX = bh < L.cellH ? 2 : 0;
       fastSmem = std::max(fastSmem, bytes(bh, &L.fSeg));
     }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)

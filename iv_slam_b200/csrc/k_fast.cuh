@@ -68,7 +68,7 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
 #endif
 constexpr int FC_THREADS = IVG_FC_THREADS; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
 constexpr int FC_WARPS = FC_THREADS / 32;
-constexpr int FC_SLACK = 512;   // bytes after the staged pixels that B's masked lanes may read
+constexpr int FC_SLACK = 272;   // bytes after the staged pixels that B's masked lanes may read (at most 65 words past the last row)
 
 __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char fsm[];
@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   const int piMask = (1 << sh) - 1;
   // shared layout: packed pixel pairs (+ slack for the masked overreads of B) | score bytes | survivor bitmap | pair list
   uint32_t* sp = reinterpret_cast<uint32_t*>(fsm);
-  const int ssBytes = (SS * (BH + 4) + 15) & ~15, bitBytes = (4 * BW * (BH + 2) + 15) & ~15;
-  uint8_t* ss = fsm + (((size_t)4 * SP * (BH + 8) + 15) & ~(size_t)15) + FC_SLACK;
+  // a single-band cell needs BH + 6 pixel rows and BH + 2 score rows; bands add one overlap score row per side (L.fBX = 2)
+  const int ssBytes = (SS * (BH + 2 + L.fBX) + 15) & ~15, bitBytes = (4 * BW * (BH + 2) + 15) & ~15;
+  uint8_t* ss = fsm + (((size_t)4 * SP * (BH + 6 + L.fBX) + 15) & ~(size_t)15) + FC_SLACK;
   uint32_t* sbit = reinterpret_cast<uint32_t*>(ss + ssBytes);
   uint16_t* slist = reinterpret_cast<uint16_t*>(ss + ssBytes + bitBytes);
   const int xa = (c.x0 - 3) & ~3;          // global x of staged column 0 (word aligned)
