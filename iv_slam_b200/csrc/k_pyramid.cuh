@@ -19,7 +19,10 @@
 
 namespace ivg {
 
-constexpr int RZ_W = 128, RZ_H = 64;
+#ifndef IVG_RZ_H
+#define IVG_RZ_H 64
+#endif
+constexpr int RZ_W = 128, RZ_H = IVG_RZ_H;
 constexpr int RZ_RPS = RZ_H / 8;           // output rows per 32-thread row segment
 
 // Level-0 ingest: frames arrive from the host as ONE contiguous copy (row-pitched DMA of 1241-byte rows runs at a third
