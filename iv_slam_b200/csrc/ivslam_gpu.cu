@@ -147,7 +147,7 @@ struct ivg_extractor {
   bool resizeTma[MAX_LEVELS] = {false};
   TmaMaps descMapsN{};                  // the same with 48 x 37 boxes
   DevBuf<PyrSpan> pyrSpanX, pyrSpanY;   // k_pyramid_fused window tables (level-major)
-  int pyrTX = 0, pyrTY = 0; size_t pyrFusedBuf = 0, pyrFusedSmem = 0; int pyrTapOffX[MAX_LEVELS] = {0}, pyrTapOffY[MAX_LEVELS] = {0};   // 0 tiles: the fused cascade is not available for this shape
+  int pyrTX = 0, pyrTY = 0; size_t pyrFusedBuf = 0, pyrFusedTOff = 0, pyrFusedSmem = 0; int pyrTapOffX[MAX_LEVELS] = {0}, pyrTapOffY[MAX_LEVELS] = {0};   // 0 tiles: the fused cascade is not available for this shape
   TmaMaps descMaps{};                   // per level: 64 x 37 x 1 boxes over the blurred planes (k_orient_describe)
   DevBuf<CellDev> dCellsPlain, dCellsWeighted;
   DevBuf<ResizeTap> rtab;
@@ -424,9 +424,20 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
       h->pyrTapOffX[l] = (int)tapEntries; tapEntries += (size_t)mw;
       h->pyrTapOffY[l] = (int)tapEntries; tapEntries += (size_t)mh;
     }
+    size_t tWords = 0;                                    // horizontal-pass buffer: (column pairs) x (source rows a window's rows read)
+    for (int l = 1; l < nl; ++l) {
+      int mw = 0, mr = 0;
+      for (int t = 0; t < TX; ++t) mw = std::max(mw, spanX[(size_t)l * TX + t].e1 - spanX[(size_t)l * TX + t].e0);
+      for (int t = 0; t < TY; ++t) {
+        const PyrSpan& s = spanY[(size_t)l * TY + t];
+        if (s.e1 > s.e0) mr = std::max(mr, taps[fs.lv[l].rtabY + std::min(s.e1, fs.lv[l].h) - 1].s1 - taps[fs.lv[l].rtabY + s.e0].s0 + 1);
+      }
+      tWords = std::max(tWords, (size_t)(mw / 2) * mr);
+    }
     h->pyrTX = TX; h->pyrTY = TY; h->pyrFusedBuf = buf;
-    h->pyrFusedSmem = 2 * buf + tapEntries * sizeof(ResizeTap);
-    if (h->pyrFusedSmem > 160 * 1024 || nl < 2) { h->pyrTX = 0; h->pyrTY = 0; }
+    h->pyrFusedTOff = align_up(2 * buf + tapEntries * sizeof(ResizeTap), 16);
+    h->pyrFusedSmem = h->pyrFusedTOff + tWords * 4;
+    if (h->pyrFusedSmem > 160 * 1024 || nl < 2 || tWords == 0) { h->pyrTX = 0; h->pyrTY = 0; }
   }
   fs.planeBytes = align_up(planeOff, (size_t)fs.lv[0].pitch * 4);   // multiple of the level-0 pitch: batched 3-D copies
   while (fs.planeBytes % fs.lv[0].pitch) fs.planeBytes += 256;
@@ -557,7 +568,7 @@ int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
     // one frame at a time: the whole cascade in one launch (k_pyramid_fused.cuh) instead of nlevels-1 dependent ones
     ProfScope ps(h, IVG_K_RESIZE);
     PyrFusedArgs A{};
-    A.spanX = h->pyrSpanX.p; A.spanY = h->pyrSpanY.p; A.TX = h->pyrTX; A.TY = h->pyrTY; A.bufBytes = (int)h->pyrFusedBuf;
+    A.spanX = h->pyrSpanX.p; A.spanY = h->pyrSpanY.p; A.TX = h->pyrTX; A.TY = h->pyrTY; A.bufBytes = (int)h->pyrFusedBuf; A.tOff = (int)h->pyrFusedTOff;
     for (int l = 0; l < MAX_LEVELS; ++l) { A.tapOffX[l] = h->pyrTapOffX[l]; A.tapOffY[l] = h->pyrTapOffY[l]; }
     k_pyramid_fused<<<dim3(h->pyrTX * h->pyrTY, planes), PF_THREADS, h->pyrFusedSmem, h->stream>>>(fs, A);
     CK(cudaGetLastError());

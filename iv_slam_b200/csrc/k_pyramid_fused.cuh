@@ -10,8 +10,9 @@
 // produced by the same integer arithmetic from the same source pixels whoever computes it.  No inter-CTA dependency, no
 // grid barrier, 7 launches become one.
 //
-// Arithmetic = k_resize_level's (OpenCV's 8-bit fixed-point bilinear path) in its direct 4-tap form:
-//   T(sy) = src[sy][sx0]*cx0 + src[sy][sx1]*cx1;   dst = (((cy0*(T(sy0) >> 4)) >> 16) + ((cy1*(T(sy1) >> 4)) >> 16) + 2) >> 2
+// Arithmetic = k_resize_level's (OpenCV's 8-bit fixed-point bilinear path), per level the same two
+// separable passes over shared memory: T(sy) = src[sy][sx0]*cx0 + src[sy][sx1]*cx1 for every source row the window's
+// rows read (kept as T >> 4), then dst = (((cy0*(T(sy0) >> 4)) >> 16) + ((cy1*(T(sy1) >> 4)) >> 16) + 2) >> 2.
 // The windows (host tables, one entry per level and tile column / tile row) are widened to whole 4-pixel words in x so that
 // a thread produces one aligned 32-bit word for shared and global memory; the pixels a window gains that way reuse the
 // taps of its edge pixel (nobody reads them), so the widening does not compound down the cascade.
@@ -25,6 +26,7 @@ struct PyrSpan { int o0, o1, e0, e1, t0, t1; };   // one tile column (or row) at
 struct PyrFusedArgs {
   const PyrSpan* spanX; const PyrSpan* spanY;   // [level][tile column], [level][tile row]
   int TX, TY, bufBytes;
+  int tOff;                                     // byte offset of the horizontal-pass buffer (T >> 4, two 16-bit values per word)
   int tapOffX[MAX_LEVELS], tapOffY[MAX_LEVELS]; // entry offsets of level l's tap slices in the shared-memory tap area
 };
 
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(FrameSet fs, const
   }
   __syncthreads();
 
+  uint32_t* sT = reinterpret_cast<uint32_t*>(psm + A.tOff);
   for (int l = 1; l < fs.nlevels; ++l) {
     const LevelDev& D = fs.lv[l];
     const PyrSpan dx_ = sSpanX[l], dy_ = sSpanY[l];
@@ -114,52 +117,71 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(FrameSet fs, const
     uint8_t* dbuf = psm + (l & 1) * bufBytes;
     const int spitch = sx.e1 - sx.e0;                         // source window: columns [sx.e0, sx.e1), rows [sy.e0, sy.e1)
     const int ew4 = (dx_.e1 - dx_.e0) >> 2, eh = dy_.e1 - dy_.e0;
+    const int ew2 = 2 * ew4;                                  // column pairs = words of a T row
     const ResizeTap* tX = stap + A.tapOffX[l];               // slices: entry i = column dx_.e0 + i / row dy_.e0 + i
     const ResizeTap* tY = stap + A.tapOffY[l];
     uint8_t* gdst = plane + D.planeOff;
-    if (ew4 > 0 && eh > 0) {
+    const bool any = ew4 > 0 && eh > 0;
+    const int ry0 = any ? tY[0].s0 : 0, nsr = any ? tY[eh - 1].s1 - ry0 + 1 : 0;      // source rows the window's rows read
+    if (any) {
+      // Horizontal pass over those source rows (k_resize_level's: a thread owns two adjacent columns, one funnel shift and
+      // two IDP.2A per row; T >> 4 kept in 16 bits): each source row is filtered once, not once per output row.
+      const float inv = 1.0f / (float)ew2;
+      int ph, pd;
+      pf_divmod(tid, ew2, inv, ph, pd);
+      const int RP = PF_THREADS / ew2;                        // row phases (windows are at most ~130 columns wide)
+      if (ph < RP) {
+        const ResizeTap tA = tX[2 * pd], tB = tX[2 * pd + 1];
+        const unsigned cA = (unsigned)(uint16_t)tA.c0 | ((unsigned)(uint16_t)tA.c1 << 16);
+        const unsigned cB = (unsigned)(uint16_t)tB.c0 | ((unsigned)(uint16_t)tB.c1 << 16);
+        const int a0 = tA.s0 - sx.e0, dB = (int)tB.s0 - (int)tA.s0;
+        const int shA = 8 * (a0 & 3), shB = 8 * min(max(dB, 0), 2);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(sbuf + (ry0 - sy.e0 + ph) * spitch) + (a0 >> 2);
+        uint32_t* o = sT + ph * ew2 + pd;
+        const int pstep = RP * (spitch >> 2), ostep = RP * ew2;
+        if (dB <= 2) {
+          for (int r = ph; r < nsr; r += RP, p += pstep, o += ostep) {
+            const unsigned w = __funnelshift_r(p[0], p[1], shA);
+            const unsigned TA = __dp2a_lo(cA, w, 0u), TB = __dp2a_lo(cB, w >> shB, 0u);
+            *o = (TA >> 4) | ((TB >> 4) << 16);
+          }
+        } else {      // scale factors above 2: the second column has its own window
+          const int b0 = tB.s0 - sx.e0, wB = (b0 >> 2) - (a0 >> 2), shB2 = 8 * (b0 & 3);
+          for (int r = ph; r < nsr; r += RP, p += pstep, o += ostep) {
+            const unsigned TA = __dp2a_lo(cA, __funnelshift_r(p[0], p[1], shA), 0u);
+            const unsigned TB = __dp2a_lo(cB, __funnelshift_r(p[wB], p[wB + 1], shB2), 0u);
+            *o = (TA >> 4) | ((TB >> 4) << 16);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (any) {
+      // Vertical pass: four output pixels (one word) per item into the next window and, for the owned part, global memory
       const float inv = 1.0f / (float)ew4;
       int wy, wx, sdy, sdx;
       pf_divmod(tid, ew4, inv, wy, wx);
       pf_divmod(PF_THREADS, ew4, inv, sdy, sdx);
-      const uint8_t* sb0 = sbuf - sy.e0 * spitch - sx.e0;     // source pixel (x, y) of the previous level at sb0[y * spitch + x]
-      // four output pixels (one word) from the previous level's window; two words per trip so that the dependent
-      // shared-memory loads of two independent items overlap
-      auto item = [&](int iy, int ix) {
-        const ResizeTap ty_ = tY[iy];
-        const uint8_t* r0 = sb0 + ty_.s0 * spitch;
-        const uint8_t* r1 = sb0 + ty_.s1 * spitch;
-        const int b0 = ty_.c0, b1 = ty_.c1;
-        uint32_t word = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const ResizeTap t = tX[4 * ix + k];
-          const int T0 = r0[t.s0] * t.c0 + r0[t.s1] * t.c1;
-          const int T1 = r1[t.s0] * t.c0 + r1[t.s1] * t.c1;
-          const int v = (((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2;
-          word |= (uint32_t)v << (8 * k);
-        }
-        return word;
-      };
-      auto emit = [&](int iy, int ix, uint32_t word) {
-        const int y = dy_.e0 + iy, x4 = dx_.e0 + 4 * ix;
-        reinterpret_cast<uint32_t*>(dbuf)[iy * ew4 + ix] = word;
+      while (wy < eh) {
+        const ResizeTap t = tY[wy];
+        const uint2 P = *reinterpret_cast<const uint2*>(sT + (t.s0 - ry0) * ew2 + 2 * wx);
+        const uint2 Q = *reinterpret_cast<const uint2*>(sT + (t.s1 - ry0) * ew2 + 2 * wx);
+        const unsigned b0 = (unsigned)(int)t.c0, b1 = (unsigned)(int)t.c1;
+        const unsigned v0 = (__umulhi(b0, P.x << 16) + __umulhi(b1, Q.x << 16) + 2u) >> 2;
+        const unsigned v1 = (__umulhi(b0, P.x & 0xFFFF0000u) + __umulhi(b1, Q.x & 0xFFFF0000u) + 2u) >> 2;
+        const unsigned v2 = (__umulhi(b0, P.y << 16) + __umulhi(b1, Q.y << 16) + 2u) >> 2;
+        const unsigned v3 = (__umulhi(b0, P.y & 0xFFFF0000u) + __umulhi(b1, Q.y & 0xFFFF0000u) + 2u) >> 2;
+        const uint32_t word = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+        const int y = dy_.e0 + wy, x4 = dx_.e0 + 4 * wx;
+        reinterpret_cast<uint32_t*>(dbuf)[wy * ew4 + wx] = word;
         if (y >= dy_.o0 && y < dy_.o1 && x4 >= dx_.o0 && x4 < dx_.o1 && x4 < D.w)
           *reinterpret_cast<uint32_t*>(gdst + (size_t)y * D.pitch + x4) = word;
-      };
-      while (wy < eh) {
-        int wy2 = wy + sdy, wx2 = wx + sdx;
-        if (wx2 >= ew4) { wx2 -= ew4; ++wy2; }
-        const bool two = wy2 < eh;
-        const uint32_t wa = item(wy, wx);
-        const uint32_t wb = two ? item(wy2, wx2) : 0u;
-        emit(wy, wx, wa);
-        if (two) emit(wy2, wx2, wb);
-        wx = wx2 + sdx; wy = wy2 + sdy;
+        wx += sdx; wy += sdy;
         if (wx >= ew4) { wx -= ew4; ++wy; }
       }
     }
     sx = dx_; sy = dy_;
+    // the next level's horizontal pass reads dbuf (written above) and overwrites sT (read above)
     __syncthreads();
   }
 }
