@@ -73,7 +73,9 @@ struct DevBuf {
     n = count;
     return IVG_OK;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
+  bool view = false;                       // p points into another DevBuf's allocation
+  void view_of(void* q, size_t count) { release(); p = static_cast<T*>(q); n = count; view = true; }
 };
 
 }  // namespace
@@ -135,6 +137,7 @@ struct ivg_extractor {
   bool haveResults = false, havePyramid = false;
   std::vector<CellDev> cellsPlain, cellsWeighted;
   DevBuf<uint8_t> pyr, blur, qual, outKp, outDesc, stageImg, stageCost;
+  DevBuf<uint8_t> outAll; size_t outDescOff = 0, outNOff = 0;                // owner of outKp | outDesc | outN (views)
   DevBuf<uint8_t> projIn; DevBuf<uint2> projCand; DevBuf<int> projInt;   // N2 scratch
   void* outHost = nullptr; size_t outHostBytes = 0;                         // pinned staging for the results of the synchronous calls
   void* projHost = nullptr; size_t projHostBytes = 0;                       // N2 pinned staging (inputs, then match[] + nmatches)
@@ -157,6 +160,7 @@ struct ivg_extractor {
   DevBuf<int> levelCount, outN, sad, nExt, rowStart;
   DevBuf<uint4> sortedR;
   DevBuf<float> uRight, depth, kpQual;
+  DevBuf<float> udAll;                  // owner of uRight | depth (views)
   DevBuf<int> gridStart, gridIdx;
   // stereo on caller-supplied keypoints
   DevBuf<uint8_t> extKpL, extDescL, extKpR, extDescR;
@@ -487,11 +491,20 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   if ((rc = h->workLevel.alloc(B * fs.listCapTotal))) return rc;
   if ((rc = h->levelKp.alloc(B * fs.kpCap))) return rc;
   if ((rc = h->levelCount.alloc(B * MAX_LEVELS))) return rc;
-  if ((rc = h->outKp.alloc(B * fs.kpCap * 28))) return rc;
-  if ((rc = h->outDesc.alloc(B * fs.kpCap * 32))) return rc;
-  if ((rc = h->outN.alloc(B))) return rc;
-  if ((rc = h->uRight.alloc(B * fs.kpCap))) return rc;
-  if ((rc = h->depth.alloc(B * fs.kpCap))) return rc;
+  {
+    // keypoint records | descriptors | counts in ONE allocation: a full batch goes to the host in one copy
+    const size_t descOff = align_up(B * fs.kpCap * 28, 256), nOff = descOff + align_up(B * fs.kpCap * 32, 256);
+    h->outKp.release(); h->outDesc.release(); h->outN.release();
+    if ((rc = h->outAll.alloc(nOff + B * sizeof(int)))) return rc;
+    h->outKp.view_of(h->outAll.p, B * fs.kpCap * 28);
+    h->outDesc.view_of(h->outAll.p + descOff, B * fs.kpCap * 32);
+    h->outN.view_of(h->outAll.p + nOff, B);
+    h->outDescOff = descOff; h->outNOff = nOff;
+  }
+  h->uRight.release(); h->depth.release();                     // uRight | depth in one allocation, for the same reason
+  if ((rc = h->udAll.alloc(2 * B * fs.kpCap))) return rc;
+  h->uRight.view_of(h->udAll.p, B * fs.kpCap);
+  h->depth.view_of(h->udAll.p + B * fs.kpCap, B * fs.kpCap);
   if ((rc = h->sad.alloc(B * fs.kpCap))) return rc;
   CK(cudaMemcpyAsync(h->dCellsPlain.p, h->cellsPlain.data(), h->cellsPlain.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->dCellsWeighted.p, h->cellsWeighted.data(), h->cellsWeighted.size() * sizeof(CellDev), cudaMemcpyHostToDevice, h->stream));
@@ -775,11 +788,11 @@ void ivg_extractor_destroy(ivg_extractor* h) {
   if (h->stream && h->ownsStream) cudaStreamSynchronize(h->stream);
   if (h->copyIn) cudaStreamSynchronize(h->copyIn);
   if (h->copyOut) cudaStreamSynchronize(h->copyOut);
-  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release(); if (h->projHost) { cudaFreeHost(h->projHost); h->projHost = nullptr; } if (h->outHost) { cudaFreeHost(h->outHost); h->outHost = nullptr; }
+  h->pyr.release(); h->blur.release(); h->qual.release(); h->outKp.release(); h->outDesc.release(); h->outN.release(); h->outAll.release(); h->stageImg.release(); h->stageCost.release(); h->mapX.release(); h->mapY.release(); h->projIn.release(); h->projCand.release(); h->projInt.release(); if (h->projHost) { cudaFreeHost(h->projHost); h->projHost = nullptr; } if (h->outHost) { cudaFreeHost(h->outHost); h->outHost = nullptr; }
   h->dCellsPlain.release(); h->dCellsWeighted.release(); h->rtab.release(); h->pyrSpanX.release(); h->pyrSpanY.release(); h->cellList.release(); h->cellCost.release(); h->blurTiles.release();
   h->cellCount.release(); h->workCell.release(); h->workLevel.release(); h->levelKp.release(); h->levelCount.release();
   h->kpQual.release(); h->gridStart.release(); h->gridIdx.release();
-  h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release();
+  h->outN.release(); h->sad.release(); h->nExt.release(); h->uRight.release(); h->depth.release(); h->udAll.release();
   h->extKpL.release(); h->extDescL.release(); h->extKpR.release(); h->extDescR.release(); h->extU.release(); h->extD.release(); h->extS.release(); h->sortedR.release(); h->rowStart.release();
   for (cudaEvent_t e : h->profEv) cudaEventDestroy(e);
   drop_graph(h);
@@ -855,6 +868,11 @@ int ivg_device_input(ivg_extractor* h, int index, int which, void** dev_ptr, siz
   return IVG_OK;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
 static int copy_frames_in(ivg_extractor* h, uint8_t* plane, DevBuf<uint8_t>& stage, int n, const uint8_t* src, size_t stride, size_t frame_bytes,
                           bool src_on_device = false) {
   const FrameSet& fs = h->fs;
@@ -1162,11 +1180,6 @@ int ivg_run_batch(ivg_extractor* h) {
   return IVG_OK;
 }
 
-static bool is_pinned(const void* p) {
-  cudaPointerAttributes a{};
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
-}
 static int ensure_out_host(ivg_extractor* h, size_t bytes) {
   if (h->outHostBytes >= bytes) return IVG_OK;
   if (h->outHost) { cudaFreeHost(h->outHost); h->outHost = nullptr; h->outHostBytes = 0; }
@@ -1221,14 +1234,20 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
   // Pageable result buffers (a std::vector<cv::KeyPoint>, a cv::Mat): a device-to-host copy straight into them goes through
   // the driver's bounce buffers and blocks; land the records in the handle's pinned staging instead and copy only the
   // n records each frame really produced.
-  const size_t k = h->fs.kpCap, per = k * 60;
-  if ((rc = ensure_out_host(h, (size_t)n * per + (size_t)n * sizeof(int)))) return rc;
+  const size_t k = h->fs.kpCap;
+  const bool whole = n == h->maxBatch;         // the batch the buffers were sized for: records, descriptors and counts are one block
+  const size_t descOff = whole ? h->outDescOff : (size_t)n * k * 28, nOff = whole ? h->outNOff : (size_t)n * k * 60;
+  if ((rc = ensure_out_host(h, nOff + (size_t)n * sizeof(int)))) return rc;
   uint8_t* stg = (uint8_t*)h->outHost;
-  int* cnt = reinterpret_cast<int*>(stg + (size_t)n * per);
+  const int* cnt = reinterpret_cast<const int*>(stg + nOff);
   CK(cudaStreamWaitEvent(h->copyOut, h->evKernels, 0));
-  CK(cudaMemcpyAsync(stg, h->outKp.p, (size_t)n * k * 28, cudaMemcpyDeviceToHost, h->copyOut));
-  CK(cudaMemcpyAsync(stg + (size_t)n * k * 28, h->outDesc.p, (size_t)n * k * 32, cudaMemcpyDeviceToHost, h->copyOut));
-  CK(cudaMemcpyAsync(cnt, h->outN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
+  if (whole) {
+    CK(cudaMemcpyAsync(stg, h->outAll.p, nOff + (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
+  } else {
+    CK(cudaMemcpyAsync(stg, h->outKp.p, (size_t)n * k * 28, cudaMemcpyDeviceToHost, h->copyOut));
+    CK(cudaMemcpyAsync(stg + descOff, h->outDesc.p, (size_t)n * k * 32, cudaMemcpyDeviceToHost, h->copyOut));
+    CK(cudaMemcpyAsync(stg + nOff, h->outN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
+  }
   CK(cudaEventRecord(h->evD2H, h->copyOut));
   CK(cudaEventSynchronize(h->evD2H));      // results are on the host (=> the kernels and the upload before them are done); a
                                            // speculative matcher that the other eye's thread may have queued behind is not waited for
@@ -1236,7 +1255,7 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
     const int m = std::min(std::max(cnt[f], 0), (int)k);
     n_out[f] = cnt[f];
     std::memcpy(reinterpret_cast<uint8_t*>(keypoints) + (size_t)f * cap * 28, stg + (size_t)f * k * 28, (size_t)m * 28);
-    std::memcpy(descriptors + (size_t)f * cap * 32, stg + (size_t)n * k * 28 + (size_t)f * k * 32, (size_t)m * 32);
+    std::memcpy(descriptors + (size_t)f * cap * 32, stg + descOff + (size_t)f * k * 32, (size_t)m * 32);
   }
   return IVG_OK;
 }
@@ -1315,7 +1334,13 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
     ProfScope ps(left, IVG_K_STEREO);
     k_stereo_index<<<nPairs, 256, (nBins + 1) * sizeof(int), left->stream>>>(A);
   }
-  { ProfScope ps(left, IVG_K_STEREO); k_stereo_match<<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A); }
+  {
+    ProfScope ps(left, IVG_K_STEREO);
+    if ((long long)nPairs * ((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP)) <= 148)      // less than one CTA per SM: spread the keypoints wider
+      k_stereo_match<SM_KP_LAT><<<dim3((A.cap + SM_WARPS * SM_KP_LAT - 1) / (SM_WARPS * SM_KP_LAT), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A);
+    else
+      k_stereo_match<SM_KP><<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A);
+  }
   { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());
   return IVG_OK;
@@ -1371,9 +1396,11 @@ static void maybe_speculate_stereo(ivg_extractor* h) {
   link->specValid = false;
   if (stereo_enqueue(L, R, link->mbf, link->maxD, n) != IVG_OK) return;
   float* stg = (float*)L->specHost;
-  if (cudaMemcpyAsync(stg, L->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) != cudaSuccess ||
-      cudaMemcpyAsync(stg + (size_t)n * k, L->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) != cudaSuccess ||
-      cudaEventRecord(L->evD2Hs, L->copyOut) != cudaSuccess) { cudaGetLastError(); return; }
+  bool ok;
+  if (n == L->maxBatch) ok = cudaMemcpyAsync(stg, L->udAll.p, 2 * (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) == cudaSuccess;   // one block
+  else ok = cudaMemcpyAsync(stg, L->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) == cudaSuccess &&
+            cudaMemcpyAsync(stg + (size_t)n * k, L->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) == cudaSuccess;
+  if (!ok || cudaEventRecord(L->evD2Hs, L->copyOut) != cudaSuccess) { cudaGetLastError(); return; }
   link->specGenL = link->genL; link->specGenR = link->genR; link->specN = n; link->specValid = true;
 }
 
@@ -1419,8 +1446,12 @@ int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf,
   if (sync && uRight && depth && !is_pinned(uRight)) {           // pageable mvuRight / mvDepth: through the pinned staging (see ivg_extract_batch)
     if ((rc = ensure_out_host(left, 2 * (size_t)n * k * 4))) return rc;
     float* stg = (float*)left->outHost;
-    CK(cudaMemcpyAsync(stg, left->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
-    CK(cudaMemcpyAsync(stg + (size_t)n * k, left->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
+    if (n == left->maxBatch) {
+      CK(cudaMemcpyAsync(stg, left->udAll.p, 2 * (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
+    } else {
+      CK(cudaMemcpyAsync(stg, left->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
+      CK(cudaMemcpyAsync(stg + (size_t)n * k, left->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
+    }
     CK(cudaEventRecord(left->evD2Hs, left->copyOut));
     if ((rc = ivg_sync(left))) return rc;
     for (int f = 0; f < n; ++f) {

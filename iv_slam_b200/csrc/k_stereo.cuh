@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
 }
 
 constexpr int SM_KP = 8;                   // left keypoints per warp
+constexpr int SM_KP_LAT = 2;               // the same in the one-frame-at-a-time configuration
 constexpr int SM_ROWB = 48;                // staged bytes per patch row: right strip at [0,21), left patch at [32,43)
 constexpr int SM_SLOT = 11 * SM_ROWB;      // one keypoint's 11 rows
 #ifndef IVG_SM_WARPS
@@ -101,16 +102,19 @@ __device__ __forceinline__ unsigned dup16(unsigned w, int k) { return __byte_per
 #ifndef IVG_SM_MINB
 #define IVG_SM_MINB 10
 #endif
-__global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(FrameSet fs, StereoArgs A) {
-  __shared__ __align__(16) uint8_t patch[SM_WARPS][SM_KP][SM_SLOT];
+// KP = left keypoints per warp: SM_KP for batches (the per-keypoint chains of ten resident CTAs hide each other's latency),
+// SM_KP_LAT when one frame's 2000 keypoints are all there is: four times the warps, a quarter of the dependent loads each.
+template <int KP>
+__global__ void __launch_bounds__(32 * SM_WARPS, KP == SM_KP ? IVG_SM_MINB : 1) k_stereo_match(FrameSet fs, StereoArgs A) {
+  __shared__ __align__(16) uint8_t patch[SM_WARPS][KP][SM_SLOT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t pair = blockIdx.y;
-  const int iL0 = (blockIdx.x * SM_WARPS + warp) * SM_KP;
+  const int iL0 = (blockIdx.x * SM_WARPS + warp) * KP;
   const int N = A.nL[pair], Nr = A.nR[pair];
   if (iL0 >= A.cap) return;
   {
     uint4* z = reinterpret_cast<uint4*>(&patch[warp][0][0]);   // pad bytes must read as zero
-    for (int i = lane; i < SM_KP * SM_SLOT / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < KP * SM_SLOT / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncwarp();
 
@@ -127,17 +131,17 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
   const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
   float myU = 0.f, myV = 0.f;
   int myLev = -1;
-  if (lane < SM_KP && iL0 + lane < N) {
+  if (lane < KP && iL0 + lane < N) {
     const float* kl = reinterpret_cast<const float*>(A.kpL + (pair * A.cap + iL0 + lane) * 28);
     myU = kl[0]; myV = kl[1]; myLev = reinterpret_cast<const int*>(kl)[5];
   }
   int segB = 0, segN = 0;
   {
-    const int k3 = lane / 3, t = lane - 3 * k3, src = min(k3, SM_KP - 1);
+    const int k3 = lane / 3, t = lane - 3 * k3, src = min(k3, KP - 1);
     const float u = __shfl_sync(0xffffffffu, myU, src), v = __shfl_sync(0xffffffffu, myV, src);
     const int lev = __shfl_sync(0xffffffffu, myLev, src);
     const int oct = lev - 1 + t, row = (int)v;
-    if (k3 < SM_KP && lev >= 0 && lev < A.nLevels && oct >= 0 && oct < A.nLevels && row >= 0 && row < A.nRows && !(u < 0) && Nr > 0) {
+    if (k3 < KP && lev >= 0 && lev < A.nLevels && oct >= 0 && oct < A.nLevels && row >= 0 && row < A.nRows && !(u < 0) && Nr > 0) {
       // rows whose bucket can hold a keypoint with row in [floor(y - r), ceil(y + r)], r = 2*scale[oct]
       const int m = (int)ceilf(__fmul_rn(2.0f, fs.lv[oct].scale)) + 1;
       segB = __ldg(rs + oct * A.nRows + max(row - m, 0));
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
     }
   }
 
-  for (int k = 0; k < SM_KP; ++k) {
+  for (int k = 0; k < KP; ++k) {
     const int iL = iL0 + k;
     if (iL >= A.cap) break;
     const size_t o = pair * A.cap + iL;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
   bool kDo = false;
   float kSUR0 = 0.f, kScale = 1.f;
   int kOffR = 0, kOffL = 0, kPitch = 0;
-  if (lane < SM_KP && iL0 + lane < A.cap) {
+  if (lane < KP && iL0 + lane < A.cap) {
     if (kHit) {
       const LevelDev& L = fs.lv[myLev];
       const float sf = L.invScale;
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(32 * SM_WARPS, IVG_SM_MINB) k_stereo_match(Fra
   //   |d'| = 2*max(d',0) - d',  max(d',0) = max(R + (cL - L), cR_s) - cR_s   (one VIADDMNMX.S16x2 per pixel pair)
   // and the sum of d' over the window comes from window sums of R and the sum of L.  All integers: exact.
   // The 11th pixel of a row is paired with a dummy whose max() is exactly cR_s.
-  const int j = lane & 3, kk = lane >> 2;
+  const int j = lane & 3, kk = min(lane >> 2, KP - 1);      // lanes past 4*KP idle along (gDo is false for them)
   const uint8_t* S = &patch[warp][kk][0];
   unsigned cR2[11];
   int cL;
