@@ -26,6 +26,18 @@ constexpr int SEL_WARPS_LAT = 32;       // one-frame-at-a-time: only nlevels CTA
 // Shared memory is sized per handle (dynamic): FrameSet::selLevelCap level-list entries, selCellCap entries per warp for
 // a cell list, selCells per-cell scalars.  Lists longer than the caps are processed in global memory (same code).
 
+// Which of a[first+1], a[mid], a[last-1] libstdc++'s __move_median_to_first swaps to the front (every thread evaluates it
+// from three broadcast loads instead of waiting for one thread's compare-and-swap chain).
+__device__ __forceinline__ int sel_median3(const SelItem* a, int first, int last, uint32_t& pkey) {
+  const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
+  const uint32_t ka = a[A].key, kb = a[B].key, kc = a[C].key;      // sel_before(x, y) = x.key > y.key
+  int P;
+  if (ka > kb) P = kb > kc ? B : (ka > kc ? C : A);
+  else P = ka > kc ? A : (kb > kc ? C : B);
+  pkey = P == A ? ka : (P == B ? kb : kc);
+  return P;
+}
+
 // std::nth_element as libstdc++ runs it, executed by a WARP.  Same introselect skeleton as introselect.h (median-of-3 to
 // the front, unguarded Hoare partition, narrow, 3-element insertion sort, heap-select when the depth limit trips); only
 // the O(n) partition is parallel.  The sequential partition pairs the i-th element from the left that is not before
@@ -35,10 +47,10 @@ constexpr int SEL_WARPS_LAT = 32;       // one-frame-at-a-time: only nlevels CTA
 // positions scattered by rank into two scratch arrays, m = #{i : F[i] < R[i]} swaps done in parallel, and the cut is
 // F[m] if it lies below R[m-1] (the sequential left scan finds it first) else R[m-1] (the scan stops on the element the
 // last swap put there).  Produces the identical permutation (tests/test_gpu_parity.py::test_warp_nth_element).
-__device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int lane) {
-  if (n == 0 || nth == n) return;
-  int first = 0, last = n;
-  int depth = 2 * (31 - __clz(n));
+// The partition rounds of the replay from a given state (first, last, depth) to the end, executed by one warp.
+// The pivot swap a[first] <-> a[P] is done by lane 0 while the scan already runs: the scan reads position P as the key that
+// is being moved there (the old a[first]) and no other position changes.
+__device__ __forceinline__ void warp_nth_rounds(SelItem* a, int nth, int first, int last, int depth, uint16_t* sF, uint16_t* sR, int lane) {
   const unsigned lt = (1u << lane) - 1u;
   while (last - first > 3) {
     if (depth == 0) {
@@ -47,41 +59,36 @@ __device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uin
       return;
     }
     --depth;
-    if (lane == 0) {
-      const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
-      if (sel_before(a[A], a[B])) {
-        if (sel_before(a[B], a[C])) sel_swap(a, first, B);
-        else if (sel_before(a[A], a[C])) sel_swap(a, first, C);
-        else sel_swap(a, first, A);
-      } else if (sel_before(a[A], a[C])) sel_swap(a, first, A);
-      else if (sel_before(a[B], a[C])) sel_swap(a, first, C);
-      else sel_swap(a, first, B);
-    }
-    __syncwarp();
-    const uint32_t pkey = a[first].key;
+    uint32_t pkey;
+    const int P = sel_median3(a, first, last, pkey);
+    const SelItem fi = a[first];                               // the element the pivot swap moves to P
     const int lo = first + 1, hi = last;
     int TL = 0, TR = 0;
     for (int base = lo; base < hi; base += 32) {
       const int j = base + lane;
       const bool v = j < hi;
-      const uint32_t k = v ? a[j].key : 0u;
+      const uint32_t k = v ? (j == P ? fi.key : a[j].key) : 0u;
       const bool isL = v && !(k > pkey), isR = v && !(pkey > k);
       const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
       if (isL) sF[TL + __popc(mL & lt)] = (uint16_t)j;
       if (isR) sR[TR + __popc(mR & lt)] = (uint16_t)j;
       TL += __popc(mL); TR += __popc(mR);
     }
+    __syncwarp();                                              // every lane has read what it needs of the old array
+    if (lane == 0) { const SelItem pv = a[P]; a[P] = fi; a[first] = pv; }
     __syncwarp();
-    int m = 0;
+    int m = 0, x0 = 0, y0 = 0;
     const int lim = min(TL, TR);
     for (int base = 0; base < lim; base += 32) {
       const int i = base + lane;
-      const bool ok = i < lim && sF[i] < sR[TR - 1 - i];
-      const unsigned b = __ballot_sync(0xffffffffu, ok);
+      const int x = i < lim ? sF[i] : 0, y = i < lim ? sR[TR - 1 - i] : 0;
+      if (base == 0) { x0 = x; y0 = y; }
+      const unsigned b = __ballot_sync(0xffffffffu, i < lim && x < y);
       m += __popc(b);
       if (b != 0xffffffffu) break;
     }
-    for (int i = lane; i < m; i += 32) {
+    if (lane < m) { const SelItem t = a[x0]; a[x0] = a[y0]; a[y0] = t; }
+    for (int i = lane + 32; i < m; i += 32) {
       const int x = sF[i], y = sR[TR - 1 - i];
       const SelItem t = a[x]; a[x] = a[y]; a[y] = t;
     }
@@ -106,13 +113,18 @@ __device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uin
   __syncwarp();
 }
 
-// The same replay executed by a whole CTA (the one-frame-at-a-time configuration: one CTA per level, 32 warps): every
-// partition round handles all elements at once — stopper ranks from warp ballots plus a prefix over the warps' counts,
-// m from __syncthreads_count (the predicate F[i] < R[TR-1-i] is a prefix of trues), swaps in parallel.  Identical
-// permutation; every thread of the CTA must call it (n <= 65535, lists in shared memory).
-// BN_THREADS threads take part (the first BN_THREADS of the CTA; the rest must not call it): they meet on named barrier 1, so
-// the barriers cost what 8 warps cost, not what the whole CTA costs.
-constexpr int BN_THREADS = 256;
+__device__ __forceinline__ void warp_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int lane) {
+  if (n == 0 || nth == n) return;
+  warp_nth_rounds(a, nth, 0, n, 2 * (31 - __clz(n)), sF, sR, lane);
+}
+
+// The same replay executed by BN_THREADS threads of a CTA (the one-frame-at-a-time configuration: one CTA per level): a
+// partition round handles BN_THREADS elements per trip — stopper ranks from warp ballots plus a prefix over the warps'
+// counts, m from a counting barrier (the predicate F[i] < R[TR-1-i] is a prefix of trues), swaps in parallel.  Once the
+// range is down to BN_MIN elements, warp 0 finishes alone (rounds without barriers).  Identical permutation; exactly the
+// first BN_THREADS threads of the CTA call it (n <= 65535, lists in shared memory); they meet on named barrier 1, so a
+// barrier costs what 8 warps cost, not what the whole CTA costs.
+constexpr int BN_THREADS = 256, BN_MIN = 96;
 __device__ __forceinline__ void bn_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BN_THREADS) : "memory"); }
 __device__ __forceinline__ int bn_sync_count(bool p) {
   int r;
@@ -120,55 +132,45 @@ __device__ __forceinline__ int bn_sync_count(bool p) {
   return r;
 }
 
-__device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int* wcnt /*[2*32]*/) {
+__device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, uint16_t* sF, uint16_t* sR, int* wcnt /*[2][2*32]*/) {
   if (n == 0 || nth == n) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = BN_THREADS, nw = nthr >> 5;
   int first = 0, last = n;
   int depth = 2 * (31 - __clz(n));
   const unsigned lt = (1u << lane) - 1u;
-  while (last - first > 3) {
-    if (depth == 0) {
-      if (tid == 0) { sel_heap_select(a + first, nth + 1 - first, last - first); sel_swap(a, first, nth); }
-      bn_sync();
-      return;
-    }
+  int buf = 0;                                                // wcnt is double buffered: one barrier per trip
+  while (last - first > BN_MIN && depth > 0) {
     --depth;
-    if (tid == 0) {
-      const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
-      if (sel_before(a[A], a[B])) {
-        if (sel_before(a[B], a[C])) sel_swap(a, first, B);
-        else if (sel_before(a[A], a[C])) sel_swap(a, first, C);
-        else sel_swap(a, first, A);
-      } else if (sel_before(a[A], a[C])) sel_swap(a, first, A);
-      else if (sel_before(a[B], a[C])) sel_swap(a, first, C);
-      else sel_swap(a, first, B);
-    }
-    bn_sync();
-    const uint32_t pkey = a[first].key;
+    uint32_t pkey;
+    const int P = sel_median3(a, first, last, pkey);
+    const uint32_t fkey = a[first].key;
     const int lo = first + 1, hi = last;
     int TL = 0, TR = 0;
     for (int base = lo; base < hi; base += nthr) {
       const int j = base + tid;
       const bool v = j < hi;
-      const uint32_t k = v ? a[j].key : 0u;
+      const uint32_t k = v ? (j == P ? fkey : a[j].key) : 0u;
       const bool isL = v && !(k > pkey), isR = v && !(pkey > k);
       const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
-      if (lane == 0) { wcnt[warp] = __popc(mL); wcnt[32 + warp] = __popc(mR); }
+      int* wc = wcnt + 64 * buf;
+      buf ^= 1;
+      if (lane == 0) { wc[warp] = __popc(mL); wc[32 + warp] = __popc(mR); }
       bn_sync();
+      if (base == lo && tid == 0) sel_swap(a, first, P);      // every thread has read the three candidates, a[first] and a[P]
       // exclusive prefix of this warp's counts over the warps before it, and the totals: one lane per warp + a shuffle scan
-      int sl = lane < nw ? wcnt[lane] : 0, sr = lane < nw ? wcnt[32 + lane] : 0;
+      int sl = lane < nw ? wc[lane] : 0, sr = lane < nw ? wc[32 + lane] : 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+      for (int o = 1; o < 8; o <<= 1) {
         const int vl = __shfl_up_sync(0xffffffffu, sl, o), vr = __shfl_up_sync(0xffffffffu, sr, o);
         if (lane >= o) { sl += vl; sr += vr; }
       }
-      const int tL = __shfl_sync(0xffffffffu, sl, 31), tR = __shfl_sync(0xffffffffu, sr, 31);
+      const int tL = __shfl_sync(0xffffffffu, sl, nw - 1), tR = __shfl_sync(0xffffffffu, sr, nw - 1);
       const int pL = warp ? __shfl_sync(0xffffffffu, sl, warp - 1) : 0, pR = warp ? __shfl_sync(0xffffffffu, sr, warp - 1) : 0;
       if (isL) sF[TL + pL + __popc(mL & lt)] = (uint16_t)j;
       if (isR) sR[TR + pR + __popc(mR & lt)] = (uint16_t)j;
       TL += tL; TR += tR;
-      bn_sync();
     }
+    bn_sync();
     int m = 0;
     const int lim = min(TL, TR);
     for (int base = 0; base < lim; base += nthr) {
@@ -187,19 +189,7 @@ __device__ __forceinline__ void block_nth_element(SelItem* a, int nth, int n, ui
     bn_sync();
     if (cut <= nth) first = cut; else last = cut;
   }
-  if (tid == 0) {
-    for (int i = first + 1; i < last; ++i) {
-      const SelItem v = a[i];
-      if (sel_before(v, a[first])) {
-        for (int j = i; j > first; --j) a[j] = a[j - 1];
-        a[first] = v;
-      } else {
-        int j = i;
-        while (sel_before(v, a[j - 1])) { a[j] = a[j - 1]; --j; }
-        a[j] = v;
-      }
-    }
-  }
+  if (warp == 0) warp_nth_rounds(a, nth, first, last, depth, sF, sR, lane);      // also the depth-limit fallback
   bn_sync();
 }
 
@@ -211,7 +201,7 @@ __global__ void k_debug_nth_element(const uint32_t* keys, int n, int nth, uint32
   uint16_t* sR = sF + n;
   const int lane = threadIdx.x;
   if (blockDim.x > 32) {          // the CTA-wide replay of the one-frame-at-a-time configuration
-    __shared__ int wc[64];
+    __shared__ int wc[128];
     for (int i = lane; i < n; i += blockDim.x) a[i] = SelItem{keys[i], (uint32_t)i};
     __syncthreads();
     if (lane < BN_THREADS) block_nth_element(a, nth, n, sF, sR, wc);
@@ -237,37 +227,40 @@ struct SelShared {           // views into the dynamic shared memory block
   int* nTotal; int* nStored; int* nRetain; int* prefix;
   float* nfc;
   unsigned char* thr; unsigned char* noMore;
+  uint16_t* order;           // cells in the order the warps take them: those whose list has to be trimmed first
   uint16_t* cellScratch;     // [SEL_WARPS][2 * selCellCap]
   uint16_t* levelScratch;    // [2 * selLevelCap]
 };
 
 __host__ __device__ inline size_t sel_smem_bytes(int levelCap, int cellCap, int cells, int warps = SEL_WARPS) {
-  return (size_t)8 * levelCap + (size_t)8 * warps * cellCap + (size_t)cells * (5 * 4 + 2) + 16 +
+  return (size_t)8 * levelCap + (size_t)8 * warps * cellCap + (size_t)cells * (5 * 4 + 2 + 2) + 16 +
          (size_t)4 * warps * cellCap + (size_t)4 * levelCap + 16;
 }
 
 template <int MAX_THREADS>   // two instantiations: 8 warps (register budget of the throughput configuration) and 32 warps (latency)
 __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int sTotal, sCount;
+  __shared__ int sTotal, sCount, sNext;
   const int SEL_LEVEL_CAP = fs.selLevelCap, SEL_CELL_CAP = fs.selCellCap;
   const int nWarps = blockDim.x >> 5;
   SelShared S;
   {
-    unsigned char* p = smem_raw;
-    S.levelBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * SEL_LEVEL_CAP;
-    S.cellBuf = reinterpret_cast<SelItem*>(p); p += (size_t)8 * nWarps * SEL_CELL_CAP;
+    // offsets, not pointer arithmetic through uintptr_t: the compiler keeps seeing shared memory (LDS/STS, not generic accesses)
+    size_t o = 0;
+    S.levelBuf = reinterpret_cast<SelItem*>(smem_raw + o); o += (size_t)8 * SEL_LEVEL_CAP;
+    S.cellBuf = reinterpret_cast<SelItem*>(smem_raw + o); o += (size_t)8 * nWarps * SEL_CELL_CAP;
     const int nc = fs.selCells;
-    S.nTotal = reinterpret_cast<int*>(p); p += 4 * nc;
-    S.nStored = reinterpret_cast<int*>(p); p += 4 * nc;
-    S.nRetain = reinterpret_cast<int*>(p); p += 4 * nc;
-    S.prefix = reinterpret_cast<int*>(p); p += 4 * nc;
-    S.nfc = reinterpret_cast<float*>(p); p += 4 * nc;
-    S.thr = p; p += nc;
-    S.noMore = p; p += nc;
-    p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-    S.cellScratch = reinterpret_cast<uint16_t*>(p); p += (size_t)4 * nWarps * SEL_CELL_CAP;
-    S.levelScratch = reinterpret_cast<uint16_t*>(p);
+    S.nTotal = reinterpret_cast<int*>(smem_raw + o); o += 4 * (size_t)nc;
+    S.nStored = reinterpret_cast<int*>(smem_raw + o); o += 4 * (size_t)nc;
+    S.nRetain = reinterpret_cast<int*>(smem_raw + o); o += 4 * (size_t)nc;
+    S.prefix = reinterpret_cast<int*>(smem_raw + o); o += 4 * (size_t)nc;
+    S.nfc = reinterpret_cast<float*>(smem_raw + o); o += 4 * (size_t)nc;
+    S.thr = smem_raw + o; o += nc;
+    S.noMore = smem_raw + o; o += nc;
+    S.order = reinterpret_cast<uint16_t*>(smem_raw + o); o += 2 * (size_t)nc;
+    o = (o + 15) & ~(size_t)15;                                // smem_raw is 16-byte aligned
+    S.cellScratch = reinterpret_cast<uint16_t*>(smem_raw + o); o += (size_t)4 * nWarps * SEL_CELL_CAP;
+    S.levelScratch = reinterpret_cast<uint16_t*>(smem_raw + o);
   }
   const int level = blockIdx.x;
   const size_t img = blockIdx.y;
@@ -378,16 +371,25 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
     }
     __syncwarp();
     int run = 0;      // prefix[c] = retained keypoints of the cells before c (warp scan)
+    int nHeavy = 0, nLight = 0;
     for (int base = 0; base < nCells; base += 32) {
       const int c = base + lane;
-      const int k = c < nCells ? min(max(S.nRetain[c], 0), S.nTotal[c]) : 0;
+      const int nt = c < nCells ? S.nTotal[c] : 0;
+      const int k = c < nCells ? min(max(S.nRetain[c], 0), nt) : 0;
       int incl = k;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
       if (c < nCells) S.prefix[c] = run + incl - k;
       run += __shfl_sync(0xffffffffu, incl, 31);
+      // work order of the cells phase: cells that need a trim (the expensive ones) from the front, the others from the back
+      const bool heavy = c < nCells && nt > k && k > 0, light = c < nCells && !heavy;
+      const unsigned mh = __ballot_sync(0xffffffffu, heavy), ml = __ballot_sync(0xffffffffu, light);
+      const unsigned below = (1u << lane) - 1u;
+      if (heavy) S.order[nHeavy + __popc(mh & below)] = (uint16_t)c;
+      if (light) S.order[nCells - 1 - nLight - __popc(ml & below)] = (uint16_t)c;
+      nHeavy += __popc(mh); nLight += __popc(ml);
     }
-    if (lane == 0) sTotal = run;
+    if (lane == 0) { sTotal = run; sNext = 0; }
   }
   __syncthreads();
 
@@ -396,7 +398,14 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
                                              : reinterpret_cast<SelItem*>(fs.workLevel + img * fs.listCapTotal + L.listBase);
   const uint8_t* qual = fs.qual + img * fs.planeBytes + L.planeOff;
 
-  for (int c = warp; c < nCells; c += nWarps) {
+  // the warps take cells as they get free (per-cell cost varies by an order of magnitude); a cell's place in the level list
+  // is fixed by prefix[], so the order of processing does not show in the output
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&sNext, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= nCells) break;
+    const int c = S.order[q];
     const int n = S.nTotal[c];
     const int keep = min(max(S.nRetain[c], 0), n);
     if (keep == 0) continue;
@@ -423,39 +432,36 @@ __global__ void __launch_bounds__(MAX_THREADS) k_level_select(FrameSet fs) {
       run += __popc(m);
     }
     __syncwarp();
-    if (buf != wbuf) __threadfence_block();
     if (n > keep) {
-      if (buf == wbuf) warp_nth_element(buf, keep - 1, n, S.cellScratch + (size_t)warp * 2 * SEL_CELL_CAP,
+      // (wbuf, not buf: a pointer the compiler can see is shared memory -> LDS/STS instead of generic loads and stores)
+      if (buf == wbuf) warp_nth_element(wbuf, keep - 1, n, S.cellScratch + (size_t)warp * 2 * SEL_CELL_CAP,
                                         S.cellScratch + (size_t)warp * 2 * SEL_CELL_CAP + SEL_CELL_CAP, lane);
       else if (lane == 0) sel_nth_element(buf, keep - 1, n);      // oversized list in global memory: sequential replay
     }
     __syncwarp();
-    if (buf != wbuf) __threadfence_block();
     const int dst = S.prefix[c];
     for (int i = lane; i < keep; i += 32) levelBuf[dst + i] = buf[i];
     __syncwarp();
   }
-  __threadfence_block();
   __syncthreads();
 
   if (MAX_THREADS >= 512 && levelBuf == S.levelBuf && total > L.nDesired && L.nDesired > 0) {
     // latency configuration: the level's trim is the longest serial piece of the frame, all 32 warps take part
-    __shared__ int sWcnt[64];
-    if (tid < BN_THREADS) block_nth_element(levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, sWcnt);
+    __shared__ int sWcnt[128];
+    if (tid < BN_THREADS) block_nth_element(S.levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, sWcnt);
     if (tid == 0) { sCount = L.nDesired; fs.levelCount[img * MAX_LEVELS + level] = L.nDesired; }
   } else if (warp == 0) {
     int count = total;
     if (total > L.nDesired) {
       if (L.nDesired == 0) count = 0;
       else {
-        if (levelBuf == S.levelBuf) warp_nth_element(levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, lane);
+        if (levelBuf == S.levelBuf) warp_nth_element(S.levelBuf, L.nDesired - 1, total, S.levelScratch, S.levelScratch + SEL_LEVEL_CAP, lane);
         else if (lane == 0) sel_nth_element(levelBuf, L.nDesired - 1, total);
         count = L.nDesired;
       }
     }
     if (lane == 0) { sCount = count; fs.levelCount[img * MAX_LEVELS + level] = count; }
   }
-  __threadfence_block();
   __syncthreads();
   const int count = sCount;
   uint2* out = fs.levelKp + img * fs.kpCap + L.kpOff;
