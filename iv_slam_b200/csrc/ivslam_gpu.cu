@@ -635,7 +635,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
     A.kpR = h->outKp.p; A.nR = h->outN.p; A.cap = fs.kpCap; A.nRows = fs.lv[0].h; A.nLevels = fs.nlevels;
     A.sorted = h->sortedR.p; A.rowStart = h->rowStart.p;
     ProfScope ps(h, IVG_K_STEREO);
-    k_stereo_index<<<fs.nImages, 256, ((size_t)A.nRows * A.nLevels + 1) * sizeof(int), h->stream>>>(A);
+    k_stereo_index<<<fs.nImages, 1024, ((size_t)A.nRows * A.nLevels + 1) * sizeof(int), h->stream>>>(A);      // eager: a handful of frames
   }
   CK(cudaGetLastError());
   return IVG_OK;
@@ -1227,7 +1227,10 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
   int rc = ivg_upload_batch(h, n, images, width, height, stride, frame_bytes, costs, cost_stride, cost_frame_bytes);
   if (rc) return rc;
   if ((rc = ivg_run_batch(h))) return rc;
-  if (!keypoints || !descriptors || !n_out || is_pinned(keypoints)) {
+  // large pinned result buffers: straight DMA into them.  Small results (one frame at a time) and pageable buffers go through
+  // the handle's pinned staging: one device-to-host copy for records, descriptors and counts, then a memcpy of what was produced.
+  const bool smallWhole = n == h->maxBatch && (size_t)n * h->fs.kpCap * 60 <= ((size_t)1 << 20);
+  if (!keypoints || !descriptors || !n_out || (!smallWhole && is_pinned(keypoints))) {
     if ((rc = ivg_download_batch(h, keypoints, descriptors, cap, n_out))) return rc;
     return ivg_sync(h);
   }
@@ -1332,7 +1335,7 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
     if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (nBins + 1)))) return rc;
     A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
     ProfScope ps(left, IVG_K_STEREO);
-    k_stereo_index<<<nPairs, 256, (nBins + 1) * sizeof(int), left->stream>>>(A);
+    k_stereo_index<<<nPairs, nPairs <= EAGER_INDEX_MAX_BATCH ? 1024 : 256, (nBins + 1) * sizeof(int), left->stream>>>(A);
   }
   {
     ProfScope ps(left, IVG_K_STEREO);
@@ -1341,7 +1344,7 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
     else
       k_stereo_match<SM_KP><<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A);
   }
-  { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, 256, 0, left->stream>>>(A); }
+  { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, nPairs <= EAGER_INDEX_MAX_BATCH ? 1024 : 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());
   return IVG_OK;
 }

@@ -47,22 +47,25 @@ __device__ __forceinline__ int stereo_bin(float y, int oct, int nRows, int nLeve
   return oct * nRows + min(max((int)y, 0), nRows - 1);
 }
 
-__global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
+// 256 threads per pair in batches, 1024 when a handful of frames is all there is (the only CTA of the launch: the loops over
+// bins and keypoints get four times shorter)
+__global__ void __launch_bounds__(1024) k_stereo_index(StereoArgs A) {
   extern __shared__ int ssh[];               // nBins + 1 counters, then the scatter cursors in place
-  __shared__ int wsum[8];
+  __shared__ int wsum[32];
   const size_t pair = blockIdx.x;
   const int Nr = A.nR[pair], nRows = A.nRows, nBins = A.nRows * A.nLevels, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthr = blockDim.x;
   const uint8_t* kr0 = A.kpR + pair * A.cap * 28;
-  for (int i = tid; i <= nBins; i += 256) ssh[i] = 0;
+  for (int i = tid; i <= nBins; i += nthr) ssh[i] = 0;
   __syncthreads();
-  for (int iR = tid; iR < Nr; iR += 256) {
+  for (int iR = tid; iR < Nr; iR += nthr) {
     const float* kr = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28);
     const int bin = stereo_bin(kr[1], reinterpret_cast<const int*>(kr)[5], nRows, A.nLevels);
     if (bin >= 0) atomicAdd(&ssh[bin], 1);
   }
   __syncthreads();
   // exclusive scan over nBins+1 entries: each thread owns a contiguous chunk
-  const int per = (nBins + 1 + 255) / 256, b0 = min(tid * per, nBins + 1), b1 = min(b0 + per, nBins + 1);
+  const int per = (nBins + nthr) / nthr, b0 = min(tid * per, nBins + 1), b1 = min(b0 + per, nBins + 1);
   int local = 0;
   for (int i = b0; i < b1; ++i) local += ssh[i];
   int incl = local;
@@ -71,12 +74,18 @@ __global__ void __launch_bounds__(256) k_stereo_index(StereoArgs A) {
   if (lane == 31) wsum[warp] = incl;
   __syncthreads();
   int base = incl - local;
-  for (int w = 0; w < warp; ++w) base += wsum[w];
+  {
+    // sum of the warps before this one: one value per lane and a shuffle reduction
+    int ws = lane < warp ? wsum[lane] : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+    base += ws;
+  }
   int* rs = A.rowStart + pair * (size_t)(nBins + 1);
   for (int i = b0; i < b1; ++i) { const int c = ssh[i]; ssh[i] = base; rs[i] = base; base += c; }
   __syncthreads();
   uint4* out = A.sorted + pair * A.cap;
-  for (int iR = tid; iR < Nr; iR += 256) {
+  for (int iR = tid; iR < Nr; iR += nthr) {
     const float* kr = reinterpret_cast<const float*>(kr0 + (size_t)iR * 28);
     const float x = kr[0], y = kr[1];
     const int oct = reinterpret_cast<const int*>(kr)[5];
@@ -366,22 +375,25 @@ __device__ __forceinline__ void median_pick_bin(const int* hist, int k, int lane
   rest = __shfl_sync(0xffffffffu, r, owner);
 }
 
-__global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {
+constexpr int MED_STAGE = 4096;      // SAD values kept in shared memory between the three passes (longer lists are re-read)
+__global__ void __launch_bounds__(1024) k_stereo_median(StereoArgs A) {      // 256 threads per pair in batches, 1024 for a handful of frames
   __shared__ int hist[256];
+  __shared__ int ssad[MED_STAGE];
   __shared__ int sel[3];   // [0] chosen high byte, [1] rank inside it, [2] median value
   const size_t pair = blockIdx.x;
   const int N = A.nL[pair];
-  const int* sad = A.sad + pair * A.cap;
-  const int tid = threadIdx.x, lane = tid & 31;
-  hist[tid] = 0;
+  const int* gsad = A.sad + pair * A.cap;
+  const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+  const bool staged = N <= MED_STAGE;
+  if (tid < 256) hist[tid] = 0;
   __syncthreads();
-  int cnt = 0;
-  for (int i = tid; i < N; i += 256) {
-    const int s = sad[i];
-    if (s >= 0) { atomicAdd(&hist[(s >> 8) & 0xFF], 1); ++cnt; }
+  for (int i = tid; i < N; i += nthr) {
+    const int s = gsad[i];
+    if (staged) ssad[i] = s;
+    if (s >= 0) atomicAdd(&hist[(s >> 8) & 0xFF], 1);
   }
-  (void)cnt;
   __syncthreads();
+  const int* sad = staged ? ssad : gsad;
   if (tid < 32) {
     int t = 0;
 #pragma unroll
@@ -395,9 +407,9 @@ __global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {
   __syncthreads();
   const int hb = sel[0];
   if (hb < 0) return;                                  // no matches: nothing to filter
-  hist[tid] = 0;
+  if (tid < 256) hist[tid] = 0;
   __syncthreads();
-  for (int i = tid; i < N; i += 256) {
+  for (int i = tid; i < N; i += nthr) {
     const int s = sad[i];
     if (s >= 0 && ((s >> 8) & 0xFF) == hb) atomicAdd(&hist[s & 0xFF], 1);
   }
@@ -410,7 +422,7 @@ __global__ void __launch_bounds__(256) k_stereo_median(StereoArgs A) {
   __syncthreads();
   const float median = (float)sel[2];
   const float thDist = __fmul_rn(1.5f * 1.4f, median);
-  for (int i = tid; i < N; i += 256) {
+  for (int i = tid; i < N; i += nthr) {
     const int s = sad[i];
     if (s >= 0 && !((float)s < thDist)) { A.uRight[pair * A.cap + i] = -1.f; A.depth[pair * A.cap + i] = -1.f; }
   }
