@@ -144,7 +144,8 @@ struct ivg_extractor {
   bool haveGrid = false, haveStereo = false;
   DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
   int mapW = 0, mapH = 0;
-  size_t fastSmem = 0, resizeSmem = 0, selSmem = 0, selSmemLat = 0;
+  size_t fastSmem = 0, fastSmemLat = 0, resizeSmem = 0, selSmem = 0, selSmemLat = 0;
+  int fastLat[MAX_LEVELS][3] = {};      // fBH, fBX, fSeg of every level for the FC_THREADS_LAT configuration of k_fast_cells
   TmaMaps blurMaps{};                   // per level: 160 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
   TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
   bool resizeTma[MAX_LEVELS] = {false};
@@ -282,7 +283,7 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   size_t planeOff = 0;
   unsigned listOff = 0;
   int kpOff = 0, btBase = 0;
-  size_t fastSmem = 0, resizeSmem = 0;
+  size_t fastSmem = 0, fastSmemLat = 0, resizeSmem = 0;
   const float imageRatio = (float)W / H;
   for (int l = 0; l < nl; ++l) {
     LevelDev& L = fs.lv[l];
@@ -327,19 +328,25 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     L.fBW = (L.cellW + 31) / 32;
     {
       const int slots = (((L.cellW + 2) / 2 + 1 + 63) / 64) * 64;                         // pair slots a warp walks per row (64 per step)
-      auto bytes = [&](int bh, int* seg) {
+      auto bytes = [&](int bh, int* seg, int warps) {
         const int bx = bh < L.cellH ? 2 : 0;                                              // banded cells carry one overlap score row per side
         const size_t ssBytes = align_up((size_t)L.fSS * (bh + 2 + bx), 16), bitBytes = align_up((size_t)4 * L.fBW * (bh + 2), 16);
-        *seg = ((bh + bx + FC_WARPS - 1) / FC_WARPS) * slots;                             // per-warp pair list: its rows, every slot
-        return align_up((size_t)4 * L.fSP * (bh + 6 + bx), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * FC_WARPS * *seg;
+        *seg = ((bh + bx + warps - 1) / warps) * slots;                                   // per-warp pair list: its rows, every slot
+        return align_up((size_t)4 * L.fSP * (bh + 6 + bx), 16) + FC_SLACK + ssBytes + bitBytes + (size_t)2 * warps * *seg;
       };
       L.fShift = 1;
       while ((1 << L.fShift) < slots) ++L.fShift;                                         // list entry = (score row << fShift) | pair slot, 16 bits
       if ((65536 >> L.fShift) < 8) return IVG_ERR_CAPACITY;                               // cells wider than ~16k px
-      int bh = std::min(L.cellH, (65536 >> L.fShift) - 2);
-      while (bh > 4 && bytes(bh, &L.fSeg) > FAST_SMEM_BUDGET) --bh;                       // taller cells are processed in bands
-      L.fBH = bh; L.fBX = bh < L.cellH ? 2 : 0;
-      fastSmem = std::max(fastSmem, bytes(bh, &L.fSeg));
+      // band geometry for both CTA sizes (k_fast.cuh): the batch set lives in the FrameSet, the one-frame set is patched in at launch
+      for (int lat = 0; lat < 2; ++lat) {
+        const int warps = lat ? FC_WARPS_LAT : FC_WARPS;
+        int seg = 0;
+        int bh = std::min(L.cellH, (65536 >> L.fShift) - 2);
+        while (bh > 4 && bytes(bh, &seg, warps) > FAST_SMEM_BUDGET) --bh;                 // taller cells are processed in bands
+        const size_t need = bytes(bh, &seg, warps);
+        if (lat) { h->fastLat[l][0] = bh; h->fastLat[l][1] = bh < L.cellH ? 2 : 0; h->fastLat[l][2] = seg; fastSmemLat = std::max(fastSmemLat, need); }
+        else { L.fBH = bh; L.fBX = bh < L.cellH ? 2 : 0; L.fSeg = seg; fastSmem = std::max(fastSmem, need); }
+      }
     }
     const int hYlast = Hd - (L.rows - 1) * L.cellH + 6;       // window height of the last row (:951, :995)
     const int chW = std::max(hYlast - 6, 0);                    // weighted: every row searches this many rows
@@ -389,7 +396,9 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   std::vector<PyrSpan> spanX, spanY;
   {
     // k_pyramid_fused: windows of every level for every tile column / row (see k_pyramid_fused.cuh)
-    const int TX = std::max(1, (W + 99) / 100), TY = std::max(1, (H + 79) / 80);
+    // level-0 tile of a CTA: 80 x 64 measured best for one KITTI frame (96 CTAs; 100 x 80, 64 x 56, 48 x 48 are 2-3 us slower:
+    // fewer CTAs leave SMs idle, smaller tiles recompute more halo and pay the per-level fixed cost on more CTAs)
+    const int TX = std::max(1, (W + 79) / 80), TY = std::max(1, (H + 63) / 64);
     spanX.assign((size_t)nl * TX, PyrSpan{0, 0, 0, 0, 0, 0}); spanY.assign((size_t)nl * TY, PyrSpan{0, 0, 0, 0, 0, 0});
     auto build = [&](int T, bool isX, std::vector<PyrSpan>& out) {
       for (int t = 0; t < T; ++t) {
@@ -465,8 +474,8 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
     h->selSmem = sel_smem_bytes(fs.selLevelCap, fs.selCellCap, fs.selCells);
     h->selSmemLat = sel_smem_bytes(fs.selLevelCap, fs.selCellCap, fs.selCells, SEL_WARPS_LAT);
   }
-  h->fastSmem = fastSmem; h->resizeSmem = resizeSmem;
-  if (fastSmem > 200 * 1024 || resizeSmem > 200 * 1024) return IVG_ERR_CAPACITY;
+  h->fastSmem = fastSmem; h->fastSmemLat = fastSmemLat; h->resizeSmem = resizeSmem;
+  if (fastSmem > 200 * 1024 || fastSmemLat > 200 * 1024 || resizeSmem > 200 * 1024) return IVG_ERR_CAPACITY;
   if (fs.kpCap > 65535) return IVG_ERR_CAPACITY;           // stereo packs the right index in 16 bits
 
   const size_t B = (size_t)batch;
@@ -609,7 +618,16 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
     k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->aux>>>(fs, h->blurMaps);
     CK(cudaEventRecord(h->evJoin, h->aux));
   }
-  { ProfScope ps(h, IVG_K_FAST); k_fast_cells<<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS, h->fastSmem, h->stream>>>(fs); }
+  {
+    ProfScope ps(h, IVG_K_FAST);
+    if ((long long)fs.nCellsTotal * fs.nImages <= 4 * 148) {      // one or two frames: more warps per cell
+      FrameSet fl = fs;
+      for (int l = 0; l < fs.nlevels; ++l) { fl.lv[l].fBH = h->fastLat[l][0]; fl.lv[l].fBX = h->fastLat[l][1]; fl.lv[l].fSeg = h->fastLat[l][2]; }
+      k_fast_cells<FC_THREADS_LAT><<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS_LAT, h->fastSmemLat, h->stream>>>(fl);
+    } else {
+      k_fast_cells<FC_THREADS><<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS, h->fastSmem, h->stream>>>(fs);
+    }
+  }
   if (!fork) { ProfScope ps(h, IVG_K_BLUR); k_gauss7<<<dim3(fs.btTotal, fs.nImages), 256, 0, h->stream>>>(fs, h->blurMaps); }
   if (h->kpMode == 1) { ProfScope ps(h, IVG_K_SELECT); k_octree_select<<<dim3(fs.nlevels, fs.nImages), 256, sizeof(OctShared), h->stream>>>(fs); }
   else {
@@ -690,7 +708,8 @@ int init_device_constants(int device) {
   }
   CK(cudaFuncSetAttribute(k_level_select<SEL_WARPS * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_level_select<SEL_WARPS_LAT * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_fast_cells<FC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_fast_cells<FC_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_octree_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OctShared)));
   CK(cudaFuncSetAttribute(k_resize_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_pyramid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -68,12 +68,22 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&D)[16]) {
 #endif
 constexpr int FC_THREADS = IVG_FC_THREADS; // CTA size of k_fast_cells (per-cell fixed costs are paid once per warp: fewer, busier warps)
 constexpr int FC_WARPS = FC_THREADS / 32;
+#ifndef IVG_FC_THREADS_LAT
+#define IVG_FC_THREADS_LAT 256
+#endif
+constexpr int FC_THREADS_LAT = IVG_FC_THREADS_LAT, FC_WARPS_LAT = FC_THREADS_LAT / 32;
 constexpr int FC_SLACK = 272;   // bytes after the staged pixels that B's masked lanes may read (at most 65 words past the last row)
 
-__global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
+// FCT threads per cell: FC_THREADS in batches (8 CTAs per SM keep every scheduler busy; fewer, busier warps pay the per-cell
+// fixed costs less often), FC_THREADS_LAT when one or two frames' cells are all there is (two CTAs per SM: twice the warps on
+// each cell halve its critical path).  The per-level band geometry (fBH / fBX / fSeg) depends on the warp count: the host
+// passes the matching set in the FrameSet.
+template <int FCT>
+__global__ void __launch_bounds__(FCT) k_fast_cells(FrameSet fs) {
+  constexpr int FCW = FCT / 32;
   extern __shared__ __align__(16) unsigned char fsm[];
-  __shared__ int wcnt[2][FC_WARPS];
-  __shared__ int sred[3][FC_WARPS];
+  __shared__ int wcnt[2][FCW];
+  __shared__ int sred[3][FCW];
 
   const CellDev c = fs.cells[blockIdx.x];
   const LevelDev& L = fs.lv[c.level];
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     if (pass == 0 || ch > BH) {      // the minTh retry of a single-band cell finds its pixels still staged
       // per-thread source/destination pointers are set up once and bumped per row; two column groups per pass
       const int nG4 = SP >> 1;
-      const int rstep = FC_WARPS * pitch, dstep = FC_WARPS * SP;
+      const int rstep = FCW * pitch, dstep = FCW * SP;
       for (int gb = 0; gb < nG4; gb += 64) {
         const int g0 = gb + lane, g1 = g0 + 32;
         const bool st0 = g0 < nG4, st1 = g1 < nG4;
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
         const uint8_t* src = pix + (size_t)(gy0 + warp) * pitch + xa + 4 * g0;
         uint32_t* dst = sp + warp * SP + 2 * g0;
 #pragma unroll 2
-        for (int q = warp; q < nR; q += FC_WARPS, src += rstep, dst += dstep) {
+        for (int q = warp; q < nR; q += FCW, src += rstep, dst += dstep) {
           const uint32_t a0 = ld0 ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
           const uint32_t a1 = ld1 ? __ldg(reinterpret_cast<const uint32_t*>(src + 128)) : 0u;
           if (st0) *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(a0, 0u, 0x4140), __byte_perm(a0, 0u, 0x4342));
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     }
     {
       uint4* z = reinterpret_cast<uint4*>(ss);                // scores + bitmap are contiguous
-      for (int i = tid; i < ((ssBytes + bitBytes) >> 4); i += FC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < ((ssBytes + bitBytes) >> 4); i += FCT) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
 
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       const int up3 = 3 * (SP >> 1);                // three rows in 64-bit words (SP is even)
       const uint2* row = reinterpret_cast<const uint2*>(sp + (warp + 3) * SP + wE) + lane;
       unsigned e0 = (unsigned)(warp << sh) + 2u * lane;            // (score row, slot); fits 16 bits: the host bounds the band height
-      for (int y = warp; y < nSR; y += FC_WARPS, row += FC_WARPS * (SP >> 1), e0 += (unsigned)FC_WARPS << sh) {
+      for (int y = warp; y < nSR; y += FCW, row += FCW * (SP >> 1), e0 += (unsigned)FCW << sh) {
         const uint2* ctr = row;
         unsigned e = e0;
         for (int st = 0; st < nSteps; ++st, ctr += 32, e += 64) {
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     // ---- E: emit in row-major order; thread t owns the bitmap words [t*per, (t+1)*per): one scan per band
     {
       const int nWords = (r1 - r0) * BW;
-      const int per = (nWords + FC_THREADS - 1) / FC_THREADS;
+      const int per = (nWords + FCT - 1) / FCT;
       const int wbeg = tid * per, wend = min(wbeg + per, nWords);
       int cnt = 0;
       for (int i = wbeg; i < wend; ++i) cnt += __popc(sbit[i]);
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
       __syncthreads();
       int off = running + incl - cnt, tot = 0;
 #pragma unroll
-      for (int w = 0; w < FC_WARPS; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
+      for (int w = 0; w < FCW; ++w) { const int v = wcnt[par][w]; if (w < warp) off += v; tot += v; }
       running += tot;
       par ^= 1;
       if (cnt) {
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
     const uint8_t* q = fs.qual + img * fs.planeBytes + L.planeOff;
     // aligned words + DP4A against a byte mask that cuts the window's first and last word to [wx, wx + ww)
     const int xa0 = c.wx & ~3, xe = c.wx + c.ww, nw = (xe - xa0 + 3) >> 2;
-    for (int y = warp; y < c.wh; y += FC_WARPS) {
+    for (int y = warp; y < c.wh; y += FCW) {
       const uint32_t* qr = reinterpret_cast<const uint32_t*>(q + (size_t)(c.wy + y) * L.pitch + xa0);
       for (int k = lane; k < nw; k += 32) {
         const int b0 = xa0 + 4 * k;
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(FrameSet fs) {
   if (tid == 0) {
     int a = 0; unsigned s = 0;
 #pragma unroll
-    for (int w = 0; w < FC_WARPS; ++w) { a += sred[0][w]; s += (unsigned)sred[2][w]; }
+    for (int w = 0; w < FCW; ++w) { a += sred[0][w]; s += (unsigned)sred[2][w]; }
     // x: entries in the list (corners at the lower threshold), y: corners at iniTh
     fs.cellCount[img * fs.nCellsTotal + blockIdx.x] = countHigh ? make_int2(a, nIniPass) : make_int2(running, nIniPass);
     fs.cellCost[img * fs.cellCostStride + blockIdx.x] = s;

@@ -53,57 +53,53 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(FrameSet fs, const
   const int tid = threadIdx.x;
   ResizeTap* stap = reinterpret_cast<ResizeTap*>(psm + 2 * (size_t)bufBytes);
 
-  // Everything that costs a global-memory latency happens up front, in two rounds: (1) this CTA's window table of every
-  // level, (2) the tap-table slices of every level plus the level-0 window.  Inside the cascade every load is then a
-  // shared-memory load.
+  // Everything that costs a global-memory latency happens up front and at once: warp w stages tap slice w (x or y taps of
+  // one level, read through this CTA's window entry of that level), the first threads copy the window table of every level
+  // to shared memory, and all threads load the level-0 window.  Inside the cascade every load is a shared-memory load.
   __shared__ PyrSpan sSpanX[MAX_LEVELS], sSpanY[MAX_LEVELS];
-  __shared__ int4 sSeg[2 * MAX_LEVELS];        // tap slices to stage: (first flat entry, destination offset, source index of entry 0, -)
-  __shared__ int2 sSegClamp[2 * MAX_LEVELS];   // first / last source index an entry may use
-  __shared__ int sNSeg, sNEnt;
+  {
+    const int warp = tid >> 5, lane = tid & 31, nSeg = 2 * (fs.nlevels - 1);
+    for (int sgi = warp; sgi < nSeg; sgi += PF_THREADS / 32) {
+      const int l = 1 + (sgi >> 1);
+      const bool isY = sgi & 1;
+      const PyrSpan sp = isY ? A.spanY[l * TY + ty] : A.spanX[l * TX + tx];
+      const LevelDev& D = fs.lv[l];
+      const int rt = isY ? D.rtabY : D.rtabX, dim = isY ? D.h : D.w;
+      const int lo = rt + sp.t0, hi = rt + min(sp.t1, dim) - 1, src0 = rt + sp.e0, len = sp.e1 - sp.e0;      // entries outside the needed range reuse its edge
+      ResizeTap* dst = stap + (isY ? A.tapOffY[l] : A.tapOffX[l]);
+      for (int i = lane; i < len; i += 32) dst[i] = fs.rtab[min(max(src0 + i, lo), hi)];
+    }
+  }
   if (tid < fs.nlevels) sSpanX[tid] = A.spanX[tid * TX + tx];
   else if (tid >= 32 && tid < 32 + fs.nlevels) sSpanY[tid - 32] = A.spanY[(tid - 32) * TY + ty];
-  __syncthreads();
-  if (tid == 0) {
-    int n = 0, e = 0;
-    for (int l = 1; l < fs.nlevels; ++l) {
-      const LevelDev& D = fs.lv[l];
-      sSegClamp[n] = make_int2(D.rtabX + sSpanX[l].t0, D.rtabX + min(sSpanX[l].t1, D.w) - 1);
-      sSeg[n++] = make_int4(e, A.tapOffX[l], D.rtabX + sSpanX[l].e0, 0);
-      e += sSpanX[l].e1 - sSpanX[l].e0;
-      sSegClamp[n] = make_int2(D.rtabY + sSpanY[l].t0, D.rtabY + min(sSpanY[l].t1, D.h) - 1);
-      sSeg[n++] = make_int4(e, A.tapOffY[l], D.rtabY + sSpanY[l].e0, 0);
-      e += sSpanY[l].e1 - sSpanY[l].e0;
-    }
-    sNSeg = n; sNEnt = e;
-  }
-  __syncthreads();
-  {
-    const int nSeg = sNSeg, nEnt = sNEnt;
-    for (int i = tid; i < nEnt; i += PF_THREADS) {
-      int s = 0;
-      while (s + 1 < nSeg && sSeg[s + 1].x <= i) ++s;
-      const int4 g = sSeg[s];
-      const int2 c = sSegClamp[s];
-      stap[g.y + i - g.x] = fs.rtab[min(max(g.z + i - g.x, c.x), c.y)];
-    }
-  }
 
-  // level 0 window -> buffer 0
-  PyrSpan sx = sSpanX[0], sy = sSpanY[0];
+  // level 0 window -> buffer 0 (four independent loads in flight per thread)
+  PyrSpan sx = A.spanX[tx], sy = A.spanY[ty];
   {
     const LevelDev& S = fs.lv[0];
     const int ew4 = (sx.e1 - sx.e0) >> 2, eh = ew4 > 0 ? sy.e1 - sy.e0 : 0;
     const uint8_t* src = plane + S.planeOff + (size_t)sy.e0 * S.pitch + sx.e0;
     uint32_t* dst = reinterpret_cast<uint32_t*>(psm);
     if (eh > 0) {
-      const float inv = 1.0f / (float)ew4;
+      const float inv = __fdividef(1.0f, (float)ew4);
       int wy, wx, dy, dx;
       pf_divmod(tid, ew4, inv, wy, wx);
       pf_divmod(PF_THREADS, ew4, inv, dy, dx);
       while (wy < eh) {
-        dst[wy * ew4 + wx] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)wy * S.pitch) + wx);
-        wx += dx; wy += dy;
-        if (wx >= ew4) { wx -= ew4; ++wy; }
+        int py[4], px[4];
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          py[k] = wy; px[k] = wx;
+          wx += dx; wy += dy;
+          if (wx >= ew4) { wx -= ew4; ++wy; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (py[k] < eh) v[k] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)py[k] * S.pitch) + px[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (py[k] < eh) dst[py[k] * ew4 + px[k]] = v[k];
       }
     }
   }
@@ -126,7 +122,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(FrameSet fs, const
     if (any) {
       // Horizontal pass over those source rows (k_resize_level's: a thread owns two adjacent columns, one funnel shift and
       // two IDP.2A per row; T >> 4 kept in 16 bits): each source row is filtered once, not once per output row.
-      const float inv = 1.0f / (float)ew2;
+      const float inv = __fdividef(1.0f, (float)ew2);
       int ph, pd;
       pf_divmod(tid, ew2, inv, ph, pd);
       const int RP = PF_THREADS / ew2;                        // row phases (windows are at most ~130 columns wide)
@@ -155,13 +151,15 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(FrameSet fs, const
         }
       }
     }
-    __syncthreads();
+    // Vertical pass: four output pixels (one word) per item into the next window and, for the owned part, global memory
+    int wy = 0, wx = 0, sdy = 0, sdx = 0;
     if (any) {
-      // Vertical pass: four output pixels (one word) per item into the next window and, for the owned part, global memory
-      const float inv = 1.0f / (float)ew4;
-      int wy, wx, sdy, sdx;
+      const float inv = __fdividef(1.0f, (float)ew4);
       pf_divmod(tid, ew4, inv, wy, wx);
       pf_divmod(PF_THREADS, ew4, inv, sdy, sdx);
+    }
+    __syncthreads();
+    if (any) {
       while (wy < eh) {
         const ResizeTap t = tY[wy];
         const uint2 P = *reinterpret_cast<const uint2*>(sT + (t.s0 - ry0) * ew2 + 2 * wx);
@@ -183,7 +181,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(FrameSet fs, const
     sx = dx_; sy = dy_;
     // the next level's horizontal pass reads dbuf (written above) and overwrites sT (read above)
     __syncthreads();
-  }
+    }
 }
 
 }  // namespace ivg
