@@ -620,7 +620,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   }
   {
     ProfScope ps(h, IVG_K_FAST);
-    if ((long long)fs.nCellsTotal * fs.nImages <= 4 * 148) {      // one or two frames: more warps per cell
+    if ((long long)fs.nCellsTotal * fs.nImages <= 4 * 148) {      // one or two KITTI frames: more warps per cell (measured: 4 frames and up prefer 128)
       FrameSet fl = fs;
       for (int l = 0; l < fs.nlevels; ++l) { fl.lv[l].fBH = h->fastLat[l][0]; fl.lv[l].fBX = h->fastLat[l][1]; fl.lv[l].fSeg = h->fastLat[l][2]; }
       k_fast_cells<FC_THREADS_LAT><<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS_LAT, h->fastSmemLat, h->stream>>>(fl);

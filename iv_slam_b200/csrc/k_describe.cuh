@@ -49,7 +49,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int DK_SLOTS_BATCH = 64;       // keypoint slots per CTA, throughput configuration
-constexpr int DK_SLOTS_LAT = 16;         // latency configuration (small batches): 4x the CTAs, 2 keypoints per warp
+#ifndef IVG_DK_SLOTS_LAT
+#define IVG_DK_SLOTS_LAT 16
+#endif
+constexpr int DK_SLOTS_LAT = IVG_DK_SLOTS_LAT;         // latency configuration (small batches): 4x the CTAs, 2 keypoints per warp
 constexpr int DK_PR = 18;                // |rotated pattern offset| <= 18 (pattern radius 13*sqrt(2) rounds to 18)
 constexpr int DK_BOXW = 64, DK_BOXH = 2 * DK_PR + 1;   // TMA box: 64 x 37 bytes
 constexpr int DK_BOXN = 48;                             // narrow box for keypoints whose 37 columns start within 11 bytes of a 16-byte boundary
