@@ -669,3 +669,36 @@ def test_second_gpu_reproduces_the_first_and_one_host_result_array(gpu_api):
         assert out[k].tobytes() == ref[k].tobytes(), "%s differs between the 2-GPU and the 1-GPU run" % k
     assert int(out["nL"].min()) > 1500
     multi.close(), one.close()
+
+
+def test_one_frame_on_handles_reserved_for_a_batch_and_pinned_results(gpu_api, oracle):
+    """The synchronous one-frame calls take the one-copy path only when the frame IS the reserved batch.  On handles reserved for
+    more frames (records / descriptors / counts of a partial batch are not contiguous on the device) and with pinned result
+    buffers the other paths run; all of them must return the same frame."""
+    c = S.CONFIGS["C1"]
+    left, right = S.make_stereo_pair(c["w"], c["h"], 910)
+    gL, gR, oL, oR = _pair(gpu_api, oracle, 2000, 20, 7, False)
+    mb, maxD = reference_mb(c["mbf"], c["maxD"])
+    r = oracle.stereo_frame(oL, oR, left, right, None, c["mbf"], maxD, threads=2)
+    n = r["kL"].size
+
+    def check(tag):
+        kL, dL = gL(left)
+        kR, dR = gR(right)
+        u, d = gpu_api.compute_stereo_matches(gL, gR, c["mbf"], maxD)
+        assert_keypoints_equal(kL, r["kL"], tag + " left")
+        assert_keypoints_equal(kR, r["kR"], tag + " right")
+        assert np.array_equal(dL, r["dL"]) and np.array_equal(dR, r["dR"]), tag + ": descriptors"
+        assert np.array_equal(u[:n], r["uRight"]) and np.array_equal(d[:n], r["depth"]), tag + ": stereo"
+
+    check("frame = reserved batch")
+    gL.reserve(c["w"], c["h"], 3), gR.reserve(c["w"], c["h"], 3)
+    check("reserved for 3, first call")
+    check("reserved for 3, speculative matcher")
+    # split phases into pinned result arrays (straight DMA, three copies)
+    cap = gL.cap
+    kp = gpu_api.PinnedArray((1, cap), gpu_api.KP_DTYPE); ds = gpu_api.PinnedArray((1, cap, 32), np.uint8); ct = gpu_api.PinnedArray((1,), np.int32)
+    gL.upload(left[None]); gL.run(); gL.download(kp.array, ds.array, ct.array); gL.sync()
+    m = int(ct.array[0])
+    assert_keypoints_equal(kp.array[0, :m], r["kL"], "pinned results")
+    assert np.array_equal(ds.array[0, :m], r["dL"])
