@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     tma_load_3d(spatch[warp][q & 1], narrow ? &mapsN.m[level] : &maps.m[level], &bars[warp][q & 1], xa, sCy[j] - DK_PR, (int)img);
   };
   issue_patch(0);
-  issue_patch(1);
+  if (DK_SLOTS / 8 > 1) issue_patch(1);
 
   // ---- moments: lane = (row r of 3, word k of 9): every load instruction fetches three 36-byte row segments (the rows'
   // 31 patch bytes as aligned words), 11 instructions cover the 31 rows.  A word is funnel-shifted with its right
