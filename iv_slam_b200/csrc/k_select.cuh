@@ -47,6 +47,72 @@ __device__ __forceinline__ int sel_median3(const SelItem* a, int first, int last
 // positions scattered by rank into two scratch arrays, m = #{i : F[i] < R[i]} swaps done in parallel, and the cut is
 // F[m] if it lies below R[m-1] (the sequential left scan finds it first) else R[m-1] (the scan stops on the element the
 // last swap put there).  Produces the identical permutation (tests/test_gpu_parity.py::test_warp_nth_element).
+// Partition rounds on a range of at most 32 elements, held one per lane in registers (lane l = position first + l): the
+// same round as below, but stopper ranks and the cut come from ballots and popcounts instead of
+// scratch arrays in shared memory (one 32-entry scatter remains: the lanes of a swap find each other through it) — a round is a
+// chain of ~25 dependent register instructions and one shared-memory round trip instead of seven.  With r = rank of an L-stopper from the left and t = number of R-stoppers above a lane (= rank of an R-stopper
+// from the right): F[i] < R[TR-1-i] for the L-stopper of rank r is "t > r" on its own lane, the i-th swap pairs the lanes with
+// r == i and t == i, F[m] is the L-stopper with r == m and R[TR-m] the R-stopper with t == m-1.  Runs until the range is down
+// to three elements or the depth limit trips, writes the elements back and returns the narrowed range.
+__device__ __forceinline__ void warp_nth_rounds_reg(SelItem* a, int nth, int& first, int& last, int& depth, uint16_t* sF, uint16_t* sR, int lane) {
+  const int base = first, cnt = last - first, nr = nth - base;
+  SelItem it = SelItem{0u, 0u};
+  if (lane < cnt) it = a[base + lane];
+  uint32_t key = it.key, val = it.val;
+  int f = 0, e = cnt;
+  const unsigned lt = (1u << lane) - 1u, gt = ~lt & ~(1u << lane);
+  while (e - f > 3 && depth > 0) {
+    --depth;
+    const int A = f + 1, B = f + (e - f) / 2, C = e - 1;
+    const uint32_t ka = __shfl_sync(0xffffffffu, key, A), kb = __shfl_sync(0xffffffffu, key, B), kc = __shfl_sync(0xffffffffu, key, C);
+    int P;
+    if (ka > kb) P = kb > kc ? B : (ka > kc ? C : A);
+    else P = ka > kc ? A : (kb > kc ? C : B);
+    const uint32_t pkey = P == A ? ka : (P == B ? kb : kc);
+    {
+      // pivot swap a[first] <-> a[P]
+      const uint32_t kf = __shfl_sync(0xffffffffu, key, f), vf = __shfl_sync(0xffffffffu, val, f), vp = __shfl_sync(0xffffffffu, val, P);
+      if (lane == f) { key = pkey; val = vp; }
+      else if (lane == P) { key = kf; val = vf; }
+    }
+    const bool in = lane > f && lane < e;
+    const bool isL = in && !(key > pkey), isR = in && !(pkey > key);
+    const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
+    const int r = __popc(mL & lt), t = __popc(mR & gt);
+    const int m = __popc(__ballot_sync(0xffffffffu, isL && t > r));
+    const bool swL = isL && r < m, swR = isR && t < m;            // never both: a position takes part in at most one swap
+    // swap partners meet through two 32-entry scratch rows (MATCH.ANY costs ~11 cycles per distinct value: 350 cycles here)
+    if (swL) sF[r] = (uint16_t)lane;
+    if (swR) sR[t] = (uint16_t)lane;
+    const unsigned bF = __ballot_sync(0xffffffffu, isL && r == m), bR = __ballot_sync(0xffffffffu, isR && t == m - 1);
+    __syncwarp();
+    const int partner = swL ? (int)sR[r] : (swR ? (int)sF[t] : lane);
+    __syncwarp();
+    key = __shfl_sync(0xffffffffu, key, partner);
+    val = __shfl_sync(0xffffffffu, val, partner);
+    const int rprev = m > 0 ? __ffs(bR) - 1 : e;
+    const int fm = __ffs(bF) - 1;                                   // -1: no L-stopper of rank m (m == TL)
+    const int cut = (bF && fm < rprev) ? fm : rprev;
+    if (cut <= nr) f = cut; else e = cut;
+  }
+  if (e - f <= 3) {
+    // the closing __insertion_sort of at most three elements, also in registers: an element's place is the number of
+    // elements that go before it (larger key, or equal key and earlier position: the sort is stable)
+    const uint32_t k0 = __shfl_sync(0xffffffffu, key, f), k1 = __shfl_sync(0xffffffffu, key, min(f + 1, 31)), k2 = __shfl_sync(0xffffffffu, key, min(f + 2, 31));
+    const int c = e - f;
+    const int r0 = (c > 1 && k1 > k0) + (c > 2 && k2 > k0);
+    const int r1 = (k0 >= k1) + (c > 2 && k2 > k1);
+    const int o = lane - f;                                    // this lane's place in the range
+    const int srcLane = (o >= 0 && o < c) ? f + (r0 == o ? 0 : (c > 1 && r1 == o ? 1 : 2)) : lane;      // the third one takes the place that is left
+    key = __shfl_sync(0xffffffffu, key, srcLane);
+    val = __shfl_sync(0xffffffffu, val, srcLane);
+    f = e;                                                     // nothing left for the caller to sort
+  }
+  if (lane < cnt) a[base + lane] = SelItem{key, val};
+  __syncwarp();
+  first = base + f; last = base + e;
+}
+
 // The partition rounds of the replay from a given state (first, last, depth) to the end, executed by one warp.
 // The pivot swap a[first] <-> a[P] is done by lane 0 while the scan already runs: the scan reads position P as the key that
 // is being moved there (the old a[first]) and no other position changes.
@@ -58,6 +124,7 @@ __device__ __forceinline__ void warp_nth_rounds(SelItem* a, int nth, int first, 
       __syncwarp();
       return;
     }
+    if (last - first <= 32) { warp_nth_rounds_reg(a, nth, first, last, depth, sF, sR, lane); continue; }
     --depth;
     uint32_t pkey;
     const int P = sel_median3(a, first, last, pkey);
@@ -211,7 +278,14 @@ __global__ void k_debug_nth_element(const uint32_t* keys, int n, int nth, uint32
   }
   for (int i = lane; i < n; i += 32) a[i] = SelItem{keys[i], (uint32_t)i};
   __syncwarp();
+#ifdef IVG_SEL_CLOCK                      // developer build: cycles of one replay
+  const long long t0 = clock64();
+#endif
   warp_nth_element(a, nth, n, sF, sR, lane);
+#ifdef IVG_SEL_CLOCK
+  const long long t1 = clock64();
+  if (lane == 0) printf("warp nth_element n %d nth %d: %lld cycles\n", n, nth, t1 - t0);
+#endif
   for (int i = lane; i < n; i += 32) order[i] = a[i].val;
 }
 
