@@ -521,7 +521,7 @@ int build_shape(ivg_extractor* h, int W, int H, int batch) {
   if (!taps.empty()) CK(cudaMemcpyAsync(h->rtab.p, taps.data(), taps.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->pyrSpanX.p, spanX.data(), spanX.size() * sizeof(PyrSpan), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->pyrSpanY.p, spanY.data(), spanY.size() * sizeof(PyrSpan), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(h->outN.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->outAll.p, 0, h->outAll.n, h->stream));      // counts start at 0; record slots a frame does not fill and the alignment gaps are copied out with the block
   CK(cudaMemsetAsync(h->levelCount.p, 0, B * MAX_LEVELS * sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
 
