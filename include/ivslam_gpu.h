@@ -247,6 +247,10 @@ int ivg_profile_read(ivg_extractor* h, double* ms, long long* launches);
 int ivg_debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order);
 /* the same replay by a 1024-thread CTA (what k_level_select uses for the level trim of a single frame) */
 int ivg_debug_nth_element_block(int device, const uint32_t* keys, int n, int nth, uint32_t* order);
+/* Test hook: every kernel of the path exists in a throughput configuration (batches) and a one-frame configuration, chosen
+ * by grid size at launch.  mode 0 = automatic (default), 1 = always the throughput kernels, 2 = the one-frame kernels wherever
+ * their preconditions hold.  Results are identical in every mode; the tests run odd geometries through both. */
+int ivg_debug_force_config(ivg_extractor* h, int mode);
 /* When enabled (default off) run_batch wraps the kernel sequence of a batch in a CUDA graph that is re-used while
  * shape/batch stay the same. */
 int ivg_set_graph_mode(ivg_extractor* h, int enable);

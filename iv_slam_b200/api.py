@@ -99,6 +99,7 @@ def lib():
         "ivg_profile_read": (C.c_int, [vp, vp, vp]),
         "ivg_debug_nth_element": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
         "ivg_debug_nth_element_block": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+        "ivg_debug_force_config": (C.c_int, [vp, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -444,6 +445,10 @@ class ORBextractor:
         cnt = np.zeros(len(KERNEL_NAMES), np.int64)
         _ck(lib().ivg_profile_read(self._h, _p(ms), _p(cnt)), "ivg_profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_NAMES)}
+
+    def debug_force_config(self, mode):
+        """Test hook: 0 automatic, 1 always the throughput kernels, 2 the one-frame kernels wherever they apply."""
+        _ck(lib().ivg_debug_force_config(self._h, int(mode)), "ivg_debug_force_config")
 
     def set_graph_mode(self, on=True):
         """Replay the kernel sequence of a run as one CUDA graph (single-frame latency)."""

@@ -145,6 +145,7 @@ struct ivg_extractor {
   DevBuf<float> mapX, mapY;                   // N4: rectification maps of ivg_set_rectify_maps
   int mapW = 0, mapH = 0;
   size_t fastSmem = 0, fastSmemLat = 0, resizeSmem = 0, selSmem = 0, selSmemLat = 0;
+  int forceCfg = 0;                     // test hook (ivg_debug_force_config): 0 auto, 1 throughput kernels, 2 one-frame kernels
   int fastLat[MAX_LEVELS][3] = {};      // fBH, fBX, fSeg of every level for the FC_THREADS_LAT configuration of k_fast_cells
   TmaMaps blurMaps{};                   // per level: 160 x 38 x 1 boxes over the image-pyramid planes (k_gauss7)
   TmaMaps resizeMaps{}, resizeMapsQ{};  // per destination level l >= 1: source boxes over level l-1 of the image / cost-map planes
@@ -574,6 +575,9 @@ int honour_wait(ivg_extractor* h) {
   return IVG_OK;
 }
 
+// one-frame (latency) configuration of a kernel?  `small` = the launch would leave most of the GPU idle in the throughput configuration
+static inline bool one_frame_cfg(const ivg_extractor* h, bool small) { return h->forceCfg == 2 || (h->forceCfg == 0 && small); }
+
 FrameSet active_fs(const ivg_extractor* h) {
   FrameSet fs = h->fs;
   fs.nImages = h->curBatch;
@@ -586,7 +590,7 @@ FrameSet active_fs(const ivg_extractor* h) {
 int launch_pyramid(ivg_extractor* h, const FrameSet& fs) {
   const int planes = fs.nImages * (fs.weighted ? 2 : 1);
   static const bool noFused = getenv("IVSLAM_NO_FUSED_PYRAMID") != nullptr;      // developer A/B switch
-  if (h->pyrTX > 0 && !noFused && (long long)planes * h->pyrTX * h->pyrTY <= 2 * 148) {
+  if (h->pyrTX > 0 && !noFused && one_frame_cfg(h, (long long)planes * h->pyrTX * h->pyrTY <= 2 * 148) && (long long)planes * h->pyrTX * h->pyrTY <= 65535) {
     // one frame at a time: the whole cascade in one launch (k_pyramid_fused.cuh) instead of nlevels-1 dependent ones
     ProfScope ps(h, IVG_K_RESIZE);
     PyrFusedArgs A{};
@@ -620,7 +624,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   }
   {
     ProfScope ps(h, IVG_K_FAST);
-    if ((long long)fs.nCellsTotal * fs.nImages <= 4 * 148) {      // one or two KITTI frames: more warps per cell (measured: 4 frames and up prefer 128)
+    if (one_frame_cfg(h, (long long)fs.nCellsTotal * fs.nImages <= 4 * 148)) {      // one or two KITTI frames: more warps per cell (measured: 4 frames and up prefer 128)
       FrameSet fl = fs;
       for (int l = 0; l < fs.nlevels; ++l) { fl.lv[l].fBH = h->fastLat[l][0]; fl.lv[l].fBX = h->fastLat[l][1]; fl.lv[l].fSeg = h->fastLat[l][2]; }
       k_fast_cells<FC_THREADS_LAT><<<dim3(fs.nCellsTotal, fs.nImages), FC_THREADS_LAT, h->fastSmemLat, h->stream>>>(fl);
@@ -632,7 +636,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   if (h->kpMode == 1) { ProfScope ps(h, IVG_K_SELECT); k_octree_select<<<dim3(fs.nlevels, fs.nImages), 256, sizeof(OctShared), h->stream>>>(fs); }
   else {
     // few CTAs (one per level and frame): give each every warp it can use; big batches fill the GPU with 8-warp CTAs
-    const bool lat = fs.nlevels * fs.nImages <= 2 * 148 && h->selSmemLat <= 200 * 1024;
+    const bool lat = one_frame_cfg(h, fs.nlevels * fs.nImages <= 2 * 148) && h->selSmemLat <= 200 * 1024;
     ProfScope ps(h, IVG_K_SELECT);
     if (lat) k_level_select<SEL_WARPS_LAT * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS_LAT * 32, h->selSmemLat, h->stream>>>(fs);
     else k_level_select<SEL_WARPS * 32><<<dim3(fs.nlevels, fs.nImages), SEL_WARPS * 32, h->selSmem, h->stream>>>(fs);
@@ -641,7 +645,7 @@ int launch_extract_kernels(ivg_extractor* h, const FrameSet& fs) {
   {
     ProfScope ps(h, IVG_K_DESCRIBE);
     // one frame at a time: 16 keypoint slots per CTA, so that ~2000 keypoints spread over 125 CTAs instead of 32
-    if ((fs.kpCap + DK_SLOTS_BATCH - 1) / DK_SLOTS_BATCH * fs.nImages < 2 * 148)
+    if (one_frame_cfg(h, (fs.kpCap + DK_SLOTS_BATCH - 1) / DK_SLOTS_BATCH * fs.nImages < 2 * 148))
       k_orient_describe<DK_SLOTS_LAT><<<dim3((fs.kpCap + DK_SLOTS_LAT - 1) / DK_SLOTS_LAT, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN);
     else
       k_orient_describe<DK_SLOTS_BATCH><<<dim3((fs.kpCap + DK_SLOTS_BATCH - 1) / DK_SLOTS_BATCH, fs.nImages), 256, 0, h->stream>>>(fs, h->descMaps, h->descMapsN);
@@ -1354,16 +1358,16 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
     if ((rc = left->sortedR.alloc((size_t)nPairs * A.cap)) || (rc = left->rowStart.alloc((size_t)nPairs * (nBins + 1)))) return rc;
     A.sorted = left->sortedR.p; A.rowStart = left->rowStart.p;
     ProfScope ps(left, IVG_K_STEREO);
-    k_stereo_index<<<nPairs, nPairs <= EAGER_INDEX_MAX_BATCH ? 1024 : 256, (nBins + 1) * sizeof(int), left->stream>>>(A);
+    k_stereo_index<<<nPairs, one_frame_cfg(left, nPairs <= EAGER_INDEX_MAX_BATCH) ? 1024 : 256, (nBins + 1) * sizeof(int), left->stream>>>(A);
   }
   {
     ProfScope ps(left, IVG_K_STEREO);
-    if ((long long)nPairs * ((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP)) <= 148)      // less than one CTA per SM: spread the keypoints wider
+    if (one_frame_cfg(left, (long long)nPairs * ((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP)) <= 148))      // less than one CTA per SM: spread the keypoints wider
       k_stereo_match<SM_KP_LAT><<<dim3((A.cap + SM_WARPS * SM_KP_LAT - 1) / (SM_WARPS * SM_KP_LAT), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A);
     else
       k_stereo_match<SM_KP><<<dim3((A.cap + SM_WARPS * SM_KP - 1) / (SM_WARPS * SM_KP), nPairs), 32 * SM_WARPS, 0, left->stream>>>(fs, A);
   }
-  { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, nPairs <= EAGER_INDEX_MAX_BATCH ? 1024 : 256, 0, left->stream>>>(A); }
+  { ProfScope ps(left, IVG_K_MEDIAN); k_stereo_median<<<nPairs, one_frame_cfg(left, nPairs <= EAGER_INDEX_MAX_BATCH) ? 1024 : 256, 0, left->stream>>>(A); }
   CK(cudaGetLastError());
   return IVG_OK;
 }
@@ -1590,6 +1594,14 @@ int ivg_flush_l2(ivg_extractor* h, size_t bytes) {
   int rc = scratch.alloc(bytes);
   if (rc) return rc;
   CK(cudaMemsetAsync(scratch.p, 0x5a, bytes, h->stream));
+  return IVG_OK;
+}
+int ivg_debug_force_config(ivg_extractor* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return IVG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graph(h);                       // a captured graph holds the kernels of the old configuration
+  h->forceCfg = mode;
   return IVG_OK;
 }
 static int debug_nth_element(int device, const uint32_t* keys, int n, int nth, uint32_t* order, int threads);

@@ -105,6 +105,20 @@ def test_c4_4k_pair(gpu_api, oracle):
     assert info["n"] == 8000
 
 
+@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
+def test_baseline_configs_in_both_kernel_configurations(gpu_api, oracle, name):
+    """A single frame normally runs the one-frame kernels (fused pyramid, FAST with 8 warps per cell, 1024-thread selection,
+    16-slot describe, 2-keypoint matcher) and a batch the throughput ones; forcing each set on the BASELINE configurations
+    (4K included: banded FAST cells, 1632 pyramid tiles) must not change a bit."""
+    c = S.CONFIGS[name]
+    left, right = S.make_stereo_pair(c["w"], c["h"], c["seed"])
+    cost = S.make_cost_map(c["w"], c["h"], c["cost_seed"]) if name == "C2" else None
+    g = _pair(gpu_api, oracle, c["nfeatures"], c["iniThFAST"], c["minThFAST"], name == "C2")
+    for mode in (1, 2):
+        g[0].debug_force_config(mode), g[1].debug_force_config(mode)
+        _check_frame(gpu_api, oracle, *g, left, right, cost, c["mbf"], c["maxD"], "%s forced configuration %d" % (name, mode))
+
+
 def test_c5_stereo_stress_5000_keypoints(gpu_api, oracle):
     c = S.CONFIGS["C1"]
     left, right = S.make_stereo_pair(c["w"], c["h"], 4)
@@ -194,6 +208,11 @@ def test_random_geometries(gpu_api, oracle, seed):
             g[0](left, cost)
         return
     _check_frame(gpu_api, oracle, *g, left, right, cost, 120.0, 300.0, what)
+    # every kernel has a throughput and a one-frame configuration, picked by grid size: the same odd geometry through both
+    for mode, tag in ((1, "throughput kernels"), (2, "one-frame kernels")):
+        g[0].debug_force_config(mode), g[1].debug_force_config(mode)
+        _check_frame(gpu_api, oracle, *g, left, right, cost, 120.0, 300.0, what + " / " + tag)
+    g[0].debug_force_config(0), g[1].debug_force_config(0)
 
 
 # ----------------------------------------------------------------------------- edge cases
