@@ -91,6 +91,18 @@ int ivg_extract(ivg_extractor* h, const uint8_t* image, int width, int height, s
                 const uint8_t* cost, size_t cost_stride,
                 ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
 
+/* ---- both eyes of one stereo frame and the matcher in ONE call from ONE thread ----
+ * What Frame::Frame does with two std::threads (src/Frame.cc:115-125: ExtractORB on the left and right image) followed by
+ * ComputeStereoMatches (:127).  Uploads, kernels and downloads of the two handles are queued back to back on their streams, the
+ * matcher right behind them, and the host waits once per result: no thread creation, no two threads contending for the driver.
+ * Outputs as ivg_extract (per eye) and ivg_stereo_match (uRight / depth: cap floats, -1 where there is no match).
+ * cost_left: the left eye's cost-map or NULL (the right eye is never weighted). */
+int ivg_extract_stereo(ivg_extractor* left, ivg_extractor* right, const uint8_t* image_left, const uint8_t* image_right,
+                       int width, int height, size_t stride, const uint8_t* cost_left, size_t cost_stride,
+                       ivg_keypoint* kp_left, uint8_t* desc_left, int* n_left,
+                       ivg_keypoint* kp_right, uint8_t* desc_right, int* n_right,
+                       float mbf, float maxD, float* uRight, float* depth, int cap);
+
 /* ---- the same for a batch of n equally-shaped images (frame-parallel data path) ----
  * images: n frames, frame f starts at images + f*frame_bytes, rows `stride` bytes apart.  costs likewise or NULL.
  * keypoints: n*cap records, descriptors: n*cap*32 bytes, n_out: n ints.  Frame f writes at f*cap.

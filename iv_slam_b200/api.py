@@ -65,6 +65,7 @@ def lib():
         "ivg_max_keypoints": (C.c_int, [vp]),
         "ivg_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, C.c_int, i32p]),
         "ivg_extract_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz, vp, vp, C.c_int, vp]),
+        "ivg_extract_stereo": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, i32p, vp, vp, i32p, C.c_float, C.c_float, vp, vp, C.c_int]),
         "ivg_upload_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_upload_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_set_rectify_maps": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, sz]),
@@ -464,6 +465,26 @@ def compute_stereo_matches(left, right, mbf, maxD):
     d = np.empty(left.cap, np.float32)
     _ck(lib().ivg_stereo_match(left._h, right._h, mbf, maxD, _p(u), _p(d), left.cap), "ivg_stereo_match")
     return u, d
+
+
+def extract_stereo(left, right, image_left, image_right, mbf, maxD, mask_left=None):
+    """Both eyes and the matcher in one call from one thread (ivg_extract_stereo) ->
+    (kpsL, descL, kpsR, descR, mvuRight[nL], mvDepth[nL])."""
+    for im in (image_left, image_right):
+        assert im.dtype == np.uint8 and im.ndim == 2 and im.strides[1] == 1
+    assert image_left.shape == image_right.shape and image_left.strides == image_right.strides
+    if mask_left is not None:
+        assert mask_left.dtype == np.uint8 and mask_left.shape == image_left.shape and mask_left.strides[1] == 1
+    cap = max(left.cap, right.cap)
+    kL, kR = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    dL, dR = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    u, d = np.empty(cap, np.float32), np.empty(cap, np.float32)
+    nL, nR = C.c_int(0), C.c_int(0)
+    _ck(lib().ivg_extract_stereo(left._h, right._h, _p(image_left), _p(image_right), image_left.shape[1], image_left.shape[0],
+                                 image_left.strides[0], _p(mask_left), mask_left.strides[0] if mask_left is not None else 0,
+                                 _p(kL), _p(dL), C.byref(nL), _p(kR), _p(dR), C.byref(nR), mbf, maxD, _p(u), _p(d), cap), "ivg_extract_stereo")
+    left._batch = right._batch = 1
+    return kL[:nL.value].copy(), dL[:nL.value].copy(), kR[:nR.value].copy(), dR[:nR.value].copy(), u[:nL.value].copy(), d[:nL.value].copy()
 
 
 def compute_stereo_matches_batch(left, right, mbf, maxD, uRight=None, depth=None, sync=True):

@@ -98,7 +98,7 @@ struct ivg_extractor {
   int device = 0;
   std::shared_ptr<StereoLink> link;     // set by the first single-frame ivg_stereo_match of this handle with a partner
   unsigned long long runGen = 0;        // bumped by every upload and run: identifies what the device buffers currently hold
-  void* specHost = nullptr; size_t specHostBytes = 0;   // pinned staging of the speculative matcher's uRight / depth (left handle)
+  void* specHost = nullptr; size_t specHostBytes = 0;   // pinned staging of the matcher's uRight / depth (left handle)
   int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
   double scaleFactor = 1.2;
   bool enableIntrospection = false;
@@ -1242,30 +1242,16 @@ int ivg_share_stream(ivg_extractor* h, ivg_extractor* owner) {
   return IVG_OK;
 }
 
-int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
-                      size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes,
-                      ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
-  if (!h) return IVG_ERR_INVALID;
-  if (cap < h->kpCap) return IVG_ERR_CAPACITY;
-  int rc = ivg_upload_batch(h, n, images, width, height, stride, frame_bytes, costs, cost_stride, cost_frame_bytes);
-  if (rc) return rc;
-  if ((rc = ivg_run_batch(h))) return rc;
-  // large pinned result buffers: straight DMA into them.  Small results (one frame at a time) and pageable buffers go through
-  // the handle's pinned staging: one device-to-host copy for records, descriptors and counts, then a memcpy of what was produced.
-  const bool smallWhole = n == h->maxBatch && (size_t)n * h->fs.kpCap * 60 <= ((size_t)1 << 20);
-  if (!keypoints || !descriptors || !n_out || (!smallWhole && is_pinned(keypoints))) {
-    if ((rc = ivg_download_batch(h, keypoints, descriptors, cap, n_out))) return rc;
-    return ivg_sync(h);
-  }
-  // Pageable result buffers (a std::vector<cv::KeyPoint>, a cv::Mat): a device-to-host copy straight into them goes through
-  // the driver's bounce buffers and blocks; land the records in the handle's pinned staging instead and copy only the
-  // n records each frame really produced.
+// Results of the current run into the handle's pinned staging: one device-to-host copy when the run is the batch the buffers
+// were sized for (records | descriptors | counts are one block), three otherwise.  Leaves evD2H recorded on copyOut.
+static int staged_download_enqueue(ivg_extractor* h) {
+  const int n = h->curBatch;
   const size_t k = h->fs.kpCap;
-  const bool whole = n == h->maxBatch;         // the batch the buffers were sized for: records, descriptors and counts are one block
+  const bool whole = n == h->maxBatch;
   const size_t descOff = whole ? h->outDescOff : (size_t)n * k * 28, nOff = whole ? h->outNOff : (size_t)n * k * 60;
-  if ((rc = ensure_out_host(h, nOff + (size_t)n * sizeof(int)))) return rc;
+  int rc = ensure_out_host(h, nOff + (size_t)n * sizeof(int));
+  if (rc) return rc;
   uint8_t* stg = (uint8_t*)h->outHost;
-  const int* cnt = reinterpret_cast<const int*>(stg + nOff);
   CK(cudaStreamWaitEvent(h->copyOut, h->evKernels, 0));
   if (whole) {
     CK(cudaMemcpyAsync(stg, h->outAll.p, nOff + (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
@@ -1275,6 +1261,16 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
     CK(cudaMemcpyAsync(stg + nOff, h->outN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyOut));
   }
   CK(cudaEventRecord(h->evD2H, h->copyOut));
+  return IVG_OK;
+}
+// Waits for that copy and hands the caller the records each frame really produced.
+static int staged_download_collect(ivg_extractor* h, ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+  const int n = h->curBatch;
+  const size_t k = h->fs.kpCap;
+  const bool whole = n == h->maxBatch;
+  const size_t descOff = whole ? h->outDescOff : (size_t)n * k * 28, nOff = whole ? h->outNOff : (size_t)n * k * 60;
+  const uint8_t* stg = (const uint8_t*)h->outHost;
+  const int* cnt = reinterpret_cast<const int*>(stg + nOff);
   CK(cudaEventSynchronize(h->evD2H));      // results are on the host (=> the kernels and the upload before them are done); a
                                            // speculative matcher that the other eye's thread may have queued behind is not waited for
   for (int f = 0; f < n; ++f) {
@@ -1284,6 +1280,48 @@ int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width,
     std::memcpy(descriptors + (size_t)f * cap * 32, stg + descOff + (size_t)f * k * 32, (size_t)m * 32);
   }
   return IVG_OK;
+}
+
+int ivg_extract_batch(ivg_extractor* h, int n, const uint8_t* images, int width, int height, size_t stride,
+                      size_t frame_bytes, const uint8_t* costs, size_t cost_stride, size_t cost_frame_bytes,
+                      ivg_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+  if (!h) return IVG_ERR_INVALID;
+  if (cap < h->kpCap) return IVG_ERR_CAPACITY;
+  int rc = ivg_upload_batch(h, n, images, width, height, stride, frame_bytes, costs, cost_stride, cost_frame_bytes);
+  if (rc) return rc;
+  if ((rc = ivg_run_batch(h))) return rc;
+  // large pinned result buffers: straight DMA into them.  Small results (one frame at a time) and pageable buffers go through
+  // the handle's pinned staging: one device-to-host copy for records, descriptors and counts, then a memcpy of what was produced
+  // (a device-to-host copy straight into pageable memory goes through the driver's bounce buffers and blocks).
+  const bool smallWhole = n == h->maxBatch && (size_t)n * h->fs.kpCap * 60 <= ((size_t)1 << 20);
+  if (!keypoints || !descriptors || !n_out || (!smallWhole && is_pinned(keypoints))) {
+    if ((rc = ivg_download_batch(h, keypoints, descriptors, cap, n_out))) return rc;
+    return ivg_sync(h);
+  }
+  if ((rc = staged_download_enqueue(h))) return rc;
+  return staged_download_collect(h, keypoints, descriptors, cap, n_out);
+}
+
+// Both eyes of one stereo frame and the matcher from ONE host thread: everything is queued back to back on the two handles'
+// streams and the host waits once per result.  See include/ivslam_gpu.h.
+int ivg_extract_stereo(ivg_extractor* left, ivg_extractor* right, const uint8_t* image_left, const uint8_t* image_right,
+                       int width, int height, size_t stride, const uint8_t* cost_left, size_t cost_stride,
+                       ivg_keypoint* kp_left, uint8_t* desc_left, int* n_left, ivg_keypoint* kp_right, uint8_t* desc_right, int* n_right,
+                       float mbf, float maxD, float* uRight, float* depth, int cap) {
+  if (!left || !right || left == right || !image_left || !image_right || width <= 0 || height <= 0) return IVG_ERR_INVALID;
+  if (!kp_left || !desc_left || !n_left || !kp_right || !desc_right || !n_right || !uRight || !depth) return IVG_ERR_INVALID;
+  if (cap < left->kpCap || cap < right->kpCap) return IVG_ERR_CAPACITY;
+  const size_t fb = (size_t)height * stride;
+  int rc;
+  if ((rc = ivg_upload_batch(left, 1, image_left, width, height, stride, fb, cost_left, cost_stride, (size_t)height * cost_stride))) return rc;
+  if ((rc = ivg_run_batch(left))) return rc;
+  if ((rc = staged_download_enqueue(left))) return rc;   // before the matcher's results queue up on the same copy stream
+  if ((rc = ivg_upload_batch(right, 1, image_right, width, height, stride, fb, nullptr, 0, 0))) return rc;
+  if ((rc = ivg_run_batch(right))) return rc;          // a linked pair queues the matcher here (maybe_speculate_stereo)
+  if ((rc = staged_download_enqueue(right))) return rc;
+  if ((rc = ivg_stereo_match_batch(left, right, mbf, maxD, uRight, depth, cap, 1))) return rc;   // collects the queued matcher, or runs it and links the pair
+  if ((rc = staged_download_collect(left, kp_left, desc_left, cap, n_left))) return rc;
+  return staged_download_collect(right, kp_right, desc_right, cap, n_right);
 }
 
 int ivg_extract(ivg_extractor* h, const uint8_t* image, int width, int height, size_t stride,
@@ -1396,6 +1434,16 @@ static int stereo_enqueue(ivg_extractor* left, ivg_extractor* right, float mbf, 
   return IVG_OK;
 }
 
+// pinned staging of uRight | depth on the left handle (speculative and synchronous matcher results)
+static int ensure_spec_host(ivg_extractor* L, size_t bytes) {
+  if (L->specHostBytes >= bytes) return IVG_OK;
+  CK(cudaStreamSynchronize(L->copyOut));                         // nothing may still be landing in the old buffer
+  if (L->specHost) { cudaFreeHost(L->specHost); L->specHost = nullptr; L->specHostBytes = 0; }
+  CK(cudaHostAlloc(&L->specHost, bytes, cudaHostAllocPortable));
+  L->specHostBytes = bytes;
+  return IVG_OK;
+}
+
 static bool stereo_compatible(const ivg_extractor* left, const ivg_extractor* right) {
   return left->haveResults && right->haveResults && left->device == right->device && left->W == right->W && left->H == right->H &&
          left->nlevels == right->nlevels && left->curBatch == right->curBatch && left->fs.planeBytes == right->fs.planeBytes &&
@@ -1414,11 +1462,7 @@ static void maybe_speculate_stereo(ivg_extractor* h) {
   if (link->genL != L->runGen || link->genR != R->runGen || L->profile || R->profile || !stereo_compatible(L, R)) return;
   const int n = L->curBatch;
   const size_t k = L->fs.kpCap, bytes = 2 * (size_t)n * k * 4;
-  if (L->specHostBytes < bytes) {
-    if (L->specHost) { cudaFreeHost(L->specHost); L->specHost = nullptr; L->specHostBytes = 0; }
-    if (cudaHostAlloc(&L->specHost, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return; }
-    L->specHostBytes = bytes;
-  }
+  if (ensure_spec_host(L, bytes) != IVG_OK) { cudaGetLastError(); return; }
   link->specValid = false;
   if (stereo_enqueue(L, R, link->mbf, link->maxD, n) != IVG_OK) return;
   float* stg = (float*)L->specHost;
@@ -1470,8 +1514,9 @@ int ivg_stereo_match_batch(ivg_extractor* left, ivg_extractor* right, float mbf,
     link->genL = link->specGenL = left->runGen; link->genR = link->specGenR = right->runGen;
   }
   if (sync && uRight && depth && !is_pinned(uRight)) {           // pageable mvuRight / mvDepth: through the pinned staging (see ivg_extract_batch)
-    if ((rc = ensure_out_host(left, 2 * (size_t)n * k * 4))) return rc;
-    float* stg = (float*)left->outHost;
+    // (its own staging, not outHost: the keypoint records of ivg_extract_stereo may still be on their way into that one)
+    if ((rc = ensure_spec_host(left, 2 * (size_t)n * k * 4))) return rc;
+    float* stg = (float*)left->specHost;
     if (n == left->maxBatch) {
       CK(cudaMemcpyAsync(stg, left->udAll.p, 2 * (size_t)n * k * 4, cudaMemcpyDeviceToHost, left->copyOut));
     } else {

@@ -28,6 +28,19 @@ extern "C" int shim_stereo_frame(const unsigned char* left, const unsigned char*
     for (int i = 0; i < dL.rows; ++i) std::memcpy(descL + 32 * i, dL.data + (size_t)i * dL.step, 32);
     std::memcpy(uRight, u.data(), u.size() * sizeof(float));
     std::memcpy(depth, d.data(), d.size() * sizeof(float));
+    // the one-call front-end (ExtractStereoGPU) must return exactly what the two extractor calls + ComputeStereoMatchesGPU returned:
+    // first call = explicit matcher launch (links the pair), second and third = the matcher queued behind the right eye's run
+    for (int rep = 0; rep < 3; ++rep) {
+      std::vector<cv::KeyPoint> k2, kR2;
+      cv::Mat d2, dR2;
+      std::vector<float> u2, dd2;
+      ORB_SLAM2::ExtractStereoGPU(&exL, &exR, imL, imR, none, k2, d2, kR2, dR2, mbf, maxD, u2, dd2);
+      if (k2.size() != kL.size() || kR2.size() != kR.size() || u2.size() != u.size()) return -2;
+      if (std::memcmp(k2.data(), kL.data(), kL.size() * sizeof(cv::KeyPoint)) || std::memcmp(kR2.data(), kR.data(), kR.size() * sizeof(cv::KeyPoint))) return -3;
+      for (int i = 0; i < dL.rows; ++i) if (std::memcmp(d2.data + (size_t)i * d2.step, dL.data + (size_t)i * dL.step, 32)) return -4;
+      for (int i = 0; i < dR.rows; ++i) if (std::memcmp(dR2.data + (size_t)i * dR2.step, dR.data + (size_t)i * dR.step, 32)) return -4;
+      if (std::memcmp(u2.data(), u.data(), u.size() * sizeof(float)) || std::memcmp(dd2.data(), d.data(), d.size() * sizeof(float))) return -5;
+    }
     *levels = exL.GetLevels();
     *scale1 = exL.GetScaleFactors()[1];
     exL.SyncPyramidsToHost();
@@ -47,6 +60,7 @@ extern "C" int shim_construct_only() {
 // Drop-in latency: one stereo frame at a time exactly like the reference's Frame constructor — two std::threads run the
 // two extractor objects (src/Frame.cc:115-125), join, then ComputeStereoMatches (:193).  Returns mean milliseconds.
 #include "ivslam_gpu.h"
+// graph bit 2: the whole frame through ExtractStereoGPU (one call from one thread) instead of two threads + ComputeStereoMatches;
 // graph bit 0: CUDA-graph replay of the kernel sequence; bit 1: the caller keeps its two images in page-locked memory
 // (cv::cuda::HostMem / cudaHostAlloc — a one-line change where the reference allocates imLeft/imRight) so the upload is a
 // plain asynchronous DMA instead of the driver's pageable bounce path.
@@ -67,6 +81,7 @@ extern "C" double shim_frame_latency_ms(const unsigned char* left, const unsigne
     cv::Mat dL, dR;
     std::vector<float> u, d;
     auto frame = [&] {
+      if (graph & 4) { ORB_SLAM2::ExtractStereoGPU(&exL, &exR, imL, imR, none, kL, dL, kR, dR, mbf, maxD, u, d); return; }
       std::thread tl([&] { exL(imL, none, kL, dL); });
       std::thread tr([&] { exR(imR, none, kR, dR); });
       tl.join(); tr.join();

@@ -721,3 +721,22 @@ def test_one_frame_on_handles_reserved_for_a_batch_and_pinned_results(gpu_api, o
     m = int(ct.array[0])
     assert_keypoints_equal(kp.array[0, :m], r["kL"], "pinned results")
     assert np.array_equal(ds.array[0, :m], r["dL"])
+
+
+def test_one_call_stereo_front_end(gpu_api, oracle):
+    """ivg_extract_stereo = both eyes + the matcher queued from one thread.  First call: the matcher is launched explicitly and the
+    pair gets linked; from the second call on it is queued behind the right eye's run.  With and without a cost-map on the left
+    eye, changing images and calibration between calls; every call must equal the reference."""
+    c = S.CONFIGS["C2"]
+    gL, gR, oL, oR = _pair(gpu_api, oracle, c["nfeatures"], c["iniThFAST"], c["minThFAST"], True)
+    gL.set_graph_mode(True), gR.set_graph_mode(True)
+    mb, maxD = reference_mb(c["mbf"], c["maxD"])
+    for i, (seed, use_cost, md) in enumerate([(31, False, maxD), (32, False, maxD), (33, True, maxD), (34, True, 0.5 * maxD), (35, False, 0.5 * maxD)]):
+        left, right = S.make_stereo_pair(c["w"], c["h"], seed)
+        cost = S.make_cost_map(c["w"], c["h"], seed) if use_cost else None
+        kL, dL, kR, dR, u, d = gpu_api.extract_stereo(gL, gR, left, right, c["mbf"], md, cost)
+        r = oracle.stereo_frame(oL, oR, left, right, cost, c["mbf"], md, threads=2)
+        assert_keypoints_equal(kL, r["kL"], "one-call frame %d left" % i)
+        assert_keypoints_equal(kR, r["kR"], "one-call frame %d right" % i)
+        assert np.array_equal(dL, r["dL"]) and np.array_equal(dR, r["dR"]), "one-call frame %d: descriptors" % i
+        assert np.array_equal(u, r["uRight"]) and np.array_equal(d, r["depth"]), "one-call frame %d: stereo" % i

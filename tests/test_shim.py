@@ -49,7 +49,7 @@ def test_shim_matches_oracle(tmp_path, gpu_api, oracle):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = L.shim_stereo_frame(p(left), p(right), w, h, nf, 20, 7, C.c_float(386.1448), C.c_float(718.856), p(kps), p(desc),
                              C.byref(n), p(u), p(d), C.byref(levels), C.byref(s1), p(pyr1), C.byref(pw), C.byref(ph))
-    assert rc == 0
+    assert rc == 0, "shim_stereo_frame rc=%d (-2..-5: ExtractStereoGPU differs from the two extractor calls + ComputeStereoMatchesGPU)" % rc
     oL, oR = oracle.OracleExtractor(nf, 1.2, 8, 20, 7), oracle.OracleExtractor(nf, 1.2, 8, 20, 7)
     r = oracle.stereo_frame(oL, oR, left, right, None, 386.1448, 718.856)
     m = n.value

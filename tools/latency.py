@@ -22,7 +22,7 @@ def measure(iters=200):
     left, right = S.make_stereo_pair(1241, 376, 0)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     out = {}
-    for g, name in ((0, "plain"), (1, "graph"), (3, "graph_pinned_input")):
+    for g, name in ((0, "plain"), (1, "graph"), (3, "graph_pinned_input"), (5, "one_call"), (7, "one_call_pinned_input")):
         out[name] = L.shim_frame_latency_ms(p(left), p(right), 1241, 376, 2000, 20, 7, C.c_float(386.1448), C.c_float(718.856), iters, g)
     return out
 
