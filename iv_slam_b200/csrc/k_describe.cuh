@@ -48,7 +48,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int DK_SLOTS_BATCH = 64;       // keypoint slots per CTA, throughput configuration
+#ifndef IVG_DK_SLOTS_BATCH
+#define IVG_DK_SLOTS_BATCH 64
+#endif
+constexpr int DK_SLOTS_BATCH = IVG_DK_SLOTS_BATCH;       // keypoint slots per CTA, throughput configuration
 #ifndef IVG_DK_SLOTS_LAT
 #define IVG_DK_SLOTS_LAT 16
 #endif
