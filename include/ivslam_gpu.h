@@ -123,6 +123,12 @@ int ivg_upload_batch(ivg_extractor* h, int n, const uint8_t* images, int width, 
  * The caller guarantees the producer has finished writing (or was enqueued on a stream this handle is ordered after). */
 int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, int width, int height, size_t stride,
                             size_t frame_bytes, const uint8_t* d_costs, size_t cost_stride, size_t cost_frame_bytes);
+/* The same with the cost-maps as the introspection CNN emits them: FLOAT frames in device memory (n frames of height rows,
+ * cost_stride_floats apart).  The conversion the example driver asks libtorch for before it copies the map to the host,
+ * `(cost_img * 255.0).to(torch::kByte)` (Examples/Stereo/stereo_kitti.cc:513-514: float multiply, truncation toward zero,
+ * modulo 256), happens on the way into the cost-map plane. */
+int ivg_upload_batch_device_cost_f32(ivg_extractor* h, int n, const uint8_t* d_images, int width, int height, size_t stride,
+                                     size_t frame_bytes, const float* d_costs, size_t cost_stride_floats, size_t cost_frame_floats);
 /* SURVEY §8(f) N4 — the input prologue, fused into the upload.
  * ivg_set_rectify_maps: the CV_32FC1 maps of cv::initUndistortRectifyMap (Examples/Stereo/stereo_kitti.cc:284-343,
  *   stereo_euroc.cc:247-254), uploaded once; width x height is the rectified (output) size.  NULL maps clear them.

@@ -68,6 +68,7 @@ def lib():
         "ivg_extract_stereo": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, i32p, vp, vp, i32p, C.c_float, C.c_float, vp, vp, C.c_int]),
         "ivg_upload_batch": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_upload_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
+        "ivg_upload_batch_device_cost_f32": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, vp, sz, sz]),
         "ivg_set_rectify_maps": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, sz]),
         "ivg_search_by_projection_last": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp] + [C.c_float] * 9 +
                                           [C.c_int, C.c_float, C.c_int, vp, C.c_int, i32p]),
@@ -368,6 +369,12 @@ class ORBextractor:
         """Frames already in device memory (integer device pointers to n contiguous HxW u8 frames)."""
         _ck(lib().ivg_upload_batch_device(self._h, n, C.c_void_p(d_images), width, height, width, width * height,
                                           C.c_void_p(d_masks) if d_masks else None, width, width * height), "ivg_upload_batch_device")
+        self._batch = n
+
+    def upload_device_cost_f32(self, n, width, height, d_images, d_costs_f32):
+        """Device-resident u8 frames plus FLOAT cost-maps as the introspection CNN emits them (converted like (t * 255).to(uint8))."""
+        _ck(lib().ivg_upload_batch_device_cost_f32(self._h, n, C.c_void_p(d_images), width, height, width, width * height,
+                                                   C.c_void_p(d_costs_f32), width, width * height), "ivg_upload_batch_device_cost_f32")
         self._batch = n
 
     def run(self):

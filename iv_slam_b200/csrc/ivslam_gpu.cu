@@ -974,6 +974,20 @@ int ivg_upload_batch_device(ivg_extractor* h, int n, const uint8_t* d_images, in
   return IVG_OK;
 }
 
+int ivg_upload_batch_device_cost_f32(ivg_extractor* h, int n, const uint8_t* d_images, int width, int height, size_t stride,
+                                     size_t frame_bytes, const float* d_costs, size_t cost_stride_floats, size_t cost_frame_floats) {
+  if (!h || !d_images || !d_costs || n < 1 || stride < (size_t)width || cost_stride_floats < (size_t)width) return IVG_ERR_INVALID;
+  int rc = ivg_set_batch(h, n, width, height, 1);
+  if (rc) return rc;
+  if ((rc = honour_wait(h))) return rc;
+  if ((rc = copy_frames_in(h, h->pyr.p, h->stageImg, n, d_images, stride, frame_bytes, true))) return rc;
+  dim3 grid(((width + 3) / 4 + 255) / 256, height, n);
+  k_cost_from_f32<<<grid, 256, 0, h->stream>>>(d_costs, cost_frame_floats, cost_stride_floats, h->qual.p, h->fs.planeBytes, width, height, h->fs.lv[0].pitch);
+  h->launches++;
+  CK(cudaGetLastError());
+  return IVG_OK;
+}
+
 // ---------------------------------------------------------------------------------------- N2: SearchByProjection
 namespace {
 struct ProjUpload {   // packs the caller's host arrays into one pinned staging buffer -> one H2D copy

@@ -47,6 +47,24 @@ __global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ stag
   *reinterpret_cast<uint4*>(plane + f * planeBytes + (size_t)y * pitch + x16) = o;      // bytes past w land in the row padding
 }
 
+// N3 hand-off, float form: the introspection CNN's output as it leaves the network (float in [0, 1], contiguous H x W per
+// frame) becomes the u8 cost-map plane on the device — what Examples/Stereo/stereo_kitti.cc:513-514 does with
+// `(cost_img * 255.0).to(torch::kByte)`: a float multiply, then torch's float -> uint8 cast (through int64: truncation toward
+// zero, modulo 256).  Four pixels per thread, one aligned 32-bit store.
+__global__ void __launch_bounds__(256) k_cost_from_f32(const float* __restrict__ src, size_t frameFloats, size_t strideFloats,
+                                                       uint8_t* __restrict__ plane, size_t planeBytes, int w, int h, int pitch) {
+  const int x4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const size_t f = blockIdx.z;
+  if (x4 >= w) return;
+  const float* s = src + f * frameFloats + (size_t)y * strideFloats + x4;
+  uint32_t o = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (x4 + k < w) o |= (uint32_t)(uint8_t)(long long)__fmul_rn(__ldg(s + k), 255.0f) << (8 * k);
+  *reinterpret_cast<uint32_t*>(plane + f * planeBytes + (size_t)y * pitch + x4) = o;       // bytes past w land in the row padding
+}
+
 // blockIdx.z < nImages: image planes; blockIdx.z >= nImages (weighted batches only): the cost-map planes of the same
 // level — both pyramids of a level go out in one launch.
 __global__ void __launch_bounds__(256) k_resize_level(FrameSet fs, int level, const __grid_constant__ TmaMaps maps,

@@ -433,6 +433,31 @@ def test_device_resident_inputs_and_weighted_batch(gpu_api, oracle):
     assert np.array_equal(c2, cnt) and k2.tobytes() == kps.tobytes() and d2.tobytes() == desc.tobytes()
 
 
+def test_device_resident_float_cost_map(gpu_api, oracle):
+    """N3, float form: the CNN's float output stays on the GPU; the (t * 255).to(torch.uint8) of stereo_kitti.cc:513-514 happens on
+    the way into the cost-map plane.  Must equal the path that lets torch do the conversion and goes through the host."""
+    import torch
+    n, w, h = 2, 962, 598                                        # width not a multiple of 4: the last word of a row is partial
+    L = np.stack([S.make_image(w, h, 170 + i) for i in range(n)])
+    t = torch.rand((n, h, w), generator=torch.Generator().manual_seed(3), dtype=torch.float32)
+    t[0, 0, :8] = torch.tensor([0.0, 1.0, 0.5, 1.0 / 255.0, 0.999999, 254.9999 / 255.0, 1.0039216, 0.0039215])    # edges: 1.0 -> 255, just past 1 wraps
+    dL, dT = torch.from_numpy(L).cuda(), t.cuda()
+    cost = (dT * 255.0).to(torch.uint8).cpu().numpy()            # the reference's conversion, by torch itself
+    torch.cuda.synchronize()
+    g = gpu_api.ORBextractor(2000, 1.2, 8, 12, 7, True)
+    o = oracle.OracleExtractor(2000, 1.2, 8, 12, 7, True)
+    g.upload_device_cost_f32(n, w, h, dL.data_ptr(), dT.data_ptr())
+    g.run()
+    kps = np.zeros((n, g.cap), gpu_api.KP_DTYPE); desc = np.zeros((n, g.cap, 32), np.uint8); cnt = np.zeros(n, np.int32)
+    g.download(kps, desc, cnt)
+    g.sync()
+    for f in range(n):
+        assert np.array_equal(g.level(0, 2, f), cost[f]), "frame %d: converted cost-map plane" % f
+        ko, do = o(L[f], cost[f])
+        assert_keypoints_equal(kps[f, :cnt[f]], ko, "float cost frame %d" % f)
+        assert np.array_equal(desc[f, :cnt[f]], do)
+
+
 @pytest.mark.parametrize("intro", [False, True])
 def test_n1_frame_postprocess(gpu_api, oracle, intro):
     """N1: mvKeyQualScore (cost/256 at the rounded level-0 position) and AssignFeaturesToGrid (64x48, ascending indices)."""
