@@ -96,7 +96,8 @@ int ivg_extract(ivg_extractor* h, const uint8_t* image, int width, int height, s
  * ComputeStereoMatches (:127).  Uploads, kernels and downloads of the two handles are queued back to back on their streams, the
  * matcher right behind them, and the host waits once per result: no thread creation, no two threads contending for the driver.
  * Outputs as ivg_extract (per eye) and ivg_stereo_match (uRight / depth: cap floats, -1 where there is no match).
- * cost_left: the left eye's cost-map or NULL (the right eye is never weighted). */
+ * cost_left: the cost-map both ExtractORBWeighted threads receive (src/Frame.cc:116-117) or NULL; it weights an eye only if that
+ * handle was created with enableIntrospection — the reference creates the right one without (src/Tracking.cc:182-183). */
 int ivg_extract_stereo(ivg_extractor* left, ivg_extractor* right, const uint8_t* image_left, const uint8_t* image_right,
                        int width, int height, size_t stride, const uint8_t* cost_left, size_t cost_stride,
                        ivg_keypoint* kp_left, uint8_t* desc_left, int* n_left,

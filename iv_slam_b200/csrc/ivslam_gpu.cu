@@ -1330,7 +1330,10 @@ int ivg_extract_stereo(ivg_extractor* left, ivg_extractor* right, const uint8_t*
   if ((rc = ivg_upload_batch(left, 1, image_left, width, height, stride, fb, cost_left, cost_stride, (size_t)height * cost_stride))) return rc;
   if ((rc = ivg_run_batch(left))) return rc;
   if ((rc = staged_download_enqueue(left))) return rc;   // before the matcher's results queue up on the same copy stream
-  if ((rc = ivg_upload_batch(right, 1, image_right, width, height, stride, fb, nullptr, 0, 0))) return rc;
+  // Frame::Frame hands the same cost-map to both extraction threads (src/Frame.cc:116-117); it weights an eye only if that extractor
+  // was built with introspection — the reference builds the right one without (src/Tracking.cc:182-183), so it normally stays home
+  const uint8_t* cost_right = right->enableIntrospection ? cost_left : nullptr;
+  if ((rc = ivg_upload_batch(right, 1, image_right, width, height, stride, fb, cost_right, cost_stride, (size_t)height * cost_stride))) return rc;
   if ((rc = ivg_run_batch(right))) return rc;          // a linked pair queues the matcher here (maybe_speculate_stereo)
   if ((rc = staged_download_enqueue(right))) return rc;
   if ((rc = ivg_stereo_match_batch(left, right, mbf, maxD, uRight, depth, cap, 1))) return rc;   // collects the queued matcher, or runs it and links the pair

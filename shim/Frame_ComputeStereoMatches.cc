@@ -47,15 +47,16 @@ void ExtractStereoGPU(ORBextractor* left, ORBextractor* right, const cv::Mat& im
   if (imLeft.empty() || imRight.empty() || imLeft.cols != imRight.cols || imLeft.rows != imRight.rows || imLeft.step != imRight.step)
     throw std::runtime_error("ExtractStereoGPU: two non-empty images of the same size and row step expected");
   const bool weighted = !maskLeft.empty() && left->IntrospectionEnabled();     // src/ORBextractor.cc:1231
+  const bool useMask = !maskLeft.empty() && (left->IntrospectionEnabled() || right->IntrospectionEnabled());
   left->SetQualityScoresAvailable(weighted);
-  right->SetQualityScoresAvailable(false);
+  right->SetQualityScoresAvailable(!maskLeft.empty() && right->IntrospectionEnabled());
   const int cap = std::max(ivg_max_keypoints(left->handle()), ivg_max_keypoints(right->handle()));
   keysLeft.resize(cap); keysRight.resize(cap);
   cv::Mat dL(cap, 32, CV_8U), dR(cap, 32, CV_8U);
   std::vector<float> u(cap, -1.0f), d(cap, -1.0f);
   int nL = 0, nR = 0;
   const int rc = ivg_extract_stereo(left->handle(), right->handle(), imLeft.data, imRight.data, imLeft.cols, imLeft.rows, imLeft.step,
-                                    weighted ? maskLeft.data : nullptr, weighted ? (size_t)maskLeft.step : 0,
+                                    useMask ? maskLeft.data : nullptr, useMask ? (size_t)maskLeft.step : 0,
                                     reinterpret_cast<ivg_keypoint*>(keysLeft.data()), dL.data, &nL,
                                     reinterpret_cast<ivg_keypoint*>(keysRight.data()), dR.data, &nR, mbf, maxD, u.data(), d.data(), cap);
   if (rc != IVG_OK) throw std::runtime_error(std::string("ivg_extract_stereo: ") + ivg_strerror(rc) + " " + ivg_last_cuda_error());

@@ -98,7 +98,8 @@ void ComputeStereoMatchesGPU(ORBextractor* left, ORBextractor* right, int N, flo
 // Optional: the whole stereo front-end of Frame::Frame in one call from one thread — the two ExtractORB threads
 // (src/Frame.cc:115-125) and ComputeStereoMatches (:127).  Both eyes and the matcher are queued back to back on the device and
 // the host waits once: no thread creation per frame, no two threads contending for the driver (0.18 -> 0.13 ms per KITTI frame).
-// maskLeft: the left eye's cost-map or an empty Mat.  See shim/Frame_ComputeStereoMatches.cc for the lines to change in Frame.cc.
+// maskLeft: the cost-map Frame::Frame hands to both ExtractORBWeighted threads, or an empty Mat (it weights an eye only if that
+// extractor was built with introspection; the reference builds the right one without).  See shim/Frame_ComputeStereoMatches.cc for the lines to change in Frame.cc.
 void ExtractStereoGPU(ORBextractor* left, ORBextractor* right, const cv::Mat& imLeft, const cv::Mat& imRight, const cv::Mat& maskLeft,
                       std::vector<cv::KeyPoint>& keysLeft, cv::Mat& descLeft, std::vector<cv::KeyPoint>& keysRight, cv::Mat& descRight,
                       float mbf, float maxD, std::vector<float>& mvuRight, std::vector<float>& mvDepth);
