@@ -594,6 +594,19 @@ def main():
                 traffic_source = "profiles/ncu_dram_bytes_per_image.json: dram__bytes_read+write per image from the committed ncu --set full capture at 64 images per launch, scaled to %d images; not measured in this run" % B
         except Exception:
             pass
+        # the same kernel against the ISSUE roofline (it is integer-ALU work, not HBM-bound): warp instructions per image from the
+        # committed ncu capture / (SMs x 4 schedulers x the SM clock sampled during the run); not measured in this run either
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_warp_inst_per_image.json")) as f:
+                wi = json.load(f).get(dom)
+            mhz = (clocks or {}).get("sm_mhz")
+            if wi and mhz:
+                issue_peak = 148 * 4 * mhz * 1e6                  # warp instructions per second, one per scheduler per cycle
+                roof["issue_frac"] = wi * B / (roof["ms_per_launch"] * 1e-3) / issue_peak
+                roof["issue_frac_source"] = ("profiles/ncu_warp_inst_per_image.json (smsp__inst_executed per image, committed capture) x %d images / "
+                                             "launch time / (148 SMs x 4 schedulers x %.0f MHz)" % (B, mhz))
+        except Exception:
+            pass
         pb = 21.9e6
         roof.update({"traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_kind,
                      "whole_pipeline_GBps": pb * value / world / 1e9, "whole_pipeline_frac": pb * value / world / 1e9 / peak})

@@ -6,7 +6,10 @@ tag = sys.argv[1]
 rnd = sys.argv[2] if len(sys.argv) > 2 else "r2"      # file prefix under profiles/
 g = lambda n: os.path.join(ROOT, "gpurun_out", "%s_%s" % (tag, n))
 p = lambda n: os.path.join(ROOT, "profiles", n)
-subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), g("full.ncu-rep"), "64", p(rnd + "_ncu_summary.csv"), "/tmp/dram.json"], stdout=subprocess.DEVNULL)
+subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), g("full.ncu-rep"), "64", p(rnd + "_ncu_summary.csv"), "/tmp/dram.json", "/tmp/inst.json"], stdout=subprocess.DEVNULL)
+wi = json.load(open("/tmp/inst.json"))
+wi["k_stereo_match"] = wi.get("k_stereo_match", 0) + wi.pop("k_stereo_index", 0)
+json.dump(dict({"_note": "smsp__inst_executed.sum (warp instructions) per image (per pair for k_stereo_match incl. k_stereo_index; all 7 levels for k_resize_level) from the same capture"}, **wi), open(p("ncu_warp_inst_per_image.json"), "w"), indent=1)
 d = json.load(open("/tmp/dram.json"))
 d["k_stereo_match"] += d.pop("k_stereo_index", 0)
 out = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per image (per pair for k_stereo_match incl. k_stereo_index; all 7 levels for k_resize_level) from one ncu --set full capture at 64 images per launch (tools/record_run.sh, tools/ncu_summary.py)"}
