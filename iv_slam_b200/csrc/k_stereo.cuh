@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(1024) k_stereo_index(StereoArgs A) {
 }
 
 constexpr int SM_KP = 8;                   // left keypoints per warp
-constexpr int SM_KP_LAT = 2;               // the same in the one-frame-at-a-time configuration
+#ifndef IVG_SM_KP_LAT
+#define IVG_SM_KP_LAT 2
+#endif
+constexpr int SM_KP_LAT = IVG_SM_KP_LAT;   // the same in the one-frame-at-a-time configuration (1 and 4 measured: see profiles/README.md)
 constexpr int SM_ROWB = 48;                // staged bytes per patch row: right strip at [0,21), left patch at [32,43)
 constexpr int SM_SLOT = 11 * SM_ROWB;      // one keypoint's 11 rows
 #ifndef IVG_SM_WARPS
