@@ -44,3 +44,12 @@ for i in range(3):
     tl.start(); tr.start(); tl.join(); tr.join()
     us, ds = api.compute_stereo_matches(sL, sR, 100.0, 400.0)
 print("single-frame stereo matches", int((us >= 0).sum()))
+# the one-call front-end (both eyes + matcher queued from one thread), then both kernel configurations by force
+for i in range(3):
+    kL1, dL1, kR1, dR1, u1, d1 = api.extract_stereo(sL, sR, L[i % 2], R[i % 2], 100.0, 400.0)
+print("one-call stereo matches", int((u1 >= 0).sum()))
+for mode in (1, 2, 0):
+    sL.debug_force_config(mode); sR.debug_force_config(mode)
+    sL(L[0]); sR(R[0])
+    us, ds = api.compute_stereo_matches(sL, sR, 100.0, 400.0)
+    print("forced configuration", mode, "stereo matches", int((us >= 0).sum()))
