@@ -765,3 +765,29 @@ def test_one_call_stereo_front_end(gpu_api, oracle):
         assert_keypoints_equal(kR, r["kR"], "one-call frame %d right" % i)
         assert np.array_equal(dL, r["dL"]) and np.array_equal(dR, r["dR"]), "one-call frame %d: descriptors" % i
         assert np.array_equal(u, r["uRight"]) and np.array_equal(d, r["depth"]), "one-call frame %d: stereo" % i
+
+
+def test_one_call_front_end_error_paths(gpu_api):
+    """ivg_extract_stereo refuses what it cannot do instead of guessing: the same handle twice, result buffers smaller than the
+    extractors' capacity, two extractors whose results cannot be matched (different feature counts)."""
+    import ctypes as C
+    left, right = S.make_stereo_pair(640, 400, 3)
+    gL, gR = gpu_api.ORBextractor(1000, 1.2, 8, 20, 7), gpu_api.ORBextractor(1000, 1.2, 8, 20, 7)
+    L = gpu_api.lib()
+    cap = gL.cap
+    kp = np.zeros((2, cap), gpu_api.KP_DTYPE); ds = np.zeros((2, cap, 32), np.uint8); u = np.zeros((2, cap), np.float32)
+    nL, nR = C.c_int(0), C.c_int(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def call(hl, hr, c):
+        return L.ivg_extract_stereo(hl._h, hr._h, p(left), p(right), 640, 400, 640, None, 0, p(kp[0]), p(ds[0]), C.byref(nL), p(kp[1]), p(ds[1]),
+                                    C.byref(nR), 100.0, 400.0, p(u[0]), p(u[1]), c)
+    assert call(gL, gL, cap) == -1            # IVG_ERR_INVALID: one handle cannot be both eyes
+    assert call(gL, gR, cap - 1) == -3        # IVG_ERR_CAPACITY
+    assert call(gL, gR, cap) == 0 and nL.value > 500 and nR.value > 500
+    other = gpu_api.ORBextractor(1500, 1.2, 8, 20, 7)
+    big = max(cap, other.cap)
+    kp = np.zeros((2, big), gpu_api.KP_DTYPE); ds = np.zeros((2, big, 32), np.uint8); u = np.zeros((2, big), np.float32)
+    assert call(gL, other, big) == -6         # IVG_ERR_STATE: the two results have different capacities, no matcher for them
+    kL, dL, kR, dR, uu, dd = gpu_api.extract_stereo(gL, gR, left, right, 100.0, 400.0)      # and the pair still works afterwards
+    assert kL.size == nL.value and (uu >= 0).sum() > 100
