@@ -1429,7 +1429,7 @@ static int stereo_launch(ivg_extractor* left, ivg_extractor* right, StereoArgs& 
 
 // matcher kernels of the current results of (left, right) on left's stream, ordered after right's work; leaves copyOut
 // of the left handle waiting for them
-static int stereo_enqueue(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD, int n) {
+static int stereo_enqueue(ivg_extractor* left, ivg_extractor* right, float mbf, float maxD, int n, float* hostU = nullptr, float* hostD = nullptr) {
   CK(cudaEventRecord(right->evDone, right->stream));
   CK(cudaStreamWaitEvent(left->stream, right->evDone, 0));
   CK(cudaStreamWaitEvent(left->stream, left->evD2Hs, 0));        // previous uRight/depth have been read
@@ -1439,6 +1439,7 @@ static int stereo_enqueue(ivg_extractor* left, ivg_extractor* right, float mbf, 
   A.pyrL = left->pyr.p; A.pyrR = right->pyr.p; A.planeBytes = left->fs.planeBytes;
   A.cap = left->fs.kpCap; A.nRows = left->fs.lv[0].h; A.mbf = mbf; A.maxD = maxD;
   A.uRight = left->uRight.p; A.depth = left->depth.p; A.sad = left->sad.p; A.bestDist = nullptr;
+  A.hostU = hostU; A.hostD = hostD;
   int rc = stereo_launch(left, right, A, n);
   if (rc) return rc;
   left->haveStereo = true;
@@ -1481,13 +1482,11 @@ static void maybe_speculate_stereo(ivg_extractor* h) {
   const size_t k = L->fs.kpCap, bytes = 2 * (size_t)n * k * 4;
   if (ensure_spec_host(L, bytes) != IVG_OK) { cudaGetLastError(); return; }
   link->specValid = false;
-  if (stereo_enqueue(L, R, link->mbf, link->maxD, n) != IVG_OK) return;
+  // the matcher's last kernel writes uRight | depth straight into the pinned staging (zero copy): the result is on the host when the
+  // kernel is done, without a device-to-host copy on a second stream behind it
   float* stg = (float*)L->specHost;
-  bool ok;
-  if (n == L->maxBatch) ok = cudaMemcpyAsync(stg, L->udAll.p, 2 * (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) == cudaSuccess;   // one block
-  else ok = cudaMemcpyAsync(stg, L->uRight.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) == cudaSuccess &&
-            cudaMemcpyAsync(stg + (size_t)n * k, L->depth.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, L->copyOut) == cudaSuccess;
-  if (!ok || cudaEventRecord(L->evD2Hs, L->copyOut) != cudaSuccess) { cudaGetLastError(); return; }
+  if (stereo_enqueue(L, R, link->mbf, link->maxD, n, stg, stg + (size_t)n * k) != IVG_OK) return;
+  if (cudaEventRecord(L->evD2Hs, L->stream) != cudaSuccess) { cudaGetLastError(); return; }
   link->specGenL = link->genL; link->specGenR = link->genR; link->specN = n; link->specValid = true;
 }
 

@@ -38,6 +38,7 @@ struct StereoArgs {
   uint4* sorted;                                             // [nPairs][cap] right keypoints bucketed by row: (x bits, y bits, octave, iR)
   int* rowStart;                                             // [nPairs][nLevels * nRows + 1], bin = octave * nRows + row
   int nLevels;
+  float* hostU; float* hostD;                                // optional: pinned host copies of uRight / depth, written by the last kernel of the matcher
 };
 
 constexpr int TH_HIGH = 100, TH_LOW = 50;
@@ -409,25 +410,32 @@ __global__ void __launch_bounds__(1024) k_stereo_median(StereoArgs A) {      // 
   }
   __syncthreads();
   const int hb = sel[0];
-  if (hb < 0) return;                                  // no matches: nothing to filter
-  if (tid < 256) hist[tid] = 0;
-  __syncthreads();
-  for (int i = tid; i < N; i += nthr) {
-    const int s = sad[i];
-    if (s >= 0 && ((s >> 8) & 0xFF) == hb) atomicAdd(&hist[s & 0xFF], 1);
+  float thDist = 3.4e38f;                              // no matches: nothing to filter
+  if (hb >= 0) {                                       // block-uniform
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += nthr) {
+      const int s = sad[i];
+      if (s >= 0 && ((s >> 8) & 0xFF) == hb) atomicAdd(&hist[s & 0xFF], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int b, k;
+      median_pick_bin(hist, sel[1], lane, b, k);
+      if (lane == 0) sel[2] = (hb << 8) | b;
+    }
+    __syncthreads();
+    const float median = (float)sel[2];
+    thDist = __fmul_rn(1.5f * 1.4f, median);
   }
-  __syncthreads();
-  if (tid < 32) {
-    int b, k;
-    median_pick_bin(hist, sel[1], lane, b, k);
-    if (lane == 0) sel[2] = (hb << 8) | b;
-  }
-  __syncthreads();
-  const float median = (float)sel[2];
-  const float thDist = __fmul_rn(1.5f * 1.4f, median);
-  for (int i = tid; i < N; i += nthr) {
-    const int s = sad[i];
-    if (s >= 0 && !((float)s < thDist)) { A.uRight[pair * A.cap + i] = -1.f; A.depth[pair * A.cap + i] = -1.f; }
+  // outliers out; with host pointers every slot's final value also goes straight into the caller-visible pinned staging (one frame
+  // at a time: no device-to-host copy, no second stream to hand over to)
+  const int last = A.hostU ? A.cap : N;
+  for (int i = tid; i < last; i += nthr) {
+    const size_t o = pair * A.cap + i;
+    const bool out = i < N && sad[i] >= 0 && !((float)sad[i] < thDist);
+    if (out) { A.uRight[o] = -1.f; A.depth[o] = -1.f; }
+    if (A.hostU) { A.hostU[o] = out ? -1.f : A.uRight[o]; A.hostD[o] = out ? -1.f : A.depth[o]; }
   }
 }
 
