@@ -35,7 +35,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
       minThFAST(_minThFAST), benableIntrospection(enableIntrospection) {
   check(ivg_extractor_create(&mHandle, GetDevice(), nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST,
                              enableIntrospection ? 1 : 0), "ivg_extractor_create");
-  ivg_set_graph_mode(mHandle, 1);   // one frame at a time: replay the kernel sequence as one CUDA graph (0.37 vs 0.385 ms per stereo frame)
+  ivg_set_graph_mode(mHandle, 1);   // one frame at a time: replay the kernel sequence as one CUDA graph (0.186 vs 0.198 ms per stereo frame)
   mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
   mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
   ivg_get_scale_table(mHandle, 0, mvScaleFactor.data());
