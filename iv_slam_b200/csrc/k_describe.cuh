@@ -194,6 +194,15 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
   __syncthreads();
 
   // ---- rotated BRIEF + output record
+  // A lane's 16 pattern points are the same for every keypoint: they stay in registers for the whole phase, packed as two bf16
+  // per word (the coordinates are integers of magnitude <= 13: exact in bf16, and bf16 -> f32 is a shift / a mask), instead of
+  // 16 shared-memory loads of 8 bytes per keypoint (a third of the kernel's shared-memory wavefronts)
+  uint32_t pp[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float2 p = spat[k * 32 + lane];
+    pp[k] = (__float_as_uint(p.x) >> 16) | (__float_as_uint(p.y) & 0xFFFF0000u);
+  }
   int useCount[2] = {0, 0};
 #pragma unroll
   for (int q = 0; q < DK_SLOTS / 8; ++q) {
@@ -212,7 +221,8 @@ __global__ void __launch_bounds__(256) k_orient_describe(FrameSet fs, const __gr
     unsigned val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float2 p0 = spat[(2 * k) * 32 + lane], p1 = spat[(2 * k + 1) * 32 + lane];
+      const float2 p0 = make_float2(__uint_as_float(pp[2 * k] << 16), __uint_as_float(pp[2 * k] & 0xFFFF0000u));
+      const float2 p1 = make_float2(__uint_as_float(pp[2 * k + 1] << 16), __uint_as_float(pp[2 * k + 1] & 0xFFFF0000u));
       const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(p0.x, b), __fmul_rn(p0.y, a)));
       const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)));
       const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)));
